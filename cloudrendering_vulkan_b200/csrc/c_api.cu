@@ -1,0 +1,988 @@
+// c_api.cu -- the C ABI of include/crv_c_api.h: contexts, volumes, images and the two render techniques.
+//
+// Host-side mirror of RenderTechniqueSV / RenderTechniquePT (RenderTechniqueSV.cpp:4-113,
+// RenderTechniquePT.cpp:12-168): the Vulkan pipeline / descriptor-set plumbing becomes a table of bound
+// resources per image index, vkCmdDispatch becomes a kernel launch on the caller's stream.
+// All host arithmetic that feeds the kernels is fp32 in the shader's evaluation order (compiled with
+// -ffp-contract=off), because the kernels take these values as if the shader had computed them.
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "crv_internal.h"
+#include "pt_wavefront.h"
+#include "sv_sweep.h"
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void crv_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define CRV_ENTER(ctxp)                                                     \
+    do {                                                                    \
+        if (!(ctxp)) { crv_set_error("null handle"); return CRV_ERR_INVALID; } \
+        CRV_CUDA(cudaSetDevice((ctxp)->device));                            \
+    } while (0)
+
+#define CRV_TRY(expr)                  \
+    do {                               \
+        const int _rc = (expr);        \
+        if (_rc != CRV_OK) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// technique objects
+// ---------------------------------------------------------------------------------------------------
+struct crv_sv {
+    crv_ctx* ctx = nullptr;
+    const crv_shadow_volume_properties* ctor_props = nullptr;   // borrowed, read at record time (.cpp:110)
+    const crv_push_constants* pc = nullptr;
+    // pending writes (m_writeQueue) and committed bindings (the descriptor set)
+    const crv_cloud_properties* q_cloud = nullptr;
+    crv_volume* q_cloud_vol = nullptr;
+    const crv_shadow_volume_properties* q_sv = nullptr;
+    crv_volume* q_out = nullptr;
+    bool has_cloud = false, has_sv = false;
+    crv_cloud_properties cloud{};
+    crv_shadow_volume_properties sv{};
+    crv_volume* cloud_vol = nullptr;
+    crv_volume* out = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+struct PTBindings {
+    const crv_cloud_properties* q_cloud = nullptr;
+    crv_volume* q_cloud_vol = nullptr;
+    const crv_camera_properties* q_cam = nullptr;
+    const crv_parameters* q_params = nullptr;
+    const crv_shadow_volume_properties* q_sv = nullptr;
+    crv_volume* q_sv_vol = nullptr;
+    bool has_cloud = false, has_cam = false, has_params = false, has_sv = false;
+    crv_cloud_properties cloud{};
+    crv_camera_properties cam{};
+    crv_parameters params{};
+    crv_shadow_volume_properties sv{};
+    crv_volume* cloud_vol = nullptr;
+    crv_volume* sv_vol = nullptr;
+};
+
+struct crv_pt {
+    crv_ctx* ctx = nullptr;
+    const crv_camera_properties* ctor_cam = nullptr;            // borrowed, dispatch size (.cpp:141)
+    const crv_push_constants* pc = nullptr;                     // borrowed, read at record time (.cpp:132)
+    std::vector<crv_image*> images;
+    std::vector<PTBindings> sets;
+    crv_pt_extensions ext{};
+    // q-table cache
+    float* qtable = nullptr;
+    size_t qtable_elems = 0;
+    const crv_volume* q_for_vol = nullptr;
+    float q_for_max_ext = -1.0f;
+    uint64_t q_for_generation = 0;
+    // per-launch buffers
+    float4* samples = nullptr;
+    size_t samples_bytes = 0;
+    unsigned int* job_counter = nullptr;
+    unsigned long long* stats = nullptr;
+    uint32_t* dbg_steps = nullptr;
+    uint32_t* dbg_coll = nullptr;
+    size_t dbg_elems = 0;
+    bool dbg_enabled = false;
+    uint64_t launches = 0;
+    // device timing of the path-tracing kernel launches of the last render call (CUDA events on its stream)
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+    // tuning
+    int ctas_per_sm = 0;
+    int track_threshold = 12;
+    uint64_t sample_budget = 2ull << 30;
+};
+
+// volumes carry an upload generation so cached q-tables notice re-uploads
+static uint64_t g_generation = 1;
+struct VolGen { const crv_volume* v; uint64_t gen; };
+static std::vector<VolGen> g_gens;
+static uint64_t vol_generation(const crv_volume* v)
+{
+    for (auto& g : g_gens) if (g.v == v) return g.gen;
+    return 0;
+}
+static void vol_touch(const crv_volume* v)
+{
+    for (auto& g : g_gens) if (g.v == v) { g.gen = ++g_generation; return; }
+    g_gens.push_back({v, ++g_generation});
+}
+static void vol_forget(const crv_volume* v)
+{
+    for (size_t i = 0; i < g_gens.size(); ++i) if (g_gens[i].v == v) { g_gens.erase(g_gens.begin() + i); return; }
+}
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------
+// library / context
+// ---------------------------------------------------------------------------------------------------
+const char* crv_version(void) { return "crv-b200 0.1 (sm_100a)"; }
+const char* crv_last_error(void) { return g_err; }
+
+int crv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int crv_ctx_create(int device, crv_ctx** out)
+{
+    CRV_REQUIRE(out != nullptr, "crv_ctx_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        crv_set_error("no CUDA device available: libcrv_b200 has no CPU fallback");
+        return CRV_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { crv_set_error("device %d out of range (0..%d)", device, n - 1); return CRV_ERR_INVALID; }
+    cudaDeviceProp prop;
+    CRV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        crv_set_error("device %d is sm_%d%d; this library carries sm_100a code only (no fallback path)", device, prop.major, prop.minor);
+        return CRV_ERR_NO_DEVICE;
+    }
+    CRV_CUDA(cudaSetDevice(device));
+    crv_ctx* c = new (std::nothrow) crv_ctx();
+    if (!c) return CRV_ERR_OOM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    *out = c;
+    return CRV_OK;
+}
+
+int crv_ctx_destroy(crv_ctx* ctx)
+{
+    delete ctx;
+    return CRV_OK;
+}
+
+int crv_ctx_synchronize(crv_ctx* ctx, void* stream)
+{
+    CRV_ENTER(ctx);
+    CRV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return CRV_OK;
+}
+
+int crv_ctx_launch_count(crv_ctx* ctx, uint64_t* out)
+{
+    CRV_REQUIRE(ctx && out, "crv_ctx_launch_count: null argument");
+    *out = ctx->launches;
+    return CRV_OK;
+}
+
+int crv_ctx_sm_count(crv_ctx* ctx, int* out)
+{
+    CRV_REQUIRE(ctx && out, "crv_ctx_sm_count: null argument");
+    *out = ctx->sm_count;
+    return CRV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// volumes
+// ---------------------------------------------------------------------------------------------------
+int crv_volume_create(crv_ctx* ctx, uint32_t nx, uint32_t ny, uint32_t nz, int layout, crv_volume** out)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(out != nullptr, "crv_volume_create: out is null");
+    *out = nullptr;
+    CRV_REQUIRE(nx > 0 && ny > 0 && nz > 0, "crv_volume_create: empty volume");
+    CRV_REQUIRE(layout >= CRV_LAYOUT_LINEAR && layout <= CRV_LAYOUT_TEX3D, "crv_volume_create: unknown layout");
+    const uint64_t nbx = (nx + 7) / 8, nby = (ny + 7) / 8, nbz = (nz + 7) / 8;
+    CRV_REQUIRE(nbx * nby * nbz * 512ull < (1ull << 32), "crv_volume_create: more than 2^32 (padded) voxels is not supported");
+    crv_volume* v = new (std::nothrow) crv_volume();
+    if (!v) return CRV_ERR_OOM;
+    v->ctx = ctx;
+    v->layout = layout;
+    v->nx = nx; v->ny = ny; v->nz = nz;
+    v->nbx = (uint32_t)nbx; v->nby = (uint32_t)nby; v->nbz = (uint32_t)nbz;
+    cudaError_t e = cudaSuccess;
+    if (layout == CRV_LAYOUT_LINEAR) {
+        v->data_elems = (size_t)nx * ny * nz;
+        e = cudaMalloc(&v->data, v->data_elems * sizeof(float));
+    } else if (layout == CRV_LAYOUT_BRICK) {
+        v->data_elems = (size_t)(nbx * nby * nbz) * 512;
+        e = cudaMalloc(&v->data, v->data_elems * sizeof(float));
+    } else {
+        const cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+        e = cudaMalloc3DArray(&v->array, &desc, make_cudaExtent(nx, ny, nz), cudaArraySurfaceLoadStore);
+        if (e == cudaSuccess) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = v->array;
+            cudaTextureDesc td{};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;          // never the 9-bit hardware lerp
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            e = cudaCreateTextureObject(&v->tex, &rd, &td, nullptr);
+            if (e == cudaSuccess) e = cudaCreateSurfaceObject(&v->surf, &rd);
+        }
+    }
+    if (e != cudaSuccess) {
+        crv_set_error("crv_volume_create(%u,%u,%u,layout %d): %s", nx, ny, nz, layout, cudaGetErrorString(e));
+        crv_volume_destroy(v);
+        return e == cudaErrorMemoryAllocation ? CRV_ERR_OOM : CRV_ERR_CUDA;
+    }
+    vol_touch(v);
+    *out = v;
+    return CRV_OK;
+}
+
+int crv_volume_destroy(crv_volume* v)
+{
+    if (!v) return CRV_OK;
+    cudaSetDevice(v->ctx->device);
+    if (v->tex) cudaDestroyTextureObject(v->tex);
+    if (v->surf) cudaDestroySurfaceObject(v->surf);
+    if (v->array) cudaFreeArray(v->array);
+    if (v->data) cudaFree(v->data);
+    if (v->brick_max) cudaFree(v->brick_max);
+    if (v->brick_absmax) cudaFree(v->brick_absmax);
+    vol_forget(v);
+    delete v;
+    return CRV_OK;
+}
+
+int crv_volume_upload(crv_volume* v, const float* data, int is_device, void* stream)
+{
+    CRV_REQUIRE(v && data, "crv_volume_upload: null argument");
+    CRV_ENTER(v->ctx);
+    cudaStream_t s = as_stream(stream);
+    const size_t n = (size_t)v->nx * v->ny * v->nz;
+    const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (v->layout == CRV_LAYOUT_LINEAR) {
+        CRV_CUDA(cudaMemcpyAsync(v->data, data, n * sizeof(float), kind, s));
+    } else if (v->layout == CRV_LAYOUT_TEX3D) {
+        cudaMemcpy3DParms p{};
+        p.srcPtr = make_cudaPitchedPtr(const_cast<float*>(data), v->nx * sizeof(float), v->nx, v->ny);
+        p.dstArray = v->array;
+        p.extent = make_cudaExtent(v->nx, v->ny, v->nz);
+        p.kind = kind;
+        CRV_CUDA(cudaMemcpy3DAsync(&p, s));
+    } else {
+        if (is_device) {
+            CRV_TRY(crv_launch_retile(v->ctx, data, v, s));
+        } else {
+            float* tmp = nullptr;
+            CRV_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
+            CRV_CUDA(cudaMemcpyAsync(tmp, data, n * sizeof(float), cudaMemcpyHostToDevice, s));
+            const int rc = crv_launch_retile(v->ctx, tmp, v, s);
+            CRV_CUDA(cudaFreeAsync(tmp, s));
+            if (rc != CRV_OK) return rc;
+        }
+    }
+    v->brick_max_valid = false;
+    v->majorant_valid = false;
+    vol_touch(v);
+    return CRV_OK;
+}
+
+int crv_volume_download(crv_volume* v, float* host_out, void* stream)
+{
+    CRV_REQUIRE(v && host_out, "crv_volume_download: null argument");
+    CRV_ENTER(v->ctx);
+    cudaStream_t s = as_stream(stream);
+    const size_t n = (size_t)v->nx * v->ny * v->nz;
+    if (v->layout == CRV_LAYOUT_LINEAR) {
+        CRV_CUDA(cudaMemcpyAsync(host_out, v->data, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+        float* tmp = nullptr;
+        CRV_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
+        const int rc = crv_launch_untile(v->ctx, v, tmp, s);
+        if (rc == CRV_OK) CRV_CUDA(cudaMemcpyAsync(host_out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CRV_CUDA(cudaFreeAsync(tmp, s));
+        if (rc != CRV_OK) return rc;
+    }
+    CRV_CUDA(cudaStreamSynchronize(s));
+    return CRV_OK;
+}
+
+int crv_volume_dims(const crv_volume* v, uint32_t* nx, uint32_t* ny, uint32_t* nz, int* layout)
+{
+    CRV_REQUIRE(v != nullptr, "crv_volume_dims: null volume");
+    if (nx) *nx = v->nx;
+    if (ny) *ny = v->ny;
+    if (nz) *nz = v->nz;
+    if (layout) *layout = v->layout;
+    return CRV_OK;
+}
+
+int crv_volume_majorant(crv_volume* v, float* out, void* stream)
+{
+    CRV_REQUIRE(v && out, "crv_volume_majorant: null argument");
+    CRV_ENTER(v->ctx);
+    if (!v->majorant_valid) CRV_TRY(crv_launch_majorant(v->ctx, v, as_stream(stream)));
+    *out = v->majorant;
+    return CRV_OK;
+}
+
+int crv_volume_device_ptr(crv_volume* v, float** out)
+{
+    CRV_REQUIRE(v && out, "crv_volume_device_ptr: null argument");
+    *out = (v->layout == CRV_LAYOUT_LINEAR) ? v->data : nullptr;
+    return CRV_OK;
+}
+
+int crv_fbm_generate(crv_volume* v, uint32_t seed, void* stream)
+{
+    CRV_REQUIRE(v != nullptr, "crv_fbm_generate: null volume");
+    CRV_ENTER(v->ctx);
+    CRV_REQUIRE(v->nx == v->ny && v->ny == v->nz, "crv_fbm_generate: the synthetic scene is a cube");
+    cudaStream_t s = as_stream(stream);
+    if (v->layout == CRV_LAYOUT_LINEAR) {
+        CRV_TRY(crv_launch_fbm(v->ctx, v->data, v->nx, seed, s));
+        v->brick_max_valid = false;
+        v->majorant_valid = false;
+        vol_touch(v);
+        return CRV_OK;
+    }
+    float* tmp = nullptr;
+    const size_t n = (size_t)v->nx * v->ny * v->nz;
+    CRV_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
+    int rc = crv_launch_fbm(v->ctx, tmp, v->nx, seed, s);
+    if (rc == CRV_OK) rc = crv_volume_upload(v, tmp, 1, stream);
+    CRV_CUDA(cudaFreeAsync(tmp, s));
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// images
+// ---------------------------------------------------------------------------------------------------
+int crv_image_create(crv_ctx* ctx, uint32_t width, uint32_t height, crv_image** out)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(out != nullptr, "crv_image_create: out is null");
+    *out = nullptr;
+    CRV_REQUIRE(width > 0 && height > 0, "crv_image_create: empty image");
+    crv_image* img = new (std::nothrow) crv_image();
+    if (!img) return CRV_ERR_OOM;
+    img->ctx = ctx; img->width = width; img->height = height; img->owned = true;
+    const cudaError_t e = cudaMalloc(&img->rgba, (size_t)width * height * 4 * sizeof(float));
+    if (e != cudaSuccess) {
+        crv_set_error("crv_image_create(%u,%u): %s", width, height, cudaGetErrorString(e));
+        delete img;
+        return e == cudaErrorMemoryAllocation ? CRV_ERR_OOM : CRV_ERR_CUDA;
+    }
+    CRV_CUDA(cudaMemset(img->rgba, 0, (size_t)width * height * 4 * sizeof(float)));
+    *out = img;
+    return CRV_OK;
+}
+
+int crv_image_wrap(crv_ctx* ctx, float* device_rgba, uint32_t width, uint32_t height, crv_image** out)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(out && device_rgba && width > 0 && height > 0, "crv_image_wrap: bad argument");
+    CRV_REQUIRE((reinterpret_cast<uintptr_t>(device_rgba) & 15u) == 0, "crv_image_wrap: pointer must be 16-byte aligned");
+    crv_image* img = new (std::nothrow) crv_image();
+    if (!img) return CRV_ERR_OOM;
+    img->ctx = ctx; img->width = width; img->height = height; img->rgba = device_rgba; img->owned = false;
+    *out = img;
+    return CRV_OK;
+}
+
+int crv_image_destroy(crv_image* img)
+{
+    if (!img) return CRV_OK;
+    cudaSetDevice(img->ctx->device);
+    if (img->owned && img->rgba) cudaFree(img->rgba);
+    delete img;
+    return CRV_OK;
+}
+
+int crv_image_clear(crv_image* img, void* stream)
+{
+    CRV_REQUIRE(img != nullptr, "crv_image_clear: null image");
+    CRV_ENTER(img->ctx);
+    CRV_CUDA(cudaMemsetAsync(img->rgba, 0, (size_t)img->width * img->height * 16, as_stream(stream)));
+    return CRV_OK;
+}
+
+int crv_image_download(crv_image* img, float* host_rgba, void* stream)
+{
+    CRV_REQUIRE(img && host_rgba, "crv_image_download: null argument");
+    CRV_ENTER(img->ctx);
+    CRV_CUDA(cudaMemcpyAsync(host_rgba, img->rgba, (size_t)img->width * img->height * 16, cudaMemcpyDeviceToHost, as_stream(stream)));
+    CRV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return CRV_OK;
+}
+
+int crv_image_upload(crv_image* img, const float* host_rgba, void* stream)
+{
+    CRV_REQUIRE(img && host_rgba, "crv_image_upload: null argument");
+    CRV_ENTER(img->ctx);
+    CRV_CUDA(cudaMemcpyAsync(img->rgba, host_rgba, (size_t)img->width * img->height * 16, cudaMemcpyHostToDevice, as_stream(stream)));
+    return CRV_OK;
+}
+
+int crv_image_device_ptr(crv_image* img, float** out)
+{
+    CRV_REQUIRE(img && out, "crv_image_device_ptr: null argument");
+    *out = img->rgba;
+    return CRV_OK;
+}
+
+int crv_image_scale(crv_image* img, float scale, void* stream)
+{
+    CRV_REQUIRE(img != nullptr, "crv_image_scale: null image");
+    CRV_ENTER(img->ctx);
+    return crv_launch_scale(img->ctx, img->rgba, (size_t)img->width * img->height * 4, scale, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RenderTechniqueSV
+// ---------------------------------------------------------------------------------------------------
+int crv_sv_create(crv_ctx* ctx, const crv_shadow_volume_properties* props, const crv_push_constants* pc, crv_sv** out)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(out != nullptr, "crv_sv_create: out is null");
+    *out = nullptr;
+    CRV_REQUIRE(props != nullptr, "crv_sv_create: ShadowVolumeProperties pointer is null");
+    crv_sv* sv = new (std::nothrow) crv_sv();
+    if (!sv) return CRV_ERR_OOM;
+    sv->ctx = ctx;
+    sv->ctor_props = props;
+    sv->pc = pc;
+    CRV_CUDA(cudaEventCreate(&sv->ev0));
+    CRV_CUDA(cudaEventCreate(&sv->ev1));
+    *out = sv;
+    return CRV_OK;
+}
+
+int crv_sv_destroy(crv_sv* sv)
+{
+    if (!sv) return CRV_OK;
+    cudaSetDevice(sv->ctx->device);
+    if (sv->ev0) cudaEventDestroy(sv->ev0);
+    if (sv->ev1) cudaEventDestroy(sv->ev1);
+    delete sv;
+    return CRV_OK;
+}
+
+int crv_sv_set_frame_references(crv_sv* sv, crv_volume* shadow_image)
+{
+    CRV_REQUIRE(sv && shadow_image, "crv_sv_set_frame_references: null argument");
+    sv->out = shadow_image;         // SetFrameReferences writes binding 0 immediately (.cpp:49-65)
+    return CRV_OK;
+}
+int crv_sv_clear_frame_references(crv_sv* sv)
+{
+    CRV_REQUIRE(sv != nullptr, "crv_sv_clear_frame_references: null technique");
+    return CRV_OK;                  // the reference's ClearFrameReferences is empty (.cpp:67-69)
+}
+int crv_sv_queue_update_cloud_data(crv_sv* sv, const crv_cloud_properties* cloud)
+{
+    CRV_REQUIRE(sv && cloud, "crv_sv_queue_update_cloud_data: null argument");
+    sv->q_cloud = cloud;
+    return CRV_OK;
+}
+int crv_sv_queue_update_cloud_data_sampler(crv_sv* sv, crv_volume* cloud_image)
+{
+    CRV_REQUIRE(sv && cloud_image, "crv_sv_queue_update_cloud_data_sampler: null argument");
+    sv->q_cloud_vol = cloud_image;
+    return CRV_OK;
+}
+int crv_sv_queue_update_camera_properties(crv_sv* sv, const crv_camera_properties*) { CRV_REQUIRE(sv != nullptr, "null technique"); return CRV_OK; }
+int crv_sv_queue_update_parameters(crv_sv* sv, const crv_parameters*) { CRV_REQUIRE(sv != nullptr, "null technique"); return CRV_OK; }
+int crv_sv_queue_update_shadow_volume(crv_sv* sv, const crv_shadow_volume_properties* p)
+{
+    CRV_REQUIRE(sv && p, "crv_sv_queue_update_shadow_volume: null argument");
+    sv->q_sv = p;
+    return CRV_OK;
+}
+int crv_sv_queue_update_shadow_volume_sampler(crv_sv* sv, crv_volume* shadow_image)
+{
+    CRV_REQUIRE(sv && shadow_image, "crv_sv_queue_update_shadow_volume_sampler: null argument");
+    sv->q_out = shadow_image;       // rebinds the STORAGE image, binding 0 (.cpp:92-95)
+    return CRV_OK;
+}
+int crv_sv_update_descriptor_sets(crv_sv* sv)
+{
+    CRV_REQUIRE(sv != nullptr, "crv_sv_update_descriptor_sets: null technique");
+    if (sv->q_cloud) { sv->cloud = *sv->q_cloud; sv->has_cloud = true; sv->q_cloud = nullptr; }
+    if (sv->q_cloud_vol) { sv->cloud_vol = sv->q_cloud_vol; sv->q_cloud_vol = nullptr; }
+    if (sv->q_sv) { sv->sv = *sv->q_sv; sv->has_sv = true; sv->q_sv = nullptr; }
+    if (sv->q_out) { sv->out = sv->q_out; sv->q_out = nullptr; }
+    return CRV_OK;
+}
+
+int crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned /*image_index*/)
+{
+    CRV_REQUIRE(sv != nullptr, "crv_sv_record_draw_commands: null technique");
+    CRV_ENTER(sv->ctx);
+    CRV_REQUIRE(sv->has_cloud && sv->cloud_vol, "RenderTechniqueSV: cloud data / sampler not bound (bindings 2,3)");
+    CRV_REQUIRE(sv->has_sv, "RenderTechniqueSV: ShadowVolumeProperties not bound (binding 1)");
+    CRV_REQUIRE(sv->out != nullptr, "RenderTechniqueSV: no shadow-volume image (binding 0)");
+    const uint32_t n = sv->sv.voxelAxisCount;
+    CRV_REQUIRE(n > 0 && sv->ctor_props->voxelAxisCount == n, "RenderTechniqueSV: dispatch size and bound voxelAxisCount disagree");
+    CRV_REQUIRE(sv->out->nx == n && sv->out->ny == n && sv->out->nz == n, "RenderTechniqueSV: shadow image is not voxelAxisCount^3");
+    CRV_REQUIRE(sv->out != sv->cloud_vol, "RenderTechniqueSV: cloud and shadow images alias");
+
+    SVConst c{};
+    for (int i = 0; i < 3; ++i) {
+        c.b0[i] = sv->sv.bounds[0][i];
+        c.right[i] = sv->sv.right[i];
+        c.up[i] = sv->sv.up[i];
+        c.light[i] = sv->sv.lightDirection[i];
+        c.cb0[i] = sv->cloud.bounds[0][i];
+        c.cb1[i] = sv->cloud.bounds[1][i];
+        c.cext[i] = sv->cloud.bounds[1][i] - sv->cloud.bounds[0][i];
+    }
+    c.voxel_size = sv->sv.voxelSize;
+    c.n = (int)n;
+    c.density_scaling = sv->cloud.densityScaling;
+    c.base_scaling = sv->cloud.baseScaling;
+    c.cloud = sv->cloud_vol->view();
+    c.out = sv->out->view();
+    cudaStream_t s = as_stream(stream);
+    CRV_CUDA(cudaEventRecord(sv->ev0, s));
+    CRV_TRY(crv_launch_sv_sweep(sv->ctx, c, sv->cloud_vol->layout, sv->out->layout, s));
+    CRV_CUDA(cudaEventRecord(sv->ev1, s));
+    sv->timed = true;
+    sv->out->brick_max_valid = false;
+    sv->out->majorant_valid = false;
+    vol_touch(sv->out);
+    return CRV_OK;
+}
+
+int crv_sv_last_build_ms(crv_sv* sv, float* ms)
+{
+    CRV_REQUIRE(sv && ms, "crv_sv_last_build_ms: null argument");
+    CRV_ENTER(sv->ctx);
+    CRV_REQUIRE(sv->timed, "crv_sv_last_build_ms: nothing recorded yet");
+    CRV_CUDA(cudaEventSynchronize(sv->ev1));
+    CRV_CUDA(cudaEventElapsedTime(ms, sv->ev0, sv->ev1));
+    return CRV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RenderTechniquePT
+// ---------------------------------------------------------------------------------------------------
+int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push_constants* pc, crv_pt** out)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(out != nullptr, "crv_pt_create: out is null");
+    *out = nullptr;
+    CRV_REQUIRE(cam && pc, "crv_pt_create: CameraProperties / PushConstants pointer is null");
+    crv_pt* pt = new (std::nothrow) crv_pt();
+    if (!pt) return CRV_ERR_OOM;
+    pt->ctx = ctx;
+    pt->ctor_cam = cam;
+    pt->pc = pc;
+    pt->sets.resize(1);
+    CRV_CUDA(cudaMalloc(&pt->job_counter, sizeof(unsigned int)));
+    CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
+    CRV_CUDA(cudaMemset(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT));
+    *out = pt;
+    return CRV_OK;
+}
+
+int crv_pt_destroy(crv_pt* pt)
+{
+    if (!pt) return CRV_OK;
+    cudaSetDevice(pt->ctx->device);
+    if (pt->qtable) cudaFree(pt->qtable);
+    if (pt->samples) cudaFree(pt->samples);
+    if (pt->job_counter) cudaFree(pt->job_counter);
+    if (pt->stats) cudaFree(pt->stats);
+    if (pt->dbg_steps) cudaFree(pt->dbg_steps);
+    if (pt->dbg_coll) cudaFree(pt->dbg_coll);
+    for (cudaEvent_t e : pt->ev) cudaEventDestroy(e);
+    delete pt;
+    return CRV_OK;
+}
+
+int crv_pt_set_frame_references(crv_pt* pt, crv_image* const* result_images, unsigned count)
+{
+    CRV_REQUIRE(pt && result_images && count > 0, "crv_pt_set_frame_references: bad argument");
+    pt->images.assign(result_images, result_images + count);
+    if (pt->sets.size() < count) pt->sets.resize(count);
+    return CRV_OK;
+}
+int crv_pt_clear_frame_references(crv_pt* pt)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_clear_frame_references: null technique");
+    pt->images.clear();
+    return CRV_OK;
+}
+
+static PTBindings* pt_set(crv_pt* pt, unsigned idx)
+{
+    if (!pt) return nullptr;
+    if (idx >= pt->sets.size()) {
+        if (idx >= 64) return nullptr;
+        pt->sets.resize(idx + 1);
+    }
+    return &pt->sets[idx];
+}
+
+int crv_pt_queue_update_cloud_data(crv_pt* pt, const crv_cloud_properties* cloud, unsigned idx)
+{
+    PTBindings* b = pt_set(pt, idx);
+    CRV_REQUIRE(b && cloud, "crv_pt_queue_update_cloud_data: bad argument");
+    b->q_cloud = cloud;
+    return CRV_OK;
+}
+int crv_pt_queue_update_cloud_data_sampler(crv_pt* pt, crv_volume* vol, unsigned idx)
+{
+    PTBindings* b = pt_set(pt, idx);
+    CRV_REQUIRE(b && vol, "crv_pt_queue_update_cloud_data_sampler: bad argument");
+    b->q_cloud_vol = vol;
+    return CRV_OK;
+}
+int crv_pt_queue_update_camera_properties(crv_pt* pt, const crv_camera_properties* cam, unsigned idx)
+{
+    PTBindings* b = pt_set(pt, idx);
+    CRV_REQUIRE(b && cam, "crv_pt_queue_update_camera_properties: bad argument");
+    b->q_cam = cam;
+    return CRV_OK;
+}
+int crv_pt_queue_update_parameters(crv_pt* pt, const crv_parameters* params, unsigned idx)
+{
+    PTBindings* b = pt_set(pt, idx);
+    CRV_REQUIRE(b && params, "crv_pt_queue_update_parameters: bad argument");
+    b->q_params = params;
+    return CRV_OK;
+}
+int crv_pt_queue_update_shadow_volume(crv_pt* pt, const crv_shadow_volume_properties* p, unsigned idx)
+{
+    PTBindings* b = pt_set(pt, idx);
+    CRV_REQUIRE(b && p, "crv_pt_queue_update_shadow_volume: bad argument");
+    b->q_sv = p;
+    return CRV_OK;
+}
+int crv_pt_queue_update_shadow_volume_sampler(crv_pt* pt, crv_volume* vol, unsigned idx)
+{
+    PTBindings* b = pt_set(pt, idx);
+    CRV_REQUIRE(b && vol, "crv_pt_queue_update_shadow_volume_sampler: bad argument");
+    b->q_sv_vol = vol;
+    return CRV_OK;
+}
+
+int crv_pt_update_descriptor_sets(crv_pt* pt)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_update_descriptor_sets: null technique");
+    for (PTBindings& b : pt->sets) {
+        if (b.q_cloud) { b.cloud = *b.q_cloud; b.has_cloud = true; b.q_cloud = nullptr; }
+        if (b.q_cloud_vol) { b.cloud_vol = b.q_cloud_vol; b.q_cloud_vol = nullptr; }
+        if (b.q_cam) { b.cam = *b.q_cam; b.has_cam = true; b.q_cam = nullptr; }
+        if (b.q_params) { b.params = *b.q_params; b.has_params = true; b.q_params = nullptr; }
+        if (b.q_sv) { b.sv = *b.q_sv; b.has_sv = true; b.q_sv = nullptr; }
+        if (b.q_sv_vol) { b.sv_vol = b.q_sv_vol; b.q_sv_vol = nullptr; }
+    }
+    return CRV_OK;
+}
+
+int crv_pt_set_extensions(crv_pt* pt, const crv_pt_extensions* ext)
+{
+    CRV_REQUIRE(pt && ext, "crv_pt_set_extensions: null argument");
+    CRV_REQUIRE(ext->absorption >= 0.0f && ext->absorption <= 1.0f, "crv_pt_set_extensions: absorption must be in [0,1]");
+    pt->ext = *ext;
+    return CRV_OK;
+}
+
+int crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_set_tuning: null technique");
+    pt->ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 0;
+    if (track_threshold > 0) pt->track_threshold = track_threshold > 32 ? 32 : track_threshold;
+    if (sample_buffer_bytes > 0) pt->sample_budget = sample_buffer_bytes;
+    return CRV_OK;
+}
+
+// Build the kernel-parameter block from the committed bindings.  fp32, shader evaluation order.
+static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
+{
+    CRV_REQUIRE(idx < pt->sets.size() && idx < pt->images.size(), "RenderTechniquePT: image index out of range");
+    PTBindings& b = pt->sets[idx];
+    crv_image* img = pt->images[idx];
+    CRV_REQUIRE(img != nullptr, "RenderTechniquePT: no result image (binding 0)");
+    CRV_REQUIRE(b.has_cam, "RenderTechniquePT: CameraProperties not bound (binding 1)");
+    CRV_REQUIRE(b.has_cloud && b.cloud_vol, "RenderTechniquePT: cloud data / sampler not bound (bindings 2,3)");
+    CRV_REQUIRE(b.has_params, "RenderTechniquePT: Parameters not bound (binding 4)");
+    CRV_REQUIRE(b.has_sv && b.sv_vol, "RenderTechniquePT: shadow volume / sampler not bound (bindings 5,6)");
+    const int W = pt->ctor_cam->halfWidth * 2, H = pt->ctor_cam->halfHeight * 2;
+    CRV_REQUIRE(W > 0 && H > 0, "RenderTechniquePT: empty resolution");
+    CRV_REQUIRE((int)img->width == W && (int)img->height == H, "RenderTechniquePT: result image size differs from CameraProperties resolution");
+    const uint32_t nsv = b.sv.voxelAxisCount;
+    CRV_REQUIRE(b.sv_vol->nx == nsv && b.sv_vol->ny == nsv && b.sv_vol->nz == nsv, "RenderTechniquePT: shadow image is not voxelAxisCount^3");
+    CRV_REQUIRE(b.cloud.maxExtinction > 0.0f, "RenderTechniquePT: maxExtinction must be positive");
+
+    std::memset(&c, 0, sizeof(c));
+    for (int i = 0; i < 3; ++i) {
+        c.cam_pos[i] = b.cam.position[i];
+        c.fwd_near[i] = b.cam.forward[i] * b.cam.nearPlane;
+        c.right_psx[i] = b.cam.right[i] * b.cam.pixelSizeX;
+        c.up_psy[i] = b.cam.up[i] * b.cam.pixelSizeY;
+        c.cb0[i] = b.cloud.bounds[0][i];
+        c.cb1[i] = b.cloud.bounds[1][i];
+        c.cext[i] = b.cloud.bounds[1][i] - b.cloud.bounds[0][i];
+        c.light[i] = b.sv.lightDirection[i];
+        c.m0[i] = b.sv.basisChange[0][i];
+        c.m1[i] = b.sv.basisChange[1][i];
+        c.m2[i] = b.sv.basisChange[2][i];
+        c.m3[i] = b.sv.basisChange[3][i];
+    }
+    c.half_w = b.cam.halfWidth;
+    c.half_h = b.cam.halfHeight;
+    c.width = W;
+    c.height = H;
+    c.row_stride = 32u * (uint32_t)(W / 32 + 1);
+    c.max_ext = b.cloud.maxExtinction;
+    c.sigma = (b.cloud.maxExtinction * b.cloud.densityScaling) / b.cloud.baseScaling;
+    c.density_scaling = b.cloud.densityScaling;
+    c.light_intensity = 1.0f * b.params.lightIntensity;
+    c.two_g = 2.0f * b.params.phaseG;
+    c.one_minus_g = 1.0f - b.params.phaseG;
+    c.one_plus_g2 = b.params.phaseOnePlusG2;
+    c.one_minus_g2 = b.params.phaseOneMinusG2;
+    c.one_over_2g = b.params.phaseOneOver2G;
+    {
+        const float PI = 3.14159265359f;
+        const float INV_4Pi = 1.0f / (4.0f * PI);
+        c.inv4pi_omg2 = INV_4Pi * b.params.phaseOneMinusG2;
+    }
+    c.isotropic = b.params.isotropic != 0;
+    c.absorption = pt->ext.absorption;
+    float d[4];
+    for (int i = 0; i < 4; ++i) {
+        c.sb0[i] = b.sv.bounds[0][i];
+        d[i] = b.sv.bounds[1][i] - b.sv.bounds[0][i];
+    }
+    for (int i = 0; i < 3; ++i)
+        c.sden[i] = ((b.sv.basisChange[0][i] * d[0] + b.sv.basisChange[1][i] * d[1]) + b.sv.basisChange[2][i] * d[2]) + b.sv.basisChange[3][i] * d[3];
+
+    c.cloud = b.cloud_vol->view();
+    c.sv = b.sv_vol->view();
+    CRV_REQUIRE((uint32_t)c.cloud.nx == b.cloud.voxelCount[0] && (uint32_t)c.cloud.ny == b.cloud.voxelCount[1] && (uint32_t)c.cloud.nz == b.cloud.voxelCount[2],
+                "RenderTechniquePT: cloud image size differs from CloudProperties.voxelCount");
+
+    // q-table: rebuilt when the cloud image, its contents or maxExtinction changed
+    crv_volume* cv = b.cloud_vol;
+    const size_t nbricks = (size_t)cv->nbx * cv->nby * cv->nbz;
+    if (!cv->brick_max_valid) CRV_TRY(crv_launch_brick_max(pt->ctx, cv, s));
+    if (pt->q_for_vol != cv || pt->q_for_generation != vol_generation(cv) || pt->q_for_max_ext != c.max_ext || pt->qtable_elems != nbricks) {
+        if (pt->qtable_elems != nbricks) {
+            if (pt->qtable) CRV_CUDA(cudaFree(pt->qtable));
+            pt->qtable = nullptr;
+            CRV_CUDA(cudaMalloc(&pt->qtable, nbricks * sizeof(float)));
+            pt->qtable_elems = nbricks;
+        }
+        CRV_TRY(crv_launch_qtable(pt->ctx, cv->brick_absmax, pt->qtable, (long long)nbricks, c.max_ext, s));
+        pt->launches++;
+        pt->q_for_vol = cv;
+        pt->q_for_generation = vol_generation(cv);
+        pt->q_for_max_ext = c.max_ext;
+    }
+    c.qtable = pt->qtable;
+
+    c.npix = (uint32_t)W * (uint32_t)H;
+    c.image = reinterpret_cast<float4*>(img->rgba);
+    c.job_counter = pt->job_counter;
+    c.stats = pt->stats;
+    c.track_threshold = pt->track_threshold;
+    return CRV_OK;
+}
+
+// launch the tracker bracketed by a CUDA-event pair on the same stream
+static int pt_timed_launch(crv_pt* pt, const PTConst& c, const PTBindings& b, cudaStream_t s)
+{
+    while (pt->ev.size() < pt->ev_used + 2) {
+        cudaEvent_t e;
+        CRV_CUDA(cudaEventCreate(&e));
+        pt->ev.push_back(e);
+    }
+    CRV_CUDA(cudaEventRecord(pt->ev[pt->ev_used], s));
+    CRV_TRY(crv_launch_pt(pt->ctx, c, b.cloud_vol->layout, b.sv_vol->layout, pt->ctas_per_sm, s));
+    CRV_CUDA(cudaEventRecord(pt->ev[pt->ev_used + 1], s));
+    pt->ev_used += 2;
+    return CRV_OK;
+}
+
+static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t first_fc, int mode, cudaStream_t s, unsigned idx)
+{
+    CRV_REQUIRE(n > 0 && seeds, "RenderTechniquePT: no frames to render");
+    CRV_REQUIRE(mode == CRV_ACCUM_RUNNING_MEAN || mode == CRV_ACCUM_SUM, "RenderTechniquePT: unknown accumulation mode");
+    PTConst c;
+    CRV_TRY(pt_build_const(pt, idx, s, c));
+    PTBindings& b = pt->sets[idx];
+    c.accum_mode = mode;
+    pt->ev_used = 0;
+
+    if (n == 1) {
+        // single dispatch: fold straight into the image (PathTracer.comp:420-424)
+        if (pt->dbg_enabled) {
+            if (pt->dbg_elems != c.npix) {
+                if (pt->dbg_steps) CRV_CUDA(cudaFree(pt->dbg_steps));
+                if (pt->dbg_coll) CRV_CUDA(cudaFree(pt->dbg_coll));
+                pt->dbg_steps = pt->dbg_coll = nullptr;
+                CRV_CUDA(cudaMalloc(&pt->dbg_steps, sizeof(uint32_t) * c.npix));
+                CRV_CUDA(cudaMalloc(&pt->dbg_coll, sizeof(uint32_t) * c.npix));
+                pt->dbg_elems = c.npix;
+            }
+            c.dbg_steps = pt->dbg_steps;
+            c.dbg_collisions = pt->dbg_coll;
+        }
+        c.direct = 1;
+        c.nframes = 1;
+        c.seeds[0] = seeds[0];
+        c.first_frame_count = first_fc;
+        CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
+        CRV_TRY(pt_timed_launch(pt, c, b, s));
+        pt->launches++;
+        return CRV_OK;
+    }
+
+    // rounds of `per_round` frames through the sample buffer
+    const size_t frame_bytes = (size_t)c.npix * sizeof(float4);
+    uint64_t per_round = pt->sample_budget / frame_bytes;
+    if (per_round < 1) per_round = 1;
+    const uint64_t max_jobs_frames = 0xffffffffull / c.npix;       // job ids are 32-bit
+    if (per_round > max_jobs_frames) per_round = max_jobs_frames;
+    if (per_round > (uint64_t)PT_MAX_FRAMES_PER_LAUNCH) per_round = PT_MAX_FRAMES_PER_LAUNCH;   // seeds travel by value
+    if (per_round > n) per_round = n;
+    const size_t need = (size_t)per_round * frame_bytes;
+    if (pt->samples_bytes < need) {
+        if (pt->samples) CRV_CUDA(cudaFree(pt->samples));
+        pt->samples = nullptr;
+        pt->samples_bytes = 0;
+        CRV_CUDA(cudaMalloc(&pt->samples, need));
+        pt->samples_bytes = need;
+    }
+    c.direct = 0;
+    c.samples = pt->samples;
+    for (unsigned f0 = 0; f0 < n; f0 += (unsigned)per_round) {
+        const unsigned nf = (n - f0 < per_round) ? (n - f0) : (unsigned)per_round;
+        c.nframes = nf;
+        std::memcpy(c.seeds, seeds + f0, sizeof(int32_t) * nf);
+        c.first_frame_count = first_fc + f0;
+        CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
+        CRV_TRY(pt_timed_launch(pt, c, b, s));
+        FoldConst fc{};
+        fc.image = c.image;
+        fc.samples = pt->samples;
+        fc.npix = c.npix;
+        fc.nframes = nf;
+        fc.first_frame_count = first_fc + f0;
+        fc.accum_mode = mode;
+        CRV_TRY(crv_launch_fold(pt->ctx, fc, s));
+        pt->launches += 2;
+    }
+    return CRV_OK;
+}
+
+int crv_pt_record_draw_commands(crv_pt* pt, void* stream, unsigned image_index)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_record_draw_commands: null technique");
+    CRV_ENTER(pt->ctx);
+    const int32_t seed = pt->pc->seed;                 // vkCmdPushConstants snapshot (.cpp:132)
+    return pt_render(pt, &seed, 1, pt->pc->frameCount, CRV_ACCUM_RUNNING_MEAN, as_stream(stream), image_index);
+}
+
+int crv_pt_render_batch(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t first_frame_count, int accum_mode,
+                        void* stream, unsigned image_index)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_render_batch: null technique");
+    CRV_ENTER(pt->ctx);
+    return pt_render(pt, seeds, n, first_frame_count, accum_mode, as_stream(stream), image_index);
+}
+
+int crv_pt_get_stats(crv_pt* pt, crv_pt_stats* out, void* stream)
+{
+    CRV_REQUIRE(pt && out, "crv_pt_get_stats: null argument");
+    CRV_ENTER(pt->ctx);
+    unsigned long long h[PT_STAT_COUNT];
+    CRV_CUDA(cudaMemcpyAsync(h, pt->stats, sizeof(h), cudaMemcpyDeviceToHost, as_stream(stream)));
+    CRV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    out->paths = h[PT_STAT_PATHS];
+    out->tracking_steps = h[PT_STAT_STEPS];
+    out->collisions = h[PT_STAT_COLLISIONS];
+    out->density_fetches = h[PT_STAT_FETCHES];
+    out->kernel_launches = pt->launches;
+    return CRV_OK;
+}
+
+int crv_pt_last_render_ms(crv_pt* pt, float* tracker_ms, unsigned* tracker_launches)
+{
+    CRV_REQUIRE(pt && tracker_ms, "crv_pt_last_render_ms: null argument");
+    CRV_ENTER(pt->ctx);
+    CRV_REQUIRE(pt->ev_used >= 2, "crv_pt_last_render_ms: nothing rendered yet");
+    CRV_CUDA(cudaEventSynchronize(pt->ev[pt->ev_used - 1]));
+    float total = 0.0f;
+    for (size_t i = 0; i + 1 < pt->ev_used; i += 2) {
+        float ms = 0.0f;
+        CRV_CUDA(cudaEventElapsedTime(&ms, pt->ev[i], pt->ev[i + 1]));
+        total += ms;
+    }
+    *tracker_ms = total;
+    if (tracker_launches) *tracker_launches = (unsigned)(pt->ev_used / 2);
+    return CRV_OK;
+}
+
+int crv_pt_reset_stats(crv_pt* pt, void* stream)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_reset_stats: null technique");
+    CRV_ENTER(pt->ctx);
+    CRV_CUDA(cudaMemsetAsync(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT, as_stream(stream)));
+    return CRV_OK;
+}
+
+int crv_pt_set_debug_counters(crv_pt* pt, int enable)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_set_debug_counters: null technique");
+    pt->dbg_enabled = enable != 0;
+    return CRV_OK;
+}
+
+int crv_pt_download_debug_counters(crv_pt* pt, uint32_t* steps, uint32_t* collisions, void* stream)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_download_debug_counters: null technique");
+    CRV_ENTER(pt->ctx);
+    CRV_REQUIRE(pt->dbg_steps && pt->dbg_coll, "crv_pt_download_debug_counters: no single-frame render with counters enabled yet");
+    cudaStream_t s = as_stream(stream);
+    if (steps) CRV_CUDA(cudaMemcpyAsync(steps, pt->dbg_steps, sizeof(uint32_t) * pt->dbg_elems, cudaMemcpyDeviceToHost, s));
+    if (collisions) CRV_CUDA(cudaMemcpyAsync(collisions, pt->dbg_coll, sizeof(uint32_t) * pt->dbg_elems, cudaMemcpyDeviceToHost, s));
+    CRV_CUDA(cudaStreamSynchronize(s));
+    return CRV_OK;
+}
+
+int crv_pt_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t width, uint32_t height, uint32_t n_draws, uint32_t* host_out, void* stream)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(host_out && width > 0 && height > 0 && n_draws > 0, "crv_pt_rng_tap: bad argument");
+    cudaStream_t s = as_stream(stream);
+    uint32_t* d = nullptr;
+    const size_t bytes = (size_t)width * height * n_draws * sizeof(uint32_t);
+    CRV_CUDA(cudaMalloc(&d, bytes));
+    int rc = crv_launch_rng_tap(ctx, seed, width, height, n_draws, d, s);
+    if (rc == CRV_OK) {
+        const cudaError_t e = cudaMemcpyAsync(host_out, d, bytes, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { crv_set_error("crv_pt_rng_tap: %s", cudaGetErrorString(e)); rc = CRV_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

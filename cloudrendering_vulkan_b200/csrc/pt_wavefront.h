@@ -1,0 +1,72 @@
+// pt_wavefront.h -- kernel-parameter block of the path tracer (see pt_wavefront.cu)
+#pragma once
+#include "crv_internal.h"
+
+// stats slots (u64 each)
+enum { PT_STAT_PATHS = 0, PT_STAT_STEPS = 1, PT_STAT_COLLISIONS = 2, PT_STAT_FETCHES = 3, PT_STAT_COUNT = 4 };
+
+constexpr int PT_MAX_FRAMES_PER_LAUNCH = 256;
+
+struct PTConst {
+    // ---- CameraProperties (PathTracer.comp:43-55), products precomputed on the host in the shader's order ----
+    float cam_pos[3];
+    float fwd_near[3];       // forward * nearPlane
+    float right_psx[3];      // right * pixelSizeX
+    float up_psy[3];         // up * pixelSizeY
+    int half_w, half_h;
+    int width, height;       // 2*half (CameraProperties::GetWidth/GetHeight)
+    uint32_t row_stride;     // gl_WorkGroupSize.x * gl_NumWorkGroups.x = 32 * (W/32 + 1)  (:368, RenderTechniquePT.cpp:141)
+
+    // ---- CloudProperties (:58-66) ----
+    float cb0[3], cb1[3], cext[3];     // bounds[0], bounds[1], bounds[1]-bounds[0]
+    float max_ext;                     // maxExtinction
+    float sigma;                       // (maxExtinction * densityScaling) / baseScaling   (:338)
+    float density_scaling;
+
+    // ---- Parameters (:68-78) ----
+    float light_intensity;             // 1.0f * lightIntensity
+    float two_g;                       // 2.0f * phaseG
+    float one_minus_g;                 // 1.0f - phaseG
+    float one_plus_g2, one_minus_g2, one_over_2g;
+    float inv4pi_omg2;                 // INV_4Pi * phaseOneMinusG2   (:249)
+    int isotropic;
+    float absorption;                  // extension; 0 = reference semantics
+
+    // ---- ShadowVolumeProperties (:81-91) ----
+    float light[3];                    // lightDirection.xyz
+    float sb0[4];                      // bounds[0]
+    float m0[3], m1[3], m2[3], m3[3];  // basisChange columns (.xyz)
+    float sden[3];                     // (basisChange * (bounds[1] - bounds[0])).xyz
+
+    // ---- resources ----
+    VolView cloud, sv;
+    const float* qtable;               // per 8^3 brick: upper bound of ext/maxExtinction over the dilated brick
+
+    // ---- job description ----
+    uint32_t npix;                     // width*height
+    uint32_t nframes;                  // frames in this launch
+    int32_t seeds[PT_MAX_FRAMES_PER_LAUNCH];   // pushConstants.seed of every frame of this launch (by value: no staging copy)
+    uint32_t first_frame_count;        // pushConstants.frameCount of frame 0 of this launch
+    int accum_mode;                    // crv_accum_mode
+    int direct;                        // 1: accumulate straight into `image` (nframes == 1); 0: write `samples`
+    float4* image;                     // W*H rgba32f result image (binding 0)
+    float4* samples;                   // nframes * npix samples (direct == 0)
+    unsigned int* job_counter;         // next unclaimed job of this launch
+    unsigned long long* stats;         // PT_STAT_COUNT u64 (may be null)
+    uint32_t* dbg_steps;               // per-pixel counters (direct mode only, may be null)
+    uint32_t* dbg_collisions;
+    int track_threshold;               // service collisions/regeneration once fewer lanes than this are tracking
+};
+
+struct FoldConst {
+    float4* image;
+    const float4* samples;
+    uint32_t npix, nframes, first_frame_count;
+    int accum_mode;
+};
+
+int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
+int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
+int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
+int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);
+int crv_launch_scale(crv_ctx* ctx, float* data, size_t n, float scale, cudaStream_t s);

@@ -1,0 +1,165 @@
+// volume.cu -- layout conversion, majorant and brick-max kernels for 3D R32F volumes.
+//
+// Replaces the staging-buffer -> image copy of the reference (main.cpp:288-295, Utilities.cpp:94-111) and
+// Grid3D::GetMajorant (Grid3D.h:181-192, an O(n) CPU scan) with device passes.  All of these are pure
+// streaming kernels (HBM-bound, 4 B/voxel in, <= 4 B/voxel out); they run once per cloud upload.
+#include "crv_internal.h"
+
+VolView crv_volume::view() const
+{
+    VolView v;
+    v.data = data;
+    v.tex = tex;
+    v.surf = surf;
+    v.nx = (int)nx; v.ny = (int)ny; v.nz = (int)nz;
+    v.nbx = (int)nbx; v.nby = (int)nby; v.nbz = (int)nbz;
+    v.fnx = (float)nx; v.fny = (float)ny; v.fnz = (float)nz;
+    return v;
+}
+
+namespace {
+
+// linear x-fastest -> native layout of `dst` (BRICK or TEX3D surface).  One thread per voxel, x fastest, so
+// reads are coalesced; BRICK writes are 32 B runs (8 voxels), i.e. whole sectors.
+template <int LAYOUT>
+__global__ void retile_kernel(const float* __restrict__ src, VolView dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= dst.nx || j >= dst.ny) return;
+    const size_t lin = (size_t)i + (size_t)dst.nx * ((size_t)j + (size_t)dst.ny * k);
+    VolAcc<LAYOUT>::store(dst, i, j, k, src[lin]);
+}
+
+template <int LAYOUT>
+__global__ void untile_kernel(VolView src, float* __restrict__ dstp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= src.nx || j >= src.ny) return;
+    const size_t lin = (size_t)i + (size_t)src.nx * ((size_t)j + (size_t)src.ny * k);
+    dstp[lin] = VolAcc<LAYOUT>::load(src, i, j, k);
+}
+
+// Brick-max grid: for brick (bx,by,bz) the max over voxels [8b, 8b+8] per axis (clamped to the volume):
+// the brick's own 8 voxels plus ONE voxel of dilation on the upper side.  A trilinear footprint whose
+// clamped lower corner (i0c,j0c,k0c) lies in the brick touches only voxels of that set, so every texel
+// of the footprint is <= this max (used by the path tracer to reject tentative collisions without
+// fetching, see pt_wavefront.cu).  One warp per brick: 9x9x9 = 729 voxels, 23 per lane.
+// Two outputs per brick: max |v| (bounds the lerp and its rounding overshoot, feeds the q-table) and
+// max(v, 0) (feeds the majorant, same start value T() = 0 as Grid3D::GetMajorant).
+template <int LAYOUT>
+__global__ void brick_max_kernel(VolView v, float* __restrict__ out_abs, float* __restrict__ out_max)
+{
+    const int warps_per_block = blockDim.x >> 5;
+    const long long brick = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const long long nbricks = (long long)v.nbx * v.nby * v.nbz;
+    if (brick >= nbricks) return;
+    const int lane = threadIdx.x & 31;
+    const int bx = (int)(brick % v.nbx);
+    const int by = (int)((brick / v.nbx) % v.nby);
+    const int bz = (int)(brick / ((long long)v.nbx * v.nby));
+    float m = 0.0f, ma = 0.0f;
+    for (int t = lane; t < 729; t += 32) {
+        const int lx = t % 9, ly = (t / 9) % 9, lz = t / 81;
+        const int i = min(bx * 8 + lx, v.nx - 1), j = min(by * 8 + ly, v.ny - 1), k = min(bz * 8 + lz, v.nz - 1);
+        const float val = VolAcc<LAYOUT>::load(v, i, j, k);
+        m = fmaxf(m, val);
+        ma = fmaxf(ma, fabsf(val));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    }
+    if (lane == 0) { out_abs[brick] = ma; out_max[brick] = m; }
+}
+
+// majorant = max over the brick-max grid (each voxel belongs to at least one brick's set)
+__global__ void majorant_kernel(const float* __restrict__ brick_max, long long n, float* __restrict__ out)
+{
+    float m = 0.0f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, brick_max[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // non-negative floats order like their bit patterns: integer atomicMax is exact
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+}  // namespace
+
+int crv_launch_retile(crv_ctx* ctx, const float* linear_src, crv_volume* dst, cudaStream_t s)
+{
+    const dim3 block(64, 4, 1);
+    const dim3 grid((dst->nx + block.x - 1) / block.x, (dst->ny + block.y - 1) / block.y, dst->nz);
+    const VolView v = dst->view();
+    if (dst->layout == CRV_LAYOUT_BRICK)
+        retile_kernel<CRV_LAYOUT_BRICK><<<grid, block, 0, s>>>(linear_src, v);
+    else if (dst->layout == CRV_LAYOUT_TEX3D)
+        retile_kernel<CRV_LAYOUT_TEX3D><<<grid, block, 0, s>>>(linear_src, v);
+    else
+        retile_kernel<CRV_LAYOUT_LINEAR><<<grid, block, 0, s>>>(linear_src, v);
+    ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    return CRV_OK;
+}
+
+int crv_launch_untile(crv_ctx* ctx, const crv_volume* src, float* linear_dst, cudaStream_t s)
+{
+    const dim3 block(64, 4, 1);
+    const dim3 grid((src->nx + block.x - 1) / block.x, (src->ny + block.y - 1) / block.y, src->nz);
+    const VolView v = src->view();
+    if (src->layout == CRV_LAYOUT_BRICK)
+        untile_kernel<CRV_LAYOUT_BRICK><<<grid, block, 0, s>>>(v, linear_dst);
+    else if (src->layout == CRV_LAYOUT_TEX3D)
+        untile_kernel<CRV_LAYOUT_TEX3D><<<grid, block, 0, s>>>(v, linear_dst);
+    else
+        untile_kernel<CRV_LAYOUT_LINEAR><<<grid, block, 0, s>>>(v, linear_dst);
+    ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    return CRV_OK;
+}
+
+int crv_launch_brick_max(crv_ctx* ctx, crv_volume* vol, cudaStream_t s)
+{
+    const long long nbricks = (long long)vol->nbx * vol->nby * vol->nbz;
+    if (!vol->brick_max) CRV_CUDA(cudaMalloc(&vol->brick_max, sizeof(float) * nbricks));
+    if (!vol->brick_absmax) CRV_CUDA(cudaMalloc(&vol->brick_absmax, sizeof(float) * nbricks));
+    const int threads = 256, wpb = threads / 32;
+    const unsigned blocks = (unsigned)((nbricks + wpb - 1) / wpb);
+    const VolView v = vol->view();
+    if (vol->layout == CRV_LAYOUT_BRICK)
+        brick_max_kernel<CRV_LAYOUT_BRICK><<<blocks, threads, 0, s>>>(v, vol->brick_absmax, vol->brick_max);
+    else if (vol->layout == CRV_LAYOUT_TEX3D)
+        brick_max_kernel<CRV_LAYOUT_TEX3D><<<blocks, threads, 0, s>>>(v, vol->brick_absmax, vol->brick_max);
+    else
+        brick_max_kernel<CRV_LAYOUT_LINEAR><<<blocks, threads, 0, s>>>(v, vol->brick_absmax, vol->brick_max);
+    ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    vol->brick_max_valid = true;
+    return CRV_OK;
+}
+
+int crv_launch_majorant(crv_ctx* ctx, crv_volume* vol, cudaStream_t s)
+{
+    if (!vol->brick_max_valid) {
+        const int rc = crv_launch_brick_max(ctx, vol, s);
+        if (rc != CRV_OK) return rc;
+    }
+    float* d_out = nullptr;
+    CRV_CUDA(cudaMalloc(&d_out, sizeof(float)));
+    CRV_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float), s));
+    const long long n = (long long)vol->nbx * vol->nby * vol->nbz;
+    const int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    majorant_kernel<<<blocks, 256, 0, s>>>(vol->brick_max, n, d_out);
+    ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    CRV_CUDA(cudaMemcpyAsync(&vol->majorant, d_out, sizeof(float), cudaMemcpyDeviceToHost, s));
+    CRV_CUDA(cudaStreamSynchronize(s));
+    CRV_CUDA(cudaFree(d_out));
+    vol->majorant_valid = true;
+    return CRV_OK;
+}

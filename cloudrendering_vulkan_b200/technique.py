@@ -1,0 +1,359 @@
+"""Headless mirror of the reference's RenderTechnique interface over the C ABI.
+
+Reference: RenderTechnique.h:15-66 (abstract operator API), RenderTechniquePT.h:8-40 / .cpp:12-168,
+RenderTechniqueSV.h:7-39 / .cpp:4-113.  Same method names and argument meaning; Vulkan handle types are
+replaced by device-resource objects:
+
+    VulkanDevice             -> Context       (one CUDA device)
+    VulkanImage R32F 3D      -> Volume        (cloud density / shadow volume; LINEAR, BRICK or TEX3D storage)
+    VulkanImage RGBA32F 2D   -> Image         (progressive result image)
+    VkDescriptorBufferInfo   -> the host parameter struct itself (structs.py)
+    VkDescriptorImageInfo    -> Volume
+    VkCommandBuffer          -> a CUDA stream handle (int, 0 = default stream)
+
+Everything computes on the GPU through libcrv_b200.so; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib
+from .structs import (CameraProperties, CloudProperties, Parameters, PathTracerExtensions, PushConstants,
+                      ShadowVolumeProperties)
+
+
+def _stream(s) -> C.c_void_p:
+    return C.c_void_p(int(s) if s else 0)
+
+
+class Context:
+    """VulkanInstance + VulkanPhysicalDevice + VulkanDevice (main.cpp:774-793) -> one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self.handle = C.c_void_p()
+        check(lib.crv_ctx_create(int(device), C.byref(self.handle)))
+        self.device = device
+
+    def synchronize(self, stream=0):
+        check(lib.crv_ctx_synchronize(self.handle, _stream(stream)))
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        check(lib.crv_ctx_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    @property
+    def sm_count(self) -> int:
+        n = C.c_int()
+        check(lib.crv_ctx_sm_count(self.handle, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.handle:
+            lib.crv_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class Volume:
+    """R32_SFLOAT 3D image + LINEAR/CLAMP_TO_EDGE sampler (main.cpp:277-285, Initializers.cpp:408-418)."""
+
+    def __init__(self, ctx: Context, nx: int, ny: int, nz: int, layout="linear"):
+        self.ctx = ctx
+        self.shape = (int(nx), int(ny), int(nz))
+        self.layout = capi.LAYOUTS[layout] if isinstance(layout, str) else int(layout)
+        self.handle = C.c_void_p()
+        check(lib.crv_volume_create(ctx.handle, nx, ny, nz, self.layout, C.byref(self.handle)))
+
+    def upload(self, data: np.ndarray, stream=0):
+        """x-fastest host floats (what Grid3D::GetData holds; staging copy of main.cpp:288-295)."""
+        a = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+        if a.size != self.shape[0] * self.shape[1] * self.shape[2]:
+            raise ValueError("volume upload: size mismatch")
+        check(lib.crv_volume_upload(self.handle, a.ctypes.data_as(C.c_void_p), 0, _stream(stream)))
+        self.ctx.synchronize(stream)          # `a` may be a temporary
+
+    def upload_device(self, device_ptr: int, stream=0):
+        check(lib.crv_volume_upload(self.handle, C.c_void_p(int(device_ptr)), 1, _stream(stream)))
+
+    def download(self, stream=0) -> np.ndarray:
+        """x-fastest flat array, whatever the storage layout."""
+        out = np.empty(self.shape[0] * self.shape[1] * self.shape[2], dtype=np.float32)
+        check(lib.crv_volume_download(self.handle, out.ctypes.data_as(C.c_void_p), _stream(stream)))
+        return out
+
+    def majorant(self, stream=0) -> float:
+        m = C.c_float()
+        check(lib.crv_volume_majorant(self.handle, C.byref(m), _stream(stream)))
+        return m.value
+
+    def fbm_generate(self, seed: int = 1234, stream=0):
+        check(lib.crv_fbm_generate(self.handle, C.c_uint32(seed), _stream(stream)))
+
+    @property
+    def device_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib.crv_volume_device_ptr(self.handle, C.byref(p)))
+        return p.value or 0
+
+    def close(self):
+        if self.handle:
+            lib.crv_volume_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class Image:
+    """R32G32B32A32_SFLOAT 2D storage image (main.cpp:405-414), zero-cleared on creation."""
+
+    def __init__(self, ctx: Context, width: int, height: int, device_ptr: Optional[int] = None):
+        self.ctx = ctx
+        self.width, self.height = int(width), int(height)
+        self.handle = C.c_void_p()
+        if device_ptr is None:
+            check(lib.crv_image_create(ctx.handle, width, height, C.byref(self.handle)))
+        else:
+            check(lib.crv_image_wrap(ctx.handle, C.c_void_p(int(device_ptr)), width, height, C.byref(self.handle)))
+
+    def clear(self, stream=0):
+        check(lib.crv_image_clear(self.handle, _stream(stream)))
+
+    def download(self, stream=0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        check(lib.crv_image_download(self.handle, out.ctypes.data_as(C.c_void_p), _stream(stream)))
+        return out
+
+    def upload(self, rgba: np.ndarray, stream=0):
+        a = np.ascontiguousarray(rgba, dtype=np.float32)
+        if a.size != self.width * self.height * 4:
+            raise ValueError("image upload: size mismatch")
+        check(lib.crv_image_upload(self.handle, a.ctypes.data_as(C.c_void_p), _stream(stream)))
+        self.ctx.synchronize(stream)
+
+    def scale(self, factor: float, stream=0):
+        check(lib.crv_image_scale(self.handle, C.c_float(factor), _stream(stream)))
+
+    @property
+    def device_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib.crv_image_device_ptr(self.handle, C.byref(p)))
+        return p.value or 0
+
+    def close(self):
+        if self.handle:
+            lib.crv_image_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class RenderTechnique:
+    """Abstract operator interface (RenderTechnique.h:15-66).
+
+    QueueUpdate* record a pending descriptor write; UpdateDescriptorSets flushes them (RenderTechnique.cpp:14-18)
+    -- the parameter-struct bytes are snapshotted at that moment (VulkanBuffer::SetData + vkUpdateDescriptorSets).
+    """
+
+    def __init__(self, device: Context, pushConstants: PushConstants):
+        self.m_device = device
+        self.m_pushConstants = pushConstants
+
+    def GetRequiredSetCount(self) -> int:      # RenderTechniquePT.cpp:124-127 / RenderTechniqueSV.cpp:97-100
+        return 1
+
+    def UpdateDescriptorSets(self):
+        raise NotImplementedError
+
+    def SetFrameReferences(self, frameImages, frameImageViews=None, swapchain=None):
+        raise NotImplementedError
+
+    def ClearFrameReferences(self):
+        raise NotImplementedError
+
+    def QueueUpdateCloudData(self, cloudBufferInfo, imageIdx=0):
+        raise NotImplementedError
+
+    def QueueUpdateCloudDataSampler(self, cloudImageInfo, imageIdx=0):
+        raise NotImplementedError
+
+    def QueueUpdateCameraProperties(self, cameraBufferInfo, imageIdx=0):
+        raise NotImplementedError
+
+    def QueueUpdateParameters(self, parametersBufferInfo, imageIdx=0):
+        raise NotImplementedError
+
+    def QueueUpdateShadowVolume(self, shadowVolumeBufferInfo, imageIdx=0):
+        raise NotImplementedError
+
+    def QueueUpdateShadowVolumeSampler(self, shadowVolumeImageInfo, imageIdx=0):
+        raise NotImplementedError
+
+    def RecordDrawCommands(self, commandBuffer=0, imageIndex=0):
+        raise NotImplementedError
+
+
+class RenderTechniqueSV(RenderTechnique):
+    """Shadow-volume precompute (RenderTechniqueSV.h:7-39): bindings 0 SV storage image, 1 SV UBO, 2 cloud
+    sampler, 3 cloud UBO; dispatch (N/32+1)^2 groups of ShadowVolume.comp (RenderTechniqueSV.cpp:102-113)."""
+
+    def __init__(self, device: Context, shadowVolumeProperties: ShadowVolumeProperties, pushConstants: PushConstants):
+        super().__init__(device, pushConstants)
+        self.m_shadowVolumeProperties = shadowVolumeProperties
+        self._keep = []
+        self.handle = C.c_void_p()
+        check(lib.crv_sv_create(device.handle, C.byref(shadowVolumeProperties), C.byref(pushConstants), C.byref(self.handle)))
+
+    def SetFrameReferences(self, frameImages: Sequence[Volume], frameImageViews=None, swapchain=None):
+        self._keep.append(frameImages[0])
+        check(lib.crv_sv_set_frame_references(self.handle, frameImages[0].handle))
+
+    def ClearFrameReferences(self):
+        check(lib.crv_sv_clear_frame_references(self.handle))
+
+    def QueueUpdateCloudData(self, cloudBufferInfo: CloudProperties, imageIdx=0):
+        self._keep.append(cloudBufferInfo)
+        check(lib.crv_sv_queue_update_cloud_data(self.handle, C.byref(cloudBufferInfo)))
+
+    def QueueUpdateCloudDataSampler(self, cloudImageInfo: Volume, imageIdx=0):
+        self._keep.append(cloudImageInfo)
+        check(lib.crv_sv_queue_update_cloud_data_sampler(self.handle, cloudImageInfo.handle))
+
+    def QueueUpdateCameraProperties(self, cameraBufferInfo, imageIdx=0):      # no-op (.cpp:79-81)
+        check(lib.crv_sv_queue_update_camera_properties(self.handle, None))
+
+    def QueueUpdateParameters(self, parametersBufferInfo, imageIdx=0):        # no-op (.cpp:83-85)
+        check(lib.crv_sv_queue_update_parameters(self.handle, None))
+
+    def QueueUpdateShadowVolume(self, shadowVolumeBufferInfo: ShadowVolumeProperties, imageIdx=0):
+        self._keep.append(shadowVolumeBufferInfo)
+        check(lib.crv_sv_queue_update_shadow_volume(self.handle, C.byref(shadowVolumeBufferInfo)))
+
+    def QueueUpdateShadowVolumeSampler(self, shadowVolumeImageInfo: Volume, imageIdx=0):
+        self._keep.append(shadowVolumeImageInfo)
+        check(lib.crv_sv_queue_update_shadow_volume_sampler(self.handle, shadowVolumeImageInfo.handle))
+
+    def UpdateDescriptorSets(self):
+        check(lib.crv_sv_update_descriptor_sets(self.handle))
+        self._keep = self._keep[-8:]
+
+    def RecordDrawCommands(self, commandBuffer=0, imageIndex=0):
+        check(lib.crv_sv_record_draw_commands(self.handle, _stream(commandBuffer), int(imageIndex)))
+
+    def last_build_ms(self) -> float:
+        ms = C.c_float()
+        check(lib.crv_sv_last_build_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.handle:
+            lib.crv_sv_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class RenderTechniquePT(RenderTechnique):
+    """Path tracing (RenderTechniquePT.h:8-40): bindings 0 result image, 1 camera UBO, 2 cloud sampler, 3 cloud UBO,
+    4 parameters UBO, 5 SV sampler, 6 SV UBO (RenderTechniquePT.cpp:20-35); push constants seed/frameCount; one
+    RecordDrawCommands = one dispatch of PathTracer.comp = one progressive frame (.cpp:129-141; the swapchain blit
+    of .cpp:143-167 is dropped: headless)."""
+
+    def __init__(self, device: Context, swapchain, cameraProperties: CameraProperties, pushConstants: PushConstants):
+        super().__init__(device, pushConstants)
+        self.m_cameraProperties = cameraProperties
+        self.m_swapchain = swapchain            # unused: headless
+        self._keep = []
+        self._images = []
+        self.handle = C.c_void_p()
+        check(lib.crv_pt_create(device.handle, C.byref(cameraProperties), C.byref(pushConstants), C.byref(self.handle)))
+
+    def SetFrameReferences(self, frameImages: Sequence[Image], frameImageViews=None, swapchain=None):
+        self._images = list(frameImages)
+        arr = (C.c_void_p * len(frameImages))(*[im.handle for im in frameImages])
+        check(lib.crv_pt_set_frame_references(self.handle, arr, len(frameImages)))
+
+    def ClearFrameReferences(self):
+        self._images = []
+        check(lib.crv_pt_clear_frame_references(self.handle))
+
+    def QueueUpdateCloudData(self, cloudBufferInfo: CloudProperties, imageIdx=0):
+        self._keep.append(cloudBufferInfo)
+        check(lib.crv_pt_queue_update_cloud_data(self.handle, C.byref(cloudBufferInfo), int(imageIdx)))
+
+    def QueueUpdateCloudDataSampler(self, cloudImageInfo: Volume, imageIdx=0):
+        self._keep.append(cloudImageInfo)
+        check(lib.crv_pt_queue_update_cloud_data_sampler(self.handle, cloudImageInfo.handle, int(imageIdx)))
+
+    def QueueUpdateCameraProperties(self, cameraBufferInfo: CameraProperties, imageIdx=0):
+        self._keep.append(cameraBufferInfo)
+        check(lib.crv_pt_queue_update_camera_properties(self.handle, C.byref(cameraBufferInfo), int(imageIdx)))
+
+    def QueueUpdateParameters(self, parametersBufferInfo: Parameters, imageIdx=0):
+        self._keep.append(parametersBufferInfo)
+        check(lib.crv_pt_queue_update_parameters(self.handle, C.byref(parametersBufferInfo), int(imageIdx)))
+
+    def QueueUpdateShadowVolume(self, shadowVolumeBufferInfo: ShadowVolumeProperties, imageIdx=0):
+        self._keep.append(shadowVolumeBufferInfo)
+        check(lib.crv_pt_queue_update_shadow_volume(self.handle, C.byref(shadowVolumeBufferInfo), int(imageIdx)))
+
+    def QueueUpdateShadowVolumeSampler(self, shadowVolumeImageInfo: Volume, imageIdx=0):
+        self._keep.append(shadowVolumeImageInfo)
+        check(lib.crv_pt_queue_update_shadow_volume_sampler(self.handle, shadowVolumeImageInfo.handle, int(imageIdx)))
+
+    def UpdateDescriptorSets(self):
+        check(lib.crv_pt_update_descriptor_sets(self.handle))
+        self._keep = self._keep[-16:]
+
+    def RecordDrawCommands(self, commandBuffer=0, imageIndex=0):
+        check(lib.crv_pt_record_draw_commands(self.handle, _stream(commandBuffer), int(imageIndex)))
+
+    # ---- extensions beyond the reference interface -----------------------------------------------------
+    def SetExtensions(self, ext: PathTracerExtensions):
+        check(lib.crv_pt_set_extensions(self.handle, C.byref(ext)))
+
+    def RenderBatch(self, seeds, first_frame_count: int = 0, accum_mode: int = capi.ACCUM_RUNNING_MEAN,
+                    commandBuffer=0, imageIndex=0):
+        """len(seeds) progressive frames in one call (bit-identical to as many RecordDrawCommands)."""
+        s = np.ascontiguousarray(seeds, dtype=np.int32)
+        check(lib.crv_pt_render_batch(self.handle, s.ctypes.data_as(C.POINTER(C.c_int32)), s.size,
+                                      C.c_uint32(first_frame_count), int(accum_mode), _stream(commandBuffer), int(imageIndex)))
+
+    def GetStats(self, stream=0) -> capi.PTStats:
+        st = capi.PTStats()
+        check(lib.crv_pt_get_stats(self.handle, C.byref(st), _stream(stream)))
+        return st
+
+    def ResetStats(self, stream=0):
+        check(lib.crv_pt_reset_stats(self.handle, _stream(stream)))
+
+    def LastRenderMs(self):
+        """(device ms spent in the tracker kernel launches of the last render call, number of launches)"""
+        ms, n = C.c_float(), C.c_uint()
+        check(lib.crv_pt_last_render_ms(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def SetDebugCounters(self, enable: bool):
+        check(lib.crv_pt_set_debug_counters(self.handle, 1 if enable else 0))
+
+    def DownloadDebugCounters(self, stream=0):
+        w, h = self.m_cameraProperties.GetWidth(), self.m_cameraProperties.GetHeight()
+        steps = np.empty((h, w), dtype=np.uint32)
+        coll = np.empty((h, w), dtype=np.uint32)
+        check(lib.crv_pt_download_debug_counters(self.handle, steps.ctypes.data_as(C.c_void_p),
+                                                 coll.ctypes.data_as(C.c_void_p), _stream(stream)))
+        return steps, coll
+
+    def SetTuning(self, ctas_per_sm: int = 0, track_threshold: int = 0, sample_buffer_bytes: int = 0):
+        check(lib.crv_pt_set_tuning(self.handle, int(ctas_per_sm), int(track_threshold), C.c_uint64(sample_buffer_bytes)))
+
+    def close(self):
+        if self.handle:
+            lib.crv_pt_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def rng_tap(ctx: Context, seed: int, width: int, height: int, n_draws: int, stream=0) -> np.ndarray:
+    """Raw xorshift states of the first n_draws draws after warm-up for every pixel (bit-exact RNG tap)."""
+    out = np.empty((height, width, n_draws), dtype=np.uint32)
+    check(lib.crv_pt_rng_tap(ctx.handle, C.c_int32(seed), width, height, n_draws, out.ctypes.data_as(C.c_void_p), _stream(stream)))
+    return out

@@ -1,0 +1,278 @@
+/* crv_c_api.h -- C ABI of the B200-native PathTracer + ShadowVolume hot path.
+ *
+ * Drop-in boundary for the one hot path of jeanfilho/CloudRendering-Vulkan:
+ *   shaders/PathTracer.comp   (delta tracking + HG phase + progressive accumulation)
+ *   shaders/ShadowVolume.comp (sun-transmittance volume it samples)
+ * behind the reference's RenderTechnique interface (RenderTechnique.h:15-66,
+ * RenderTechniquePT.h:8-40, RenderTechniqueSV.h:7-39).  Vulkan handle types are replaced
+ * by opaque device-resource handles:
+ *   VkDescriptorBufferInfo  -> pointer to the host parameter struct (same bytes the UBO held)
+ *   VkDescriptorImageInfo   -> crv_volume* / crv_image*
+ *   VkCommandBuffer         -> cudaStream_t passed as void*
+ * Everything is plain pointers and sizes: no C++ types, no torch types.
+ *
+ * Conventions
+ *   - every function returns CRV_OK (0) or a negative crv_status; crv_last_error() gives a
+ *     thread-local message.  Nothing aborts or throws across this boundary (the reference's
+ *     ValidCheck abort()s, Validation.cpp:4-10).
+ *   - parameter structs are borrowed: crv_*_queue_update_* records the pointer,
+ *     crv_*_update_descriptor_sets snapshots the bytes (== VulkanBuffer::SetData +
+ *     vkUpdateDescriptorSets, VulkanBuffer.cpp:33-39, RenderTechnique.cpp:14-18).
+ *     PushConstants / CameraProperties(resolution) / ShadowVolumeProperties(voxelAxisCount)
+ *     given to the constructors are read at record time, as the reference does
+ *     (RenderTechniquePT.cpp:132,141; RenderTechniqueSV.cpp:110).
+ *   - all launches are asynchronous on the caller's stream; crv_ctx_synchronize waits.
+ *   - there is NO CPU fallback: every entry point that computes fails with
+ *     CRV_ERR_NO_DEVICE if no sm_100-class CUDA device is usable.
+ */
+#ifndef CRV_C_API_H
+#define CRV_C_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Parameter blocks: byte-for-byte the structs of UniformBuffers.h (sizes 24/68/60/28/152,
+ * which are also the std140 offsets the shaders declare, PathTracer.comp:43-99).
+ * ---------------------------------------------------------------------------------------- */
+
+/* UniformBuffers.h:6-13; the shader reads the first 20 bytes (PathTracer.comp:93-99). */
+typedef struct crv_push_constants {
+    double   time;
+    int32_t  seed;
+    uint32_t frameCount;
+    float    pmRadius;
+    uint32_t currentBuffer;
+} crv_push_constants;
+
+/* UniformBuffers.h:15-69 / PathTracer.comp:43-55 */
+typedef struct crv_camera_properties {
+    float   position[3];
+    int32_t halfWidth;
+    float   forward[3];
+    int32_t halfHeight;
+    float   right[3];
+    float   nearPlane;
+    float   up[3];
+    float   pixelSizeY;
+    float   pixelSizeX;
+} crv_camera_properties;
+
+/* UniformBuffers.h:71-78 / PathTracer.comp:58-66 */
+typedef struct crv_cloud_properties {
+    float    bounds[2][4];
+    uint32_t voxelCount[4];
+    float    maxExtinction;
+    float    baseScaling;
+    float    densityScaling;
+} crv_cloud_properties;
+
+/* UniformBuffers.h:80-112 / PathTracer.comp:68-78.  `isotropic` is a 1-byte C++ bool followed
+ * by 3 padding bytes; only the first byte is read by this library. */
+typedef struct crv_parameters {
+    uint32_t maxRayBounces;
+    float    lightIntensity;
+    float    phaseG;
+    float    phaseOnePlusG2;
+    float    phaseOneMinusG2;
+    float    phaseOneOver2G;
+    uint8_t  isotropic;
+    uint8_t  _pad[3];
+} crv_parameters;
+
+/* UniformBuffers.h:114-167 / PathTracer.comp:81-91.  basisChange is column-major (glm::mat4). */
+typedef struct crv_shadow_volume_properties {
+    float    bounds[2][4];
+    float    lightDirection[4];
+    float    right[4];
+    float    up[4];
+    float    basisChange[4][4];
+    uint32_t voxelAxisCount;
+    float    voxelSize;
+} crv_shadow_volume_properties;
+
+/* Extension block (NOT in the reference).  The reference path tracer has no absorption and no
+ * bounce cap (PathTracer.comp:396-416).  absorption > 0 adds one RNG draw per real collision,
+ * after the direct-light add and before scatterRay, and ends the path when xi <= absorption
+ * (idiom of PPM_PT.comp:445-446).  With absorption == 0 no extra draw is made and the RNG
+ * stream is exactly the reference's. */
+typedef struct crv_pt_extensions {
+    float    absorption;      /* 0 = reference semantics */
+    uint32_t reserved[3];
+} crv_pt_extensions;
+
+/* ------------------------------------------------------------------------------------------ */
+
+typedef enum crv_status {
+    CRV_OK               = 0,
+    CRV_ERR_INVALID      = -1,   /* bad argument / object state (e.g. nothing bound)          */
+    CRV_ERR_NO_DEVICE    = -2,   /* no usable CUDA device: there is no CPU fallback           */
+    CRV_ERR_CUDA         = -3,   /* a CUDA runtime call failed; see crv_last_error            */
+    CRV_ERR_OOM          = -4,
+    CRV_ERR_IO           = -5
+} crv_status;
+
+/* Storage layout of a 3D float volume in HBM (DESIGN.md section "data layout").  The logical
+ * array is always x-fastest nx*ny*nz as Grid3D stores it (Grid3D.h:112-116). */
+typedef enum crv_volume_layout {
+    CRV_LAYOUT_LINEAR = 0,   /* x + nx*(y + ny*z), global memory                               */
+    CRV_LAYOUT_BRICK  = 1,   /* 8x8x8 bricks (2 KiB), x-fastest inside and across bricks       */
+    CRV_LAYOUT_TEX3D  = 2    /* cudaArray 3D, point-sampled texture object (no HW filtering)   */
+} crv_volume_layout;
+
+typedef enum crv_accum_mode {
+    CRV_ACCUM_RUNNING_MEAN = 0,  /* out = (sample + old*frameCount)/(frameCount+1), PathTracer.comp:420-424 */
+    CRV_ACCUM_SUM          = 1   /* out = old + sample (multi-GPU spp split; divide after the reduce)       */
+} crv_accum_mode;
+
+typedef struct crv_ctx    crv_ctx;      /* one per GPU  (~ VulkanDevice)                       */
+typedef struct crv_volume crv_volume;   /* R32_SFLOAT 3D image + sampler (cloud or shadow)     */
+typedef struct crv_image  crv_image;    /* R32G32B32A32_SFLOAT 2D storage image (result)       */
+typedef struct crv_sv     crv_sv;       /* RenderTechniqueSV                                   */
+typedef struct crv_pt     crv_pt;       /* RenderTechniquePT                                   */
+
+/* per-render statistics, filled by crv_pt_get_stats (all counts are exact u64 sums) */
+typedef struct crv_pt_stats {
+    uint64_t paths;            /* path samples traced (pixels x frames, on-image only)         */
+    uint64_t tracking_steps;   /* tentative collisions (delta-tracking loop iterations)        */
+    uint64_t collisions;       /* real collisions                                              */
+    uint64_t density_fetches;  /* trilinear cloud fetches actually issued (rest proven empty)  */
+    uint64_t kernel_launches;  /* kernels launched by this technique since creation            */
+} crv_pt_stats;
+
+/* ---- library / context ------------------------------------------------------------------ */
+const char* crv_version(void);
+const char* crv_last_error(void);
+int  crv_device_count(void);
+/* VulkanInstance/PhysicalDevice/Device (main.cpp:774-793) -> one CUDA context on `device`. */
+int  crv_ctx_create(int device, crv_ctx** out);
+int  crv_ctx_destroy(crv_ctx* ctx);
+int  crv_ctx_synchronize(crv_ctx* ctx, void* stream);                 /* vkQueueWaitIdle        */
+int  crv_ctx_launch_count(crv_ctx* ctx, uint64_t* out);               /* kernels launched so far */
+int  crv_ctx_sm_count(crv_ctx* ctx, int* out);
+
+/* ---- volumes: VulkanImage(R32_SFLOAT, 3D) + VulkanSampler (main.cpp:277-285,802-804) ------ */
+int  crv_volume_create(crv_ctx* ctx, uint32_t nx, uint32_t ny, uint32_t nz, int layout, crv_volume** out);
+int  crv_volume_destroy(crv_volume* vol);
+/* staging buffer -> image copy (main.cpp:288-295): x-fastest host floats; is_device!=0 means
+ * `data` already is a device pointer (x-fastest linear). */
+int  crv_volume_upload(crv_volume* vol, const float* data, int is_device, void* stream);
+/* read back as x-fastest linear floats regardless of layout */
+int  crv_volume_download(crv_volume* vol, float* host_out, void* stream);
+int  crv_volume_dims(const crv_volume* vol, uint32_t* nx, uint32_t* ny, uint32_t* nz, int* layout);
+/* Grid3D<float>::GetMajorant (Grid3D.h:181-192) as a device reduction */
+int  crv_volume_majorant(crv_volume* vol, float* out, void* stream);
+/* raw device pointer of a LINEAR volume (NULL otherwise); for zero-copy interop */
+int  crv_volume_device_ptr(crv_volume* vol, float** out);
+
+/* ---- result image: VulkanImage(R32G32B32A32_SFLOAT, 2D, STORAGE) (main.cpp:405-414) ------ */
+int  crv_image_create(crv_ctx* ctx, uint32_t width, uint32_t height, crv_image** out);
+/* wrap caller-owned device memory (width*height*4 floats), e.g. a torch tensor's data_ptr */
+int  crv_image_wrap(crv_ctx* ctx, float* device_rgba, uint32_t width, uint32_t height, crv_image** out);
+int  crv_image_destroy(crv_image* img);
+int  crv_image_clear(crv_image* img, void* stream);
+int  crv_image_download(crv_image* img, float* host_rgba, void* stream);
+int  crv_image_upload(crv_image* img, const float* host_rgba, void* stream);
+int  crv_image_device_ptr(crv_image* img, float** out);
+/* out = in * scale (the divide-by-spp epilogue after the multi-GPU sum reduce) */
+int  crv_image_scale(crv_image* img, float scale, void* stream);
+
+/* ---- RenderTechniqueSV (RenderTechniqueSV.h:7-39, .cpp:4-113) ----------------------------- */
+int  crv_sv_create(crv_ctx* ctx, const crv_shadow_volume_properties* props, const crv_push_constants* pc, crv_sv** out);
+int  crv_sv_destroy(crv_sv* sv);
+int  crv_sv_set_frame_references(crv_sv* sv, crv_volume* shadow_image);                     /* binding 0 */
+int  crv_sv_clear_frame_references(crv_sv* sv);
+int  crv_sv_queue_update_cloud_data(crv_sv* sv, const crv_cloud_properties* cloud);          /* binding 3 */
+int  crv_sv_queue_update_cloud_data_sampler(crv_sv* sv, crv_volume* cloud_image);            /* binding 2 */
+int  crv_sv_queue_update_camera_properties(crv_sv* sv, const crv_camera_properties* cam);    /* no-op, .cpp:79-81 */
+int  crv_sv_queue_update_parameters(crv_sv* sv, const crv_parameters* params);               /* no-op, .cpp:83-85 */
+int  crv_sv_queue_update_shadow_volume(crv_sv* sv, const crv_shadow_volume_properties* p);   /* binding 1 */
+int  crv_sv_queue_update_shadow_volume_sampler(crv_sv* sv, crv_volume* shadow_image);        /* binding 0, .cpp:92-95 */
+int  crv_sv_update_descriptor_sets(crv_sv* sv);
+/* vkCmdDispatch(N/32+1, N/32+1, 1) of ShadowVolume.comp (RenderTechniqueSV.cpp:102-113) */
+int  crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned image_index);
+/* device time of the last recorded build in ms (CUDA events on `stream`); syncs the stream */
+int  crv_sv_last_build_ms(crv_sv* sv, float* ms);
+
+/* ---- RenderTechniquePT (RenderTechniquePT.h:8-40, .cpp:12-168) ---------------------------- */
+int  crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push_constants* pc, crv_pt** out);
+int  crv_pt_destroy(crv_pt* pt);
+int  crv_pt_set_frame_references(crv_pt* pt, crv_image* const* result_images, unsigned count); /* binding 0 */
+int  crv_pt_clear_frame_references(crv_pt* pt);
+int  crv_pt_queue_update_cloud_data(crv_pt* pt, const crv_cloud_properties* cloud, unsigned image_index);          /* binding 3 */
+int  crv_pt_queue_update_cloud_data_sampler(crv_pt* pt, crv_volume* cloud_image, unsigned image_index);            /* binding 2 */
+int  crv_pt_queue_update_camera_properties(crv_pt* pt, const crv_camera_properties* cam, unsigned image_index);    /* binding 1 */
+int  crv_pt_queue_update_parameters(crv_pt* pt, const crv_parameters* params, unsigned image_index);               /* binding 4 */
+int  crv_pt_queue_update_shadow_volume(crv_pt* pt, const crv_shadow_volume_properties* p, unsigned image_index);   /* binding 6 */
+int  crv_pt_queue_update_shadow_volume_sampler(crv_pt* pt, crv_volume* shadow_image, unsigned image_index);        /* binding 5 */
+int  crv_pt_update_descriptor_sets(crv_pt* pt);
+/* One progressive frame with the exact shader semantics: seed and frameCount are read from the
+ * PushConstants given at creation (vkCmdPushConstants, RenderTechniquePT.cpp:132) and the result
+ * image `image_index` is updated in place with the running mean (PathTracer.comp:420-424). */
+int  crv_pt_record_draw_commands(crv_pt* pt, void* stream, unsigned image_index);
+
+/* ---- extensions beyond the reference interface -------------------------------------------- */
+int  crv_pt_set_extensions(crv_pt* pt, const crv_pt_extensions* ext);
+/* n progressive frames in one call: identical, bit for bit, to n crv_pt_record_draw_commands
+ * calls with seed = seeds[i] and frameCount = first_frame_count + i (CRV_ACCUM_RUNNING_MEAN),
+ * or a plain fp32 sum of the n samples added to the image in frame order (CRV_ACCUM_SUM).
+ * This is the persistent-thread wavefront fast path.  PushConstants are not modified. */
+int  crv_pt_render_batch(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t first_frame_count,
+                         int accum_mode, void* stream, unsigned image_index);
+/* enable per-path counters (steps/collisions/fetches); costs a few atomics per CTA */
+int  crv_pt_get_stats(crv_pt* pt, crv_pt_stats* out, void* stream);
+int  crv_pt_reset_stats(crv_pt* pt, void* stream);
+/* Device time (CUDA events on the render's stream) spent in the path-tracing kernel launches of the last
+ * crv_pt_record_draw_commands / crv_pt_render_batch call, and how many launches that was; syncs on them. */
+int  crv_pt_last_render_ms(crv_pt* pt, float* tracker_ms, unsigned* tracker_launches);
+/* Debug/parity taps for ONE frame: per-pixel tracking steps and collisions (u32 each, W*H,
+ * host pointers, may be NULL) of the last crv_pt_record_draw_commands. */
+int  crv_pt_set_debug_counters(crv_pt* pt, int enable);
+int  crv_pt_download_debug_counters(crv_pt* pt, uint32_t* steps, uint32_t* collisions, void* stream);
+/* First `n_draws` uniform draws (raw u32 states after warm-up) for every pixel of a WxH image
+ * with dispatch stride 32*(W/32+1) (PathTracer.comp:220-241,368): bit-exact RNG tap. */
+int  crv_pt_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t width, uint32_t height, uint32_t n_draws,
+                    uint32_t* host_out, void* stream);
+/* tuning knobs (0 = library default): CTAs per SM, min tracking lanes before servicing, max
+ * bytes of the per-round sample buffer */
+int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes);
+
+/* ---- host-side helpers with the reference's setter semantics (UniformBuffers.h) ------------ */
+void crv_push_constants_init(crv_push_constants* p);                                   /* :6-13   */
+void crv_camera_init(crv_camera_properties* c);                                        /* :15-27  */
+void crv_camera_set_resolution(crv_camera_properties* c, int width, int height);       /* :46-50  */
+void crv_camera_set_rotation(crv_camera_properties* c, float* rotation_xy);            /* :29-35  */
+void crv_camera_set_fov(crv_camera_properties* c, float* fov);                         /* :52-58  */
+void crv_cloud_init(crv_cloud_properties* c);                                          /* :71-78  */
+/* SetCloudProperties (main.cpp:144-163): bounds, voxelCount, maxExtinction = max(majorant, .01) */
+void crv_cloud_set_from_grid(crv_cloud_properties* c, const uint32_t counts[3], const double voxel_size[3], float majorant);
+void crv_parameters_init(crv_parameters* p);                                           /* :80-91  */
+void crv_parameters_set_phase_g(crv_parameters* p, float g);                           /* :93-106 */
+void crv_shadow_init(crv_shadow_volume_properties* s);                                 /* :114-127*/
+void crv_shadow_set_light_direction(crv_shadow_volume_properties* s, const float dir[3]);            /* :131-143 */
+void crv_shadow_set_origin(crv_shadow_volume_properties* s, const float lower[3], const float upper[3]); /* :145-151 */
+void crv_orthonormal_basis(const float n[3], float right[3], float up[3]);             /* Utilities.cpp:7-16 */
+/* MSVC rand() sequence after srand(seed0) (main.cpp:722,949): frame seeds */
+void crv_msvc_rand_sequence(uint32_t seed0, unsigned n, int32_t* out);
+
+/* ---- Grid3D .xyz files (Grid3D.h:45-90,167-178; GridData.h) -------------------------------- */
+/* Load: 3 x u32 counts, 3 x f64 voxel sizes, floats z-fastest -> x-fastest out.  Two-call
+ * protocol: data == NULL returns the header only.  Missing file -> CRV_ERR_IO (Load returns nullptr). */
+int  crv_grid_load(const char* path, uint32_t counts[3], double voxel_size[3], float* data, size_t capacity);
+/* Save writes the raw x-fastest array after the header, exactly as Grid3D::Save does (:167-178). */
+int  crv_grid_save(const char* path, const uint32_t counts[3], const double voxel_size[3], const float* data);
+/* GridData::save convention (GridData.h:12-25): z-fastest on disk, what Load expects. */
+int  crv_grid_save_zfastest(const char* path, const uint32_t counts[3], const double voxel_size[3], const float* data_xfastest);
+
+/* ---- synthetic scene (bench/test scaffolding; SURVEY section 8d generator) ------------------ */
+/* Fill a LINEAR/BRICK/TEX3D volume with the frozen fBm cloud of side n (seed 1234 by default). */
+int  crv_fbm_generate(crv_volume* vol, uint32_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRV_C_API_H */

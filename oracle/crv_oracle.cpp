@@ -1,0 +1,625 @@
+// oracle/crv_oracle.cpp -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY (see crv_oracle.h for the contract).
+//
+// Function-for-function scalar fp32 restatement of the reference shaders; every function cites the shader
+// lines it follows.  Build: g++ -O2 -ffp-contract=off -fno-fast-math -fopenmp (oracle/Makefile).
+// PARITY STATUS: parity unpinned by the reference (no SPIR-V, no golden vectors, no Vulkan in this image);
+// the shader text is the specification.  Driver-defined behaviour is fixed as documented in crv_oracle.h.
+#include "crv_oracle.h"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct vec3 { float x, y, z; };
+struct vec4 { float x, y, z, w; };
+
+inline vec3 operator+(vec3 a, vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline vec3 operator-(vec3 a, vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline vec3 operator*(vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline vec3 operator*(float s, vec3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline vec3 operator-(vec3 a) { return {-a.x, -a.y, -a.z}; }
+inline vec4 operator+(vec4 a, vec4 b) { return {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+inline vec4 operator-(vec4 a, vec4 b) { return {a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+inline vec4 operator*(vec4 a, float s) { return {a.x * s, a.y * s, a.z * s, a.w * s}; }
+inline vec4 operator*(float s, vec4 a) { return {s * a.x, s * a.y, s * a.z, s * a.w}; }
+inline vec4 operator/(vec4 a, vec4 b) { return {a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w}; }
+// dot products are summed left to right
+inline float dot(vec3 a, vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline float length(vec3 a) { return std::sqrt(dot(a, a)); }
+
+// ---- uniform blocks, read at the std140 offsets the shaders declare -------------------------------------
+struct Camera {          // PathTracer.comp:43-55
+    vec3 position; int halfWidth; vec3 forward; int halfHeight; vec3 right; float nearPlane;
+    vec3 up; float pixelSizeY; float pixelSizeX;
+};
+struct Cloud {           // PathTracer.comp:58-66
+    vec4 bounds[2]; uint32_t voxelCount[4]; float maxExtinction, baseScaling, densityScaling;
+};
+struct Params {          // PathTracer.comp:68-78
+    uint32_t maxRayBounces; float lightIntensity, phaseG, phaseOnePlusG2, phaseOneMinusG2, phaseOneOver2G;
+    bool isotropic;
+};
+struct Shadow {          // PathTracer.comp:81-91
+    vec4 bounds[2]; vec4 lightDirection, right, up; vec4 basisChange[4]; uint32_t voxelAxisCount; float voxelSize;
+};
+struct Push {            // PathTracer.comp:93-99
+    double time; int32_t seed; uint32_t frameCount; float pmRadius;
+};
+
+template <typename T> inline T rd(const void* base, size_t off)
+{
+    T v;
+    std::memcpy(&v, static_cast<const char*>(base) + off, sizeof(T));
+    return v;
+}
+inline vec3 rd3(const void* b, size_t off) { return {rd<float>(b, off), rd<float>(b, off + 4), rd<float>(b, off + 8)}; }
+inline vec4 rd4(const void* b, size_t off) { return {rd<float>(b, off), rd<float>(b, off + 4), rd<float>(b, off + 8), rd<float>(b, off + 12)}; }
+
+Camera load_camera(const void* p)
+{
+    Camera c;
+    c.position = rd3(p, 0);   c.halfWidth = rd<int32_t>(p, 12);
+    c.forward = rd3(p, 16);   c.halfHeight = rd<int32_t>(p, 28);
+    c.right = rd3(p, 32);     c.nearPlane = rd<float>(p, 44);
+    c.up = rd3(p, 48);        c.pixelSizeY = rd<float>(p, 60);
+    c.pixelSizeX = rd<float>(p, 64);
+    return c;
+}
+Cloud load_cloud(const void* p)
+{
+    Cloud c;
+    c.bounds[0] = rd4(p, 0); c.bounds[1] = rd4(p, 16);
+    for (int i = 0; i < 4; ++i) c.voxelCount[i] = rd<uint32_t>(p, 32 + 4 * i);
+    c.maxExtinction = rd<float>(p, 48); c.baseScaling = rd<float>(p, 52); c.densityScaling = rd<float>(p, 56);
+    return c;
+}
+Params load_params(const void* p)
+{
+    Params q;
+    q.maxRayBounces = rd<uint32_t>(p, 0); q.lightIntensity = rd<float>(p, 4); q.phaseG = rd<float>(p, 8);
+    q.phaseOnePlusG2 = rd<float>(p, 12); q.phaseOneMinusG2 = rd<float>(p, 16); q.phaseOneOver2G = rd<float>(p, 20);
+    // C++ bool = 1 byte + 3 uninitialised padding bytes on the host side (UniformBuffers.h:90): read the byte only
+    q.isotropic = rd<uint8_t>(p, 24) != 0;
+    return q;
+}
+Shadow load_shadow(const void* p)
+{
+    Shadow s;
+    s.bounds[0] = rd4(p, 0); s.bounds[1] = rd4(p, 16);
+    s.lightDirection = rd4(p, 32); s.right = rd4(p, 48); s.up = rd4(p, 64);
+    for (int i = 0; i < 4; ++i) s.basisChange[i] = rd4(p, 80 + 16 * i);
+    s.voxelAxisCount = rd<uint32_t>(p, 144); s.voxelSize = rd<float>(p, 148);
+    return s;
+}
+Push load_push(const void* p)
+{
+    Push q;
+    q.time = rd<double>(p, 0); q.seed = rd<int32_t>(p, 8); q.frameCount = rd<uint32_t>(p, 12); q.pmRadius = rd<float>(p, 16);
+    return q;
+}
+
+// ---- constants (PathTracer.comp:17-37) ------------------------------------------------------------------
+const float PI = 3.14159265359f;
+const float INV_4Pi = 1.0f / (4.0f * PI);
+const vec4 BG_COLORS[5] = {{0.00f, 0.0f, 0.02f, 1.0f}, {0.01f, 0.05f, 0.2f, 1.0f}, {0.7f, 0.9f, 1.0f, 1.0f},
+                           {0.1f, 0.3f, 1.0f, 1.0f}, {0.01f, 0.1f, 0.7f, 1.0f}};
+const float BG_DISTS[5] = {-1.0f, -0.04f, 0.0f, 0.5f, 1.0f};
+
+// ---- RNG (PathTracer.comp:220-241) ----------------------------------------------------------------------
+struct Rng {
+    uint32_t state;
+    uint32_t rand_xorshift()                 // :221-228
+    {
+        state ^= (state << 13);
+        state ^= (state >> 17);
+        state ^= (state << 5);
+        return state;
+    }
+    float generateRandomNumber()             // :230-233 ; u32 -> f32 is round-to-nearest-even, range [0,1]
+    {
+        return static_cast<float>(rand_xorshift()) / 4294967296.0f;
+    }
+    void initializeRandom(uint32_t seed)     // :235-241 ; the bound seed % 7 + 2 uses the ORIGINAL seed
+    {
+        state = seed;
+        const uint32_t n = seed % 7u + 2u;
+        for (uint32_t i = 0; i < n; ++i) generateRandomNumber();
+    }
+};
+// :368  int seed * uint(gid.x + gid.y * 32 * numGroups.x), all mod 2^32
+inline uint32_t seed_state(int32_t seed, uint32_t gx, uint32_t gy, uint32_t ngx)
+{
+    return static_cast<uint32_t>(seed) * (gx + gy * 32u * ngx);
+}
+
+// ---- texture(sampler3D) : LINEAR, CLAMP_TO_EDGE, unnormalizedCoordinates = false -------------------------
+// Vulkan texel filtering: u = s*size; i0 = floor(u-0.5); i1 = i0+1; alpha = frac(u-0.5); wrap by clamping the
+// integer texel index to [0,size-1]; blend along x, then y, then z as v0 + a*(v1 - v0).
+inline int clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+inline int to_int_sat(float f)
+{
+    // NaN -> 0 and saturation, so that a NaN coordinate cannot index out of bounds (result is NaN anyway)
+    if (!(f == f)) return 0;
+    if (f < -2147483000.0f) return -2147483647 - 1;
+    if (f > 2147483000.0f) return 2147483647;
+    return static_cast<int>(f);
+}
+float texture3d(const float* vol, uint32_t nx, uint32_t ny, uint32_t nz, vec3 s)
+{
+    const float u = s.x * static_cast<float>(nx) - 0.5f;
+    const float v = s.y * static_cast<float>(ny) - 0.5f;
+    const float w = s.z * static_cast<float>(nz) - 0.5f;
+    const float fu = std::floor(u), fv = std::floor(v), fw = std::floor(w);
+    const float a = u - fu, b = v - fv, c = w - fw;
+    const int i0 = to_int_sat(fu), j0 = to_int_sat(fv), k0 = to_int_sat(fw);
+    const int i0c = clampi(i0, (int)nx - 1), i1c = clampi(i0 == 2147483647 ? i0 : i0 + 1, (int)nx - 1);
+    const int j0c = clampi(j0, (int)ny - 1), j1c = clampi(j0 == 2147483647 ? j0 : j0 + 1, (int)ny - 1);
+    const int k0c = clampi(k0, (int)nz - 1), k1c = clampi(k0 == 2147483647 ? k0 : k0 + 1, (int)nz - 1);
+    const size_t sy = nx, sz = static_cast<size_t>(nx) * ny;
+    auto T = [&](int i, int j, int k) -> float { return vol[i + sy * j + sz * k]; };
+    const float x00 = T(i0c, j0c, k0c) + a * (T(i1c, j0c, k0c) - T(i0c, j0c, k0c));
+    const float x10 = T(i0c, j1c, k0c) + a * (T(i1c, j1c, k0c) - T(i0c, j1c, k0c));
+    const float x01 = T(i0c, j0c, k1c) + a * (T(i1c, j0c, k1c) - T(i0c, j0c, k1c));
+    const float x11 = T(i0c, j1c, k1c) + a * (T(i1c, j1c, k1c) - T(i0c, j1c, k1c));
+    const float y0 = x00 + b * (x10 - x00);
+    const float y1 = x01 + b * (x11 - x01);
+    return y0 + c * (y1 - y0);
+}
+
+// ---- shader helper functions ----------------------------------------------------------------------------
+// :104-113  (lowp evaluated in fp32; mix(a,b,t) = a*(1-t) + b*t; smoothstep = Hermite of the clamped ratio)
+vec4 sampleBackground(vec3 dir)
+{
+    const float dist = dir.y;
+    vec4 col = BG_COLORS[0];
+    for (int i = 1; i < 5; ++i) {
+        float t = (dist - BG_DISTS[i - 1]) / (BG_DISTS[i] - BG_DISTS[i - 1]);
+        t = std::fmin(std::fmax(t, 0.0f), 1.0f);         // clamp = min(max(t,0),1); fmax drops a NaN operand
+        const float s = (t * t) * (3.0f - 2.0f * t);
+        col = col * (1.0f - s) + BG_COLORS[i] * s;
+    }
+    return col;
+}
+
+// :115-119
+float sampleCloud(const float* vol, const Cloud& cp, vec3 pos)
+{
+    const vec4 n = (vec4{pos.x, pos.y, pos.z, 0.0f} - cp.bounds[0]) / (cp.bounds[1] - cp.bounds[0]);
+    return texture3d(vol, cp.voxelCount[0], cp.voxelCount[1], cp.voxelCount[2], vec3{n.x, n.y, n.z});
+}
+
+// mat4 * vec4 as the linear combination of columns, summed left to right
+inline vec4 matvec(const vec4 m[4], vec4 v)
+{
+    return ((m[0] * v.x + m[1] * v.y) + m[2] * v.z) + m[3] * v.w;
+}
+
+// :121-127   (M * (vec4(pos,1) - b0)) / (M * (b1 - b0))
+float sampleShadowVolume(const float* sv, const Shadow& sp, vec3 pos)
+{
+    const vec4 num = matvec(sp.basisChange, vec4{pos.x, pos.y, pos.z, 1.0f} - sp.bounds[0]);
+    const vec4 den = matvec(sp.basisChange, sp.bounds[1] - sp.bounds[0]);
+    const vec4 n = num / den;
+    return texture3d(sv, sp.voxelAxisCount, sp.voxelAxisCount, sp.voxelAxisCount, vec3{n.x, n.y, n.z});
+}
+
+struct Ray { vec3 pos, dir; };
+
+// :144-151
+void getCameraRay(const Camera& c, int x, int y, Ray& ray)
+{
+    ray.dir = (c.forward * c.nearPlane + (c.right * c.pixelSizeX) * static_cast<float>(x - c.halfWidth)) -
+              (c.up * c.pixelSizeY) * static_cast<float>(y - c.halfHeight);
+    ray.pos = ray.dir + c.position;
+    const float len = length(ray.dir);          // normalize(v) = v / sqrt(dot(v,v))
+    ray.dir = vec3{ray.dir.x / len, ray.dir.y / len, ray.dir.z / len};
+}
+
+// :154-184 (isNegativeSign :139-142).  Comparisons are kept literally: NaNs (0 * inf) fall through them the
+// same way they do in the shader.  Out-parameter order is (tmax, tmin).
+bool intersectCloud(const Cloud& cp, const Ray& ray, float& tmax, float& tmin)
+{
+    float tymin = 0, tymax = 0, tzmin = 0, tzmax = 0;
+    const vec3 invdir{1.0f / ray.dir.x, 1.0f / ray.dir.y, 1.0f / ray.dir.z};
+    const int sign[3] = {int(invdir.x < 0), int(invdir.y < 0), int(invdir.z < 0)};
+
+    tmin = (cp.bounds[sign[0]].x - ray.pos.x) * invdir.x;
+    tmax = (cp.bounds[1 - sign[0]].x - ray.pos.x) * invdir.x;
+    tymin = (cp.bounds[sign[1]].y - ray.pos.y) * invdir.y;
+    tymax = (cp.bounds[1 - sign[1]].y - ray.pos.y) * invdir.y;
+
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+
+    tzmin = (cp.bounds[sign[2]].z - ray.pos.z) * invdir.z;
+    tzmax = (cp.bounds[1 - sign[2]].z - ray.pos.z) * invdir.z;
+
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    return true;
+}
+
+// :197-206
+void createOrthonormalBasis(vec3 n, vec3& xp, vec3& yp)
+{
+    const float sz = n.z >= 0.0f ? 1.0f : -1.0f;
+    const float a = n.y / (1.0f + std::fabs(n.z));
+    const float b = n.y * a;
+    const float c = (-n.x) * a;
+    xp = vec3{n.z + sz * b, sz * c, -n.x};
+    yp = vec3{c, 1.0f - b, (-sz) * n.y};
+}
+
+// :247-250
+float calculatePDF(const Params& p, float costheta)
+{
+    return (INV_4Pi * p.phaseOneMinusG2) / std::pow(p.phaseOnePlusG2 - (2.0f * p.phaseG) * costheta, 1.5f);
+}
+// :252-256
+float invertCDF(const Params& p, float xi)
+{
+    const float sqrTerm = p.phaseOneMinusG2 / ((1.0f - p.phaseG) + (2.0f * p.phaseG) * xi);
+    return p.phaseOneOver2G * (p.phaseOnePlusG2 - sqrTerm * sqrTerm);
+}
+// :259-274
+float samplePhase(const Params& p, vec3 incoming, vec3 sample)
+{
+    if (p.isotropic) return INV_4Pi;
+    return calculatePDF(p, dot(incoming, sample));
+}
+
+// :277-311
+void scatterRay(const Params& p, Rng& rng, vec3 incoming, vec3& out)
+{
+    if (p.isotropic) {
+        float xi = rng.generateRandomNumber();
+        out.z = xi * 2.0f - 1.0f;
+        float sinTheta = 1.0f - out.z * out.z;          // actually sin^2
+        if (sinTheta > 0.0f) {
+            sinTheta = std::sqrt(sinTheta > 0.0f ? sinTheta : 0.0f);
+            xi = rng.generateRandomNumber();
+            const float phi = (xi * 2.0f) * PI;
+            out.x = sinTheta * std::cos(phi);
+            out.y = sinTheta * std::sin(phi);
+        } else {
+            out.x = out.y = 0.0f;                        // and NO second draw
+        }
+    } else {
+        const float phi = (rng.generateRandomNumber() * 2.0f) * PI;     // phi is drawn first
+        const float cosTheta = invertCDF(p, rng.generateRandomNumber());
+        const float s2 = 1.0f - cosTheta * cosTheta;
+        const float sinTheta = std::sqrt(s2 > 0.0f ? s2 : 0.0f);        // max(0, s2): NaN -> 0
+        vec3 t0, t1;
+        createOrthonormalBasis(incoming, t0, t1);
+        out = ((sinTheta * std::cos(phi)) * t0 + (sinTheta * std::sin(phi)) * t1) + cosTheta * incoming;  // not renormalised
+    }
+}
+
+struct Counters { uint32_t steps = 0, collisions = 0; };
+
+// :318-361
+bool findScatterPoint(const float* vol, const Cloud& cp, Rng& rng, Ray& ray, Counters& cnt)
+{
+    float tmax = 0, tmin = 0;
+    if (!intersectCloud(cp, ray, tmax, tmin)) return false;
+
+    const vec3 exitPoint = ray.pos + ray.dir * tmax;
+    const float dist = length(ray.pos - exitPoint);
+    float t = 0;
+    vec3 currentPoint{0, 0, 0};
+    const float sigma = (cp.maxExtinction * cp.densityScaling) / cp.baseScaling;
+    do {
+        const float zeta = rng.generateRandomNumber();
+        ++cnt.steps;
+        t += (-std::log(zeta)) / sigma;
+        if (t >= dist) return false;                       // left the cloud
+
+        currentPoint = ray.pos + t * ray.dir;
+        const float extinction = sampleCloud(vol, cp, currentPoint);
+
+        const float xi = rng.generateRandomNumber();
+        if (xi < extinction / cp.maxExtinction) break;
+    } while (true);
+
+    ray.pos = currentPoint;
+    return true;
+}
+
+// :366-425 without the final accumulate; returns `result`
+vec4 tracePixel(const float* vol, const float* sv, const Camera& cam, const Cloud& cp, const Params& par,
+                const Shadow& sp, int32_t seed, float absorption, uint32_t gx, uint32_t gy, uint32_t ngx, Counters& cnt)
+{
+    Rng rng;
+    rng.initializeRandom(seed_state(seed, gx, gy, ngx));
+
+    Ray ray;
+    vec4 result{0, 0, 0, 0};
+    getCameraRay(cam, (int)gx, (int)gy, ray);
+
+    float tmax = 0, tmin = 0;
+    if (!intersectCloud(cp, ray, tmax, tmin) || tmax < 0 || cp.densityScaling <= 0) {
+        result = sampleBackground(ray.dir);
+    } else {
+        ray.pos = ray.pos + ray.dir * (tmax < tmin ? tmax : tmin);
+        Ray currentRay = ray;
+        const vec3 lightDir{sp.lightDirection.x, sp.lightDirection.y, sp.lightDirection.z};
+        while (true) {
+            if (!findScatterPoint(vol, cp, rng, ray, cnt)) {
+                result = result + sampleBackground(ray.dir);
+                break;
+            }
+            ++cnt.collisions;
+            const float pdf = samplePhase(par, -ray.dir, lightDir);
+            const float accumulatedDensity = sampleShadowVolume(sv, sp, ray.pos);
+            const float c = ((1.0f * par.lightIntensity) * pdf) * accumulatedDensity;   // SUNLIGHT_COLOR = vec4(1)
+            result = result + vec4{c, c, c, c};
+
+            // EXTENSION (not in PathTracer.comp; idiom of PPM_PT.comp:445-446): survive iff xi > absorption.
+            // No draw at all when absorption == 0, so the reference RNG stream is untouched.
+            if (absorption > 0.0f) {
+                const float xi = rng.generateRandomNumber();
+                if (!(xi > absorption)) break;             // absorbed: no background term
+            }
+
+            scatterRay(par, rng, currentRay.dir, ray.dir);
+            currentRay = ray;
+        }
+    }
+    return result;
+}
+
+void trace_rect(const float* vol, const float* sv, const void* camera68, const void* cloud60, const void* params28,
+                const void* svprops152, const void* push24, float absorption, int accum_sum, int x0, int y0, int x1,
+                int y1, float* image, float* sample, uint32_t* steps, uint32_t* collisions, int num_threads)
+{
+    const Camera cam = load_camera(camera68);
+    const Cloud cp = load_cloud(cloud60);
+    const Params par = load_params(params28);
+    const Shadow sp = load_shadow(svprops152);
+    const Push pc = load_push(push24);
+    const int W = cam.halfWidth * 2, H = cam.halfHeight * 2;
+    const uint32_t ngx = static_cast<uint32_t>(W / 32 + 1);      // RenderTechniquePT.cpp:141
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > W) x1 = W;
+    if (y1 > H) y1 = H;
+#ifdef _OPENMP
+    if (num_threads <= 0) num_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads)
+#endif
+    for (int y = y0; y < y1; ++y) {
+        for (int x = x0; x < x1; ++x) {
+            Counters cnt;
+            const vec4 r = tracePixel(vol, sv, cam, cp, par, sp, pc.seed, absorption, (uint32_t)x, (uint32_t)y, ngx, cnt);
+            const size_t p = static_cast<size_t>(y) * W + x;
+            if (sample) { sample[4 * p] = r.x; sample[4 * p + 1] = r.y; sample[4 * p + 2] = r.z; sample[4 * p + 3] = r.w; }
+            if (steps) steps[p] = cnt.steps;
+            if (collisions) collisions[p] = cnt.collisions;
+            if (image) {
+                float* px = image + 4 * p;
+                const float in[4] = {r.x, r.y, r.z, r.w};
+                for (int c = 0; c < 4; ++c) {
+                    if (accum_sum) {
+                        px[c] = px[c] + in[c];
+                    } else {
+                        // :420-424  result += old * frameCount; result /= frameCount + 1
+                        float v = in[c] + px[c] * static_cast<float>(pc.frameCount);
+                        v = v / static_cast<float>(pc.frameCount + 1u);
+                        px[c] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- synthetic fBm cloud (frozen generator) ----------------------------------------
+inline uint32_t mix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
+inline float lattice(uint32_t ix, uint32_t iy, uint32_t iz, uint32_t s)
+{
+    const uint32_t h = mix32((ix * 0x8da6b343u) ^ (iy * 0xd8163841u) ^ (iz * 0xcb1ab31fu) ^ (s * 0x9e3779b9u));
+    return static_cast<float>(h >> 8) * (1.0f / 16777216.0f);
+}
+inline float fade(float t) { return (t * t) * (3.0f - 2.0f * t); }
+inline float lerp(float a, float b, float t) { return a + t * (b - a); }
+float value_noise(float px, float py, float pz, uint32_t s)
+{
+    const float fx = std::floor(px), fy = std::floor(py), fz = std::floor(pz);
+    const uint32_t ix = (uint32_t)(int)fx, iy = (uint32_t)(int)fy, iz = (uint32_t)(int)fz;
+    const float u = fade(px - fx), v = fade(py - fy), w = fade(pz - fz);
+    const float x00 = lerp(lattice(ix, iy, iz, s), lattice(ix + 1, iy, iz, s), u);
+    const float x10 = lerp(lattice(ix, iy + 1, iz, s), lattice(ix + 1, iy + 1, iz, s), u);
+    const float x01 = lerp(lattice(ix, iy, iz + 1, s), lattice(ix + 1, iy, iz + 1, s), u);
+    const float x11 = lerp(lattice(ix, iy + 1, iz + 1, s), lattice(ix + 1, iy + 1, iz + 1, s), u);
+    return lerp(lerp(x00, x10, v), lerp(x01, x11, v), w);
+}
+float fbm_density(uint32_t i, uint32_t j, uint32_t k, uint32_t n, uint32_t seed)
+{
+    const float fn = static_cast<float>(n);
+    const float px = (static_cast<float>(i) + 0.5f) / fn;
+    const float py = (static_cast<float>(j) + 0.5f) / fn;
+    const float pz = (static_cast<float>(k) + 0.5f) / fn;
+    float sum = 0.0f, amp = 1.0f, freq = 4.0f;
+    for (uint32_t o = 0; o < 5; ++o) {
+        sum = sum + amp * value_noise(px * freq, py * freq, pz * freq, seed + o);
+        freq = freq * 2.0f;
+        amp = amp * 0.5f;
+    }
+    const float fbm = sum / 1.9375f;
+    const float dx = px - 0.5f, dy = py - 0.5f, dz = pz - 0.5f;
+    const float r2 = ((dx * dx + dy * dy) + dz * dz) / 0.25f;
+    float d = ((fbm - 0.35f) - 0.65f * r2) / 0.35f;
+    d = d < 0.0f ? 0.0f : (d > 1.0f ? 1.0f : d);
+    return d;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+uint32_t orc_rng_seed_state(int32_t seed, uint32_t gx, uint32_t gy, uint32_t ngx) { return seed_state(seed, gx, gy, ngx); }
+uint32_t orc_rng_warmup_count(uint32_t state0) { return state0 % 7u + 2u; }
+
+void orc_rng_draws(int32_t seed, uint32_t gx, uint32_t gy, uint32_t ngx, uint32_t n, uint32_t* states, float* floats)
+{
+    Rng r;
+    r.initializeRandom(seed_state(seed, gx, gy, ngx));
+    for (uint32_t i = 0; i < n; ++i) {
+        const float f = r.generateRandomNumber();
+        if (states) states[i] = r.state;
+        if (floats) floats[i] = f;
+    }
+}
+
+void orc_rng_tap(int32_t seed, uint32_t width, uint32_t height, uint32_t n_draws, uint32_t* out)
+{
+    const uint32_t ngx = width / 32u + 1u;
+    for (uint32_t y = 0; y < height; ++y)
+        for (uint32_t x = 0; x < width; ++x) {
+            Rng r;
+            r.initializeRandom(seed_state(seed, x, y, ngx));
+            uint32_t* o = out + (static_cast<size_t>(y) * width + x) * n_draws;
+            for (uint32_t i = 0; i < n_draws; ++i) o[i] = r.rand_xorshift();
+        }
+}
+
+void orc_camera_ray(const void* camera68, int x, int y, float pos[3], float dir[3])
+{
+    Ray r;
+    getCameraRay(load_camera(camera68), x, y, r);
+    pos[0] = r.pos.x; pos[1] = r.pos.y; pos[2] = r.pos.z;
+    dir[0] = r.dir.x; dir[1] = r.dir.y; dir[2] = r.dir.z;
+}
+
+int orc_intersect_cloud(const void* cloud60, const float pos[3], const float dir[3], float* tmax, float* tmin)
+{
+    Ray r{{pos[0], pos[1], pos[2]}, {dir[0], dir[1], dir[2]}};
+    float a = 0, b = 0;
+    const bool hit = intersectCloud(load_cloud(cloud60), r, a, b);
+    *tmax = a; *tmin = b;
+    return hit ? 1 : 0;
+}
+
+void orc_orthonormal_basis(const float n[3], float xp[3], float yp[3])
+{
+    vec3 a, b;
+    createOrthonormalBasis(vec3{n[0], n[1], n[2]}, a, b);
+    xp[0] = a.x; xp[1] = a.y; xp[2] = a.z;
+    yp[0] = b.x; yp[1] = b.y; yp[2] = b.z;
+}
+
+float orc_calculate_pdf(const void* params28, float c) { return calculatePDF(load_params(params28), c); }
+float orc_invert_cdf(const void* params28, float xi) { return invertCDF(load_params(params28), xi); }
+float orc_sample_phase(const void* params28, const float in[3], const float s[3])
+{
+    return samplePhase(load_params(params28), vec3{in[0], in[1], in[2]}, vec3{s[0], s[1], s[2]});
+}
+void orc_background(const float dir[3], float rgba[4])
+{
+    const vec4 c = sampleBackground(vec3{dir[0], dir[1], dir[2]});
+    rgba[0] = c.x; rgba[1] = c.y; rgba[2] = c.z; rgba[3] = c.w;
+}
+float orc_texture3d(const float* vol, uint32_t nx, uint32_t ny, uint32_t nz, const float uvw[3])
+{
+    return texture3d(vol, nx, ny, nz, vec3{uvw[0], uvw[1], uvw[2]});
+}
+float orc_sample_cloud(const float* vol, const void* cloud60, const float pos[3])
+{
+    return sampleCloud(vol, load_cloud(cloud60), vec3{pos[0], pos[1], pos[2]});
+}
+float orc_sample_shadow_volume(const float* sv, const void* svprops152, const float pos[3])
+{
+    return sampleShadowVolume(sv, load_shadow(svprops152), vec3{pos[0], pos[1], pos[2]});
+}
+void orc_scatter_ray(const void* params28, uint32_t* rng_state, const float incoming[3], float out_dir[3])
+{
+    Rng r;
+    r.state = *rng_state;
+    vec3 o{0, 0, 0};
+    scatterRay(load_params(params28), r, vec3{incoming[0], incoming[1], incoming[2]}, o);
+    *rng_state = r.state;
+    out_dir[0] = o.x; out_dir[1] = o.y; out_dir[2] = o.z;
+}
+
+// ShadowVolume.comp:77-94 (helpers :34-56).  One (x,y) column per loop iteration, z serial.
+void orc_shadow_volume(const float* cloud, const void* cloud60, const void* svprops152, float* out, int num_threads)
+{
+    const Cloud cp = load_cloud(cloud60);
+    const Shadow sp = load_shadow(svprops152);
+    const uint32_t N = sp.voxelAxisCount;
+#ifdef _OPENMP
+    if (num_threads <= 0) num_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads)
+#endif
+    for (int64_t col = 0; col < static_cast<int64_t>(N) * N; ++col) {
+        const uint32_t x = static_cast<uint32_t>(col % N), y = static_cast<uint32_t>(col / N);
+        float accumulatedValue = 0.0f;          // .x of the vec4; the other channels never reach the r32f store
+        float accumulatedDistance = 0.0f;
+        for (uint32_t z = 0; z < N; ++z) {
+            // :50-56  (b0 + (x*right + y*up + z*light) * voxelSize).xyz
+            const vec4 p4 = sp.bounds[0] + ((static_cast<float>(x) * sp.right + static_cast<float>(y) * sp.up) +
+                                            static_cast<float>(z) * sp.lightDirection) * sp.voxelSize;
+            const vec3 p{p4.x, p4.y, p4.z};
+            // :34-42 inclusive AABB
+            const bool inside = !(p.x < cp.bounds[0].x || p.y < cp.bounds[0].y || p.z < cp.bounds[0].z ||
+                                  p.x > cp.bounds[1].x || p.y > cp.bounds[1].y || p.z > cp.bounds[1].z);
+            if (inside) accumulatedValue = accumulatedValue + (sampleCloud(cloud, cp, p) * cp.densityScaling) / cp.baseScaling;
+            accumulatedDistance = accumulatedDistance + sp.voxelSize;
+            const float e = ((-accumulatedDistance) * accumulatedValue) / static_cast<float>(z + 1u);
+            out[x + static_cast<size_t>(N) * (y + static_cast<size_t>(N) * z)] = std::exp(e);
+        }
+    }
+}
+
+void orc_path_trace_frame(const float* cloud, const float* sv, const void* camera68, const void* cloud60,
+                          const void* params28, const void* svprops152, const void* push24, float absorption,
+                          int accum_sum, float* image, float* sample, uint32_t* steps, uint32_t* collisions,
+                          int num_threads)
+{
+    trace_rect(cloud, sv, camera68, cloud60, params28, svprops152, push24, absorption, accum_sum, 0, 0, 1 << 30, 1 << 30,
+               image, sample, steps, collisions, num_threads);
+}
+
+void orc_path_trace_rect(const float* cloud, const float* sv, const void* camera68, const void* cloud60,
+                         const void* params28, const void* svprops152, const void* push24, float absorption,
+                         int accum_sum, int x0, int y0, int x1, int y1, float* image, float* sample,
+                         uint32_t* steps, uint32_t* collisions, int num_threads)
+{
+    trace_rect(cloud, sv, camera68, cloud60, params28, svprops152, push24, absorption, accum_sum, x0, y0, x1, y1, image,
+               sample, steps, collisions, num_threads);
+}
+
+void orc_fbm_generate(uint32_t n, uint32_t seed, float* out, int num_threads)
+{
+#ifdef _OPENMP
+    if (num_threads <= 0) num_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(num_threads)
+#endif
+    for (int64_t k = 0; k < static_cast<int64_t>(n); ++k)
+        for (uint32_t j = 0; j < n; ++j)
+            for (uint32_t i = 0; i < n; ++i)
+                out[i + static_cast<size_t>(n) * (j + static_cast<size_t>(n) * k)] = fbm_density(i, j, (uint32_t)k, n, seed);
+}
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+"""ctypes binding of the CPU oracle (oracle/libcrv_oracle.so).  TEST INFRASTRUCTURE: only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "libcrv_oracle.so")
+REF_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libcrv_refstructs.so")
+
+
+def _ensure_built():
+    if not os.path.exists(LIB_PATH):
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.run(["make", "libcrv_oracle.so"], cwd=ORACLE_DIR, env=env, check=True, stdout=subprocess.DEVNULL)
+
+
+_ensure_built()
+lib = C.CDLL(LIB_PATH)
+
+_vp, _u32, _i32, _f = C.c_void_p, C.c_uint32, C.c_int32, C.c_float
+_fp = C.POINTER(C.c_float)
+lib.orc_rng_seed_state.restype = _u32
+lib.orc_rng_seed_state.argtypes = [_i32, _u32, _u32, _u32]
+lib.orc_rng_warmup_count.restype = _u32
+lib.orc_rng_warmup_count.argtypes = [_u32]
+lib.orc_rng_draws.argtypes = [_i32, _u32, _u32, _u32, _u32, _vp, _vp]
+lib.orc_rng_tap.argtypes = [_i32, _u32, _u32, _u32, _vp]
+lib.orc_camera_ray.argtypes = [_vp, C.c_int, C.c_int, _fp, _fp]
+lib.orc_intersect_cloud.restype = C.c_int
+lib.orc_intersect_cloud.argtypes = [_vp, _fp, _fp, _fp, _fp]
+lib.orc_orthonormal_basis.argtypes = [_fp, _fp, _fp]
+lib.orc_calculate_pdf.restype = _f
+lib.orc_calculate_pdf.argtypes = [_vp, _f]
+lib.orc_invert_cdf.restype = _f
+lib.orc_invert_cdf.argtypes = [_vp, _f]
+lib.orc_sample_phase.restype = _f
+lib.orc_sample_phase.argtypes = [_vp, _fp, _fp]
+lib.orc_background.argtypes = [_fp, _fp]
+lib.orc_texture3d.restype = _f
+lib.orc_texture3d.argtypes = [_vp, _u32, _u32, _u32, _fp]
+lib.orc_sample_cloud.restype = _f
+lib.orc_sample_cloud.argtypes = [_vp, _vp, _fp]
+lib.orc_sample_shadow_volume.restype = _f
+lib.orc_sample_shadow_volume.argtypes = [_vp, _vp, _fp]
+lib.orc_scatter_ray.argtypes = [_vp, C.POINTER(_u32), _fp, _fp]
+lib.orc_shadow_volume.argtypes = [_vp, _vp, _vp, _vp, C.c_int]
+lib.orc_path_trace_frame.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, C.c_int, _vp, _vp, _vp, _vp, C.c_int]
+lib.orc_path_trace_rect.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    _vp, _vp, _vp, _vp, C.c_int]
+lib.orc_fbm_generate.argtypes = [_u32, _u32, _vp, C.c_int]
+lib.orc_max_threads.restype = C.c_int
+
+
+def _f3(v):
+    return (C.c_float * 3)(float(v[0]), float(v[1]), float(v[2]))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _raw(struct):
+    """address of a ctypes struct (the oracle reads raw bytes at the shaders' std140 offsets)"""
+    return C.cast(C.byref(struct), C.c_void_p)
+
+
+def max_threads() -> int:
+    return lib.orc_max_threads()
+
+
+def rng_draws(seed, gx, gy, ngx, n):
+    st = np.empty(n, np.uint32)
+    fl = np.empty(n, np.float32)
+    lib.orc_rng_draws(seed, gx, gy, ngx, n, _ptr(st), _ptr(fl))
+    return st, fl
+
+
+def rng_tap(seed, width, height, n_draws):
+    out = np.empty((height, width, n_draws), np.uint32)
+    lib.orc_rng_tap(seed, width, height, n_draws, _ptr(out))
+    return out
+
+
+def camera_ray(cam, x, y):
+    p, d = (C.c_float * 3)(), (C.c_float * 3)()
+    lib.orc_camera_ray(_raw(cam), x, y, p, d)
+    return np.array(p[:], np.float32), np.array(d[:], np.float32)
+
+
+def intersect_cloud(cloud, pos, direction):
+    tmax, tmin = C.c_float(), C.c_float()
+    hit = lib.orc_intersect_cloud(_raw(cloud), _f3(pos), _f3(direction), C.byref(tmax), C.byref(tmin))
+    return bool(hit), tmax.value, tmin.value
+
+
+def orthonormal_basis(n):
+    a, b = (C.c_float * 3)(), (C.c_float * 3)()
+    lib.orc_orthonormal_basis(_f3(n), a, b)
+    return np.array(a[:], np.float32), np.array(b[:], np.float32)
+
+
+def calculate_pdf(params, c):
+    return lib.orc_calculate_pdf(_raw(params), c)
+
+
+def invert_cdf(params, xi):
+    return lib.orc_invert_cdf(_raw(params), xi)
+
+
+def sample_phase(params, incoming, sample):
+    return lib.orc_sample_phase(_raw(params), _f3(incoming), _f3(sample))
+
+
+def background(direction):
+    out = (C.c_float * 4)()
+    lib.orc_background(_f3(direction), out)
+    return np.array(out[:], np.float32)
+
+
+def texture3d(vol, nx, ny, nz, uvw):
+    v = np.ascontiguousarray(vol, np.float32)
+    return lib.orc_texture3d(_ptr(v), nx, ny, nz, _f3(uvw))
+
+
+def sample_cloud(vol, cloud, pos):
+    v = np.ascontiguousarray(vol, np.float32)
+    return lib.orc_sample_cloud(_ptr(v), _raw(cloud), _f3(pos))
+
+
+def sample_shadow_volume(sv, svprops, pos):
+    v = np.ascontiguousarray(sv, np.float32)
+    return lib.orc_sample_shadow_volume(_ptr(v), _raw(svprops), _f3(pos))
+
+
+def scatter_ray(params, rng_state, incoming):
+    st = _u32(rng_state)
+    out = (C.c_float * 3)()
+    lib.orc_scatter_ray(_raw(params), C.byref(st), _f3(incoming), out)
+    return np.array(out[:], np.float32), st.value
+
+
+def shadow_volume(cloud, cloud_props, sv_props, threads=0):
+    n = sv_props.voxelAxisCount
+    v = np.ascontiguousarray(cloud, np.float32)
+    out = np.empty(n * n * n, np.float32)
+    lib.orc_shadow_volume(_ptr(v), _raw(cloud_props), _raw(sv_props), _ptr(out), threads)
+    return out
+
+
+def path_trace_frame(cloud, sv, cam, cloud_props, params, sv_props, push, absorption, image, accum_sum=0,
+                     want_sample=True, threads=0, rect=None):
+    """One dispatch of PathTracer.comp on the CPU. `image` (H,W,4) is updated in place.
+    Returns (sample, steps, collisions)."""
+    w, h = cam.halfWidth * 2, cam.halfHeight * 2
+    v = np.ascontiguousarray(cloud, np.float32)
+    s = np.ascontiguousarray(sv, np.float32)
+    sample = np.zeros((h, w, 4), np.float32) if want_sample else None
+    steps = np.zeros((h, w), np.uint32)
+    coll = np.zeros((h, w), np.uint32)
+    if image is not None:
+        assert image.dtype == np.float32 and image.flags["C_CONTIGUOUS"] and image.size == w * h * 4
+    if rect is None:
+        lib.orc_path_trace_frame(_ptr(v), _ptr(s), _raw(cam), _raw(cloud_props), _raw(params), _raw(sv_props), _raw(push),
+                                 absorption, accum_sum, _ptr(image), _ptr(sample), _ptr(steps), _ptr(coll), threads)
+    else:
+        x0, y0, x1, y1 = rect
+        lib.orc_path_trace_rect(_ptr(v), _ptr(s), _raw(cam), _raw(cloud_props), _raw(params), _raw(sv_props), _raw(push),
+                                absorption, accum_sum, x0, y0, x1, y1, _ptr(image), _ptr(sample), _ptr(steps), _ptr(coll), threads)
+    return sample, steps, coll
+
+
+def fbm_generate(n, seed=1234, threads=0):
+    out = np.empty(n * n * n, np.float32)
+    lib.orc_fbm_generate(n, seed, _ptr(out), threads)
+    return out
+
+
+def ref_structs_lib():
+    """The shim around the reference's own headers (oracle/_ref), or None when it was never built."""
+    if not os.path.exists(REF_LIB_PATH):
+        return None
+    return C.CDLL(REF_LIB_PATH)

@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star / SURVEY.md 8d):
+  * RNG: exact u32 equality
+  * shadow volume: <= 1e-5 relative for T >= 1e-30 (absolute 1e-35 below)
+  * per-sample radiance: <= 1e-4 relative (floor 1e-3) on pixels whose (steps, collisions) counters match the
+    oracle's; pixels whose counters differ are "threshold-divergent" (libm vs CUDA log/sin/cos/pow differ by
+    <= 2 ulp and a compare flipped) -- counted, reported, bounded, and covered by the statistical test
+  * converged image: |mean_gpu - mean_cpu| <= 5 sigma / sqrt(spp)
+  * everything that does not involve a transcendental difference is bit-exact: layouts, scheduling knobs,
+    batch-vs-sequential accumulation.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS = ["linear", "brick", "tex3d"]
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def make_scene(crv, orc, ctx, n=40, w=96, h=64, nsv=56, layout="linear", g=0.85, absorption=0.0, density_scaling=50.0,
+               light=(1.0, -1.0, 0.0), cloud=None):
+    wl = crv.Workload("t", n, w, h, 1, nsv, density_scaling, absorption, g, light)
+    r = crv.make_renderer(ctx, wl, cloud_layout=layout)
+    if cloud is None:
+        cloud = orc.fbm_generate(n, 1234)
+    r.set_cloud_host(cloud, (n, n, n), (1.0 / n,) * 3)
+    return r, cloud
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_rng_tap_bit_exact(crv, orc, ctx):
+    for (w, h) in [(64, 64), (96, 40), (1920, 4)]:
+        for seed in [38, 7719, 100, -5, 0]:
+            gpu = crv.rng_tap(ctx, seed, w, h, 8)
+            cpu = orc.rng_tap(seed, w, h, 8)
+            assert np.array_equal(gpu, cpu), f"RNG stream differs for seed {seed} at {w}x{h}"
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_volume_roundtrip_and_majorant(crv, ctx, layout):
+    rng = np.random.default_rng(7)
+    for shape in [(16, 16, 16), (13, 7, 21), (40, 9, 8), (1, 1, 1)]:
+        a = rng.random(shape[0] * shape[1] * shape[2], dtype=np.float32)
+        v = crv.Volume(ctx, *shape, layout=layout)
+        v.upload(a)
+        assert np.array_equal(v.download(), a)
+        assert v.majorant() == a.max()
+        v.close()
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_fbm_device_generator_matches_oracle(crv, orc, ctx, layout):
+    n = 48
+    v = crv.Volume(ctx, n, n, n, layout=layout)
+    v.fbm_generate(1234)
+    gpu = v.download()
+    cpu = orc.fbm_generate(n, 1234)
+    assert np.array_equal(_bits(gpu), _bits(cpu)), "device fBm generator is not bit-identical to the oracle's"
+    assert v.majorant() == cpu.max()
+    v.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _sv_check(gpu, cpu):
+    big = cpu >= 1e-30
+    rel = np.abs(gpu[big] - cpu[big]) / cpu[big]
+    assert rel.max() <= 1e-5, f"shadow volume: max rel err {rel.max():.3e}"
+    if (~big).any():
+        assert np.abs(gpu[~big] - cpu[~big]).max() <= 1e-35
+    return float(rel.max())
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("light", [(1.0, -1.0, 0.0), (0.3, -0.8, 0.5), (0.0, 0.0, 1.0)])
+def test_shadow_volume_parity(crv, orc, ctx, layout, light):
+    for nsv, ds in [(70, 50.0), (33, 400.0)]:
+        r, cloud = make_scene(crv, orc, ctx, n=40, nsv=nsv, layout=layout, density_scaling=ds, light=light)
+        gpu = r.shadowVolumeImage.download()
+        cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+        _sv_check(gpu, cpu)
+        assert gpu.min() < 0.9 and gpu.max() == 1.0       # the volume really holds shadow and lit voxels
+        r.close()
+
+
+def test_shadow_volume_nonuniform_grid(crv, orc, ctx):
+    """ragged, non-cubic cloud grid with a non-zero boundary (clamp-to-edge texels matter)"""
+    rng = np.random.default_rng(3)
+    nx, ny, nz = 21, 34, 13
+    cloud = rng.random(nx * ny * nz, dtype=np.float32)
+    wl = crv.Workload("t", 0, 64, 64, 1, 45, 120.0, 0.0, None, (0.2, -1.0, 0.1))
+    r = crv.make_renderer(ctx, wl)
+    r.set_cloud_host(cloud, (nx, ny, nz), (0.01, 0.02, 0.03))
+    cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+    _sv_check(r.shadowVolumeImage.download(), cpu)
+    r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _frame_parity(crv, orc, r, cloud, seed, absorption, min_match=0.99):
+    sv_cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+    r.reset_accumulation()
+    r.pathTracingTechnique.SetDebugCounters(True)
+    r.pushConstants.seed = seed
+    r.pathTracingTechnique.RecordDrawCommands(0, 0)
+    gpu = r.resultImage.download()
+    gs, gc = r.pathTracingTechnique.DownloadDebugCounters()
+    pc = crv.PushConstants()
+    pc.seed, pc.frameCount = seed, 0
+    h, w = gpu.shape[:2]
+    cpu = np.zeros((h, w, 4), np.float32)
+    _, cs, cc = orc.path_trace_frame(cloud, sv_cpu, r.cameraProperties, r.cloudProperties, r.parameters,
+                                     r.shadowVolumeProperties, pc, absorption, cpu)
+    same = (gs == cs) & (gc == cc)
+    err = np.abs(gpu - cpu) / np.maximum(np.abs(cpu), 1e-3)
+    divergent = int((~same).sum())
+    print(f"seed {seed}: {divergent}/{same.size} threshold-divergent paths ({divergent / same.size:.2e}); "
+          f"max rel err on matching paths {err[same].max():.2e}; mean steps {cs.mean():.1f}, collisions {cc.mean():.2f}")
+    assert same.mean() >= min_match, f"too many divergent paths: {divergent}/{same.size}"
+    assert err[same].max() <= 1e-4
+    assert cc.max() > 0 and (cs == 0).any(), "scene must contain both scattering paths and misses"
+    return divergent, same.size
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("g,absorption", [(None, 0.0), (0.85, 0.0), (0.85, 0.1), (-0.4, 0.3)])
+def test_pt_single_frame_parity(crv, orc, ctx, layout, g, absorption):
+    r, cloud = make_scene(crv, orc, ctx, layout=layout, g=g, absorption=absorption)
+    for seed in [38, 7719, 21238]:
+        _frame_parity(crv, orc, r, cloud, seed, absorption)
+    r.close()
+
+
+def test_pt_dense_long_paths(crv, orc, ctx):
+    """config-4 style stress: densityScaling 200, albedo 0.99 -> long paths, heavy divergence inside warps"""
+    r, cloud = make_scene(crv, orc, ctx, n=32, w=64, h=48, nsv=48, g=0.85, absorption=0.01, density_scaling=200.0)
+    d, n = _frame_parity(crv, orc, r, cloud, 2437, 0.01, min_match=0.97)
+    r.close()
+
+
+def test_pt_camera_inside_cloud_and_zero_density(crv, orc, ctx):
+    r, cloud = make_scene(crv, orc, ctx, n=32, w=64, h=48, nsv=40)
+    # camera inside the box: entry point moves BACKWARDS to tmin (PathTracer.comp:387)
+    r.cameraProperties.position[0], r.cameraProperties.position[1], r.cameraProperties.position[2] = 10.0, -20.0, 480.0
+    r.apply_parameters()
+    _frame_parity(crv, orc, r, cloud, 8855, 0.0, min_match=0.98)
+    # densityScaling <= 0: every pixel is pure background (PathTracer.comp:379)
+    r.cloudProperties.densityScaling = 0.0
+    r.apply_parameters()
+    r.reset_accumulation()
+    r.pushConstants.seed = 5
+    r.pathTracingTechnique.RecordDrawCommands(0, 0)
+    img = r.resultImage.download()
+    for (x, y) in [(0, 0), (31, 20), (63, 47)]:
+        _, d = orc.camera_ray(r.cameraProperties, x, y)
+        assert np.array_equal(_bits(img[y, x]), _bits(orc.background(d)))
+    r.close()
+
+
+def test_running_mean_over_existing_image(crv, orc, ctx):
+    """frameCount > 0 over a non-zero image: the shader's accumulate formula (:420-424), bit for bit on misses"""
+    r, cloud = make_scene(crv, orc, ctx, n=24, w=32, h=32, nsv=32)
+    rng = np.random.default_rng(0)
+    old = rng.random((32, 32, 4), dtype=np.float32)
+    r.resultImage.upload(old)
+    r.pushConstants.seed, r.pushConstants.frameCount = 1234, 7
+    r.pathTracingTechnique.SetDebugCounters(True)
+    r.pathTracingTechnique.RecordDrawCommands(0, 0)
+    gpu = r.resultImage.download()
+    steps, _ = r.pathTracingTechnique.DownloadDebugCounters()
+    miss = steps == 0
+    ys, xs = np.nonzero(miss)
+    for y, x in list(zip(ys, xs))[:64]:
+        _, d = orc.camera_ray(r.cameraProperties, int(x), int(y))
+        want = (orc.background(d) + old[y, x] * np.float32(7)) / np.float32(8)
+        assert np.array_equal(_bits(gpu[y, x]), _bits(want.astype(np.float32)))
+    r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_batch_equals_sequential_frames_bitwise(crv, orc, ctx):
+    r, _ = make_scene(crv, orc, ctx, g=0.85, absorption=0.1)
+    for _ in range(6):
+        r.DrawFrame()
+    seq = r.resultImage.download().copy()
+    r.reset_accumulation()
+    r.render(6)
+    bat = r.resultImage.download()
+    assert np.array_equal(_bits(seq), _bits(bat)), "RenderBatch differs from successive RecordDrawCommands"
+    # a second batch continues the running mean with frameCount = 6; tiny sample buffer forces several rounds
+    r.pathTracingTechnique.SetTuning(sample_buffer_bytes=2 * 96 * 64 * 16)
+    r.render(5)
+    a = r.resultImage.download().copy()
+    r.reset_accumulation()
+    for _ in range(11):
+        r.DrawFrame()
+    assert np.array_equal(_bits(a), _bits(r.resultImage.download()))
+    r.close()
+
+
+def test_layouts_and_scheduling_are_bit_identical(crv, orc, ctx):
+    """storage layout, occupancy and the wavefront threshold must not change a single bit of the image"""
+    imgs = []
+    cloud = orc.fbm_generate(40, 1234)
+    for layout, ctas, thr in [("linear", 0, 0), ("brick", 1, 1), ("tex3d", 2, 32), ("linear", 3, 20)]:
+        r, _ = make_scene(crv, orc, ctx, layout=layout, g=0.85, absorption=0.05, cloud=cloud)
+        r.pathTracingTechnique.SetTuning(ctas_per_sm=ctas, track_threshold=thr)
+        r.render(4)
+        imgs.append(r.resultImage.download().copy())
+        r.close()
+    for im in imgs[1:]:
+        assert np.array_equal(_bits(imgs[0]), _bits(im))
+
+
+def test_sum_mode_matches_mean(crv, orc, ctx):
+    r, _ = make_scene(crv, orc, ctx, g=0.85)
+    seeds = crv.msvc_rand_sequence(8)
+    r.render(8, seeds=seeds)
+    mean = r.resultImage.download().copy()
+    r.reset_accumulation()
+    r.render(8, seeds=seeds, accum_mode=crv.ACCUM_SUM)
+    r.resultImage.scale(1.0 / 8)
+    s = r.resultImage.download()
+    assert np.allclose(s, mean, rtol=1e-5, atol=1e-7)
+    r.close()
+
+
+def test_converged_image_within_noise(crv, orc, ctx):
+    """16 frames: GPU mean vs oracle mean within 5 sigma/sqrt(spp) per pixel (sigma from the oracle's samples)"""
+    n, w, h, nsv, spp = 32, 64, 48, 40, 16
+    r, cloud = make_scene(crv, orc, ctx, n=n, w=w, h=h, nsv=nsv, g=0.85, absorption=0.1)
+    seeds = crv.msvc_rand_sequence(spp)
+    r.render(spp, seeds=seeds)
+    gpu = r.resultImage.download()
+    sv_cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+    cpu = np.zeros((h, w, 4), np.float32)
+    samples = []
+    pc = crv.PushConstants()
+    for f, s in enumerate(seeds):
+        pc.seed, pc.frameCount = int(s), f
+        smp, _, _ = orc.path_trace_frame(cloud, sv_cpu, r.cameraProperties, r.cloudProperties, r.parameters,
+                                         r.shadowVolumeProperties, pc, 0.1, cpu)
+        samples.append(smp)
+    sigma = np.std(np.stack(samples), axis=0, ddof=1)
+    bound = 5.0 * sigma / np.sqrt(spp) + 1e-5 * np.abs(cpu) + 1e-7
+    outliers = np.abs(gpu - cpu) > bound
+    frac = outliers.mean()
+    print(f"converged: outlier fraction {frac:.2e}, max abs diff {np.abs(gpu - cpu).max():.3e}")
+    assert frac <= 1e-3
+    # and the images are identical wherever no path diverged: the overwhelming majority of pixels
+    assert (np.abs(gpu - cpu) <= 1e-4 * np.maximum(np.abs(cpu), 1e-3)).mean() > 0.98
+    r.close()
+
+
+def test_stats_match_oracle_counters(crv, orc, ctx):
+    r, cloud = make_scene(crv, orc, ctx, n=32, w=64, h=48, nsv=40, g=None)
+    sv_cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+    r.pathTracingTechnique.ResetStats()
+    r.pushConstants.seed = 38
+    r.pathTracingTechnique.RecordDrawCommands(0, 0)
+    st = r.pathTracingTechnique.GetStats()
+    pc = crv.PushConstants()
+    pc.seed, pc.frameCount = 38, 0
+    _, cs, cc = orc.path_trace_frame(cloud, sv_cpu, r.cameraProperties, r.cloudProperties, r.parameters,
+                                     r.shadowVolumeProperties, pc, 0.0, None)
+    assert st.paths == 64 * 48
+    assert abs(int(st.tracking_steps) - int(cs.sum())) <= 0.01 * cs.sum()
+    assert abs(int(st.collisions) - int(cc.sum())) <= 0.02 * cc.sum() + 2
+    assert 0 < st.density_fetches < st.tracking_steps, "the brick-max skip must remove fetches (and not all of them)"
+    r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_error_behaviour(crv, ctx):
+    """status codes + message instead of the reference's abort() (Validation.cpp:4-10)"""
+    cam, pc = crv.CameraProperties(), crv.PushConstants()
+    pt = crv.RenderTechniquePT(ctx, None, cam, pc)
+    with pytest.raises(crv.CrvError) as e:
+        pt.RecordDrawCommands(0, 0)                      # nothing bound
+    assert e.value.code == crv.capi.CRV_ERR_INVALID
+    img = crv.Image(ctx, 64, 64)                         # wrong size for the default 800x600 camera
+    pt.SetFrameReferences([img])
+    with pytest.raises(crv.CrvError):
+        pt.RecordDrawCommands(0, 0)
+    with pytest.raises(crv.CrvError):
+        crv.Volume(ctx, 0, 4, 4)
+    with pytest.raises(crv.CrvError):
+        pt.SetExtensions(crv.PathTracerExtensions(1.5))
+    sp = crv.ShadowVolumeProperties()
+    sv = crv.RenderTechniqueSV(ctx, sp, pc)
+    with pytest.raises(crv.CrvError):
+        sv.RecordDrawCommands(0, 0)
+    sv.close()
+    pt.close()
+    img.close()
