@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the PathTracer + ShadowVolume hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W        (N > 1)
+
+One "step" = one full progressive render of the workload (all spp) of BASELINE.json's headline configuration
+(`c2`: 512^3 fBm cloud, 1920x1080, 256 spp, albedo 0.9, HG g = 0.85) from parameters already resident in HBM.
+metric = Mpath-samples/s = W*H*spp_total / step time (PT launches + accumulation + cross-GPU reduce), whole job.
+N > 1: the density grid and shadow volume are replicated, every rank renders `spp` frames of its own
+(frame f of the global list goes to rank f mod N; weak scaling: spp_total = N * spp), partial fp32 SUMs are
+combined with one NCCL all-reduce over NVLink and divided by spp_total.
+
+Extra keys: `e2e` (same metric through the public API from HOST buffers: H2D grid upload + majorant/brick-max +
+shadow-volume rebuild + render + D2H of the image inside the timed region), `roofline` (the tracker kernel against
+the measured HBM peak, algorithmic bytes = 32 B x (tracking steps + collisions) + 32 B per path, counted by the
+kernel), `sv` (shadow-volume rebuild ms and GB/s), `cpu_baseline` (the CPU oracle on a bounded sample of the same
+workload), `clocks`, `gpu_launches`, `parity`.
+
+--impl reference times the reference's CPU restatement (oracle/, OpenMP on all host cores) on the same config:
+the reference's own SPIR-V/lavapipe path cannot exist in this image (no Vulkan loader, glslc or .spv).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mpath-samples/s"
+
+
+def _peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# =============================================================================================================
+# reference arm / cpu_baseline: the CPU oracle (the ONLY code here allowed to touch oracle/)
+# =============================================================================================================
+def _oracle_scene(wl, log):
+    """Host-side scene for the oracle with NO product code: grid from the oracle's generator, parameter structs from
+    the reference's own setters (oracle/_ref shim) + the restated SetCloudProperties, shadow volume from the oracle."""
+    from tests import oracle_binding as orc
+    t0 = time.perf_counter()
+    cloud = orc.fbm_generate(wl.n_cloud, wl.fbm_seed)
+    log(f"[reference] fBm {wl.n_cloud}^3 generated on {orc.max_threads()} threads in {time.perf_counter() - t0:.1f}s")
+    cam, cp, par, sp = orc.reference_scene_structs(wl.n_cloud, wl.width, wl.height, wl.fov, wl.n_sv, wl.light_dir,
+                                                   wl.density_scaling, wl.phase_g, float(cloud.max()))
+    return orc, cloud, cam, cp, par, sp
+
+
+def _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seed, rows):
+    """one bounded sample: every `rows`-th image row of one frame; returns (paths, seconds)"""
+    pc = orc.push_constants_bytes(seed, 0)
+    t0 = time.perf_counter()
+    paths, _, _ = orc.path_trace_rows(cloud, sv, cam, cp, par, sp, pc, wl.absorption, rows)
+    return paths, time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    log = lambda s: print(s, file=sys.stderr, flush=True)
+    orc, cloud, cam, cp, par, sp = _oracle_scene(wl, log)
+    t0 = time.perf_counter()
+    sv = orc.shadow_volume(cloud, cp, sp)
+    sv_s = time.perf_counter() - t0
+    log(f"[reference] shadow volume {wl.n_sv}^3 on the CPU: {sv_s:.1f}s")
+    seeds = orc.msvc_rand(args.steps + args.warmup)
+    # size the per-step sample to ~2 s of CPU work from a probe of every 64th row
+    p, s = _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seeds[0], 64)
+    rate = p / s
+    rows = max(1, int(round(wl.height / max(1.0, (2.0 * rate) / wl.width))))
+    for i in range(args.warmup):
+        _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seeds[i], rows)
+    paths, secs = 0, 0.0
+    for i in range(args.steps):
+        p, s = _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seeds[args.warmup + i], rows)
+        paths += p
+        secs += s
+    value = paths / secs / 1e6
+    sample = f"every {rows}th image row of one {wl.width}x{wl.height} frame per step ({paths // args.steps} paths/step)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config_dict(wl, args, 1, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "Mpath-samples/s", "cores": orc.max_threads(), "kind": "port",
+                         "sample": sample, "sv_build_s": sv_s,
+                         "note": "CPU restatement of the shaders (lavapipe / SPIR-V unavailable in this image)"},
+        "e2e": {"value": value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def _config_dict(wl, args, world, layout):
+    return {"workload": f"{wl.name}: {wl.n_cloud}^3 fBm cloud, {wl.width}x{wl.height}, {wl.spp} spp/GPU, "
+                        f"densityScaling {wl.density_scaling:g}, absorption {wl.absorption:g}, "
+                        f"g {wl.phase_g if wl.phase_g is not None else 'isotropic'}, N_sv {wl.n_sv}",
+            "spp_total": wl.spp * world, "parallelism": f"spp-split x{world} (grid replicated, fp32 sum all-reduce)",
+            "layout": layout,
+            "l2": "inputs larger than L2 (grid + shadow volume >= 1 GB vs 126 MB)"}
+
+
+# =============================================================================================================
+# our arm
+# =============================================================================================================
+def run_ours(args, wl):
+    import torch
+
+    import cloudrendering_vulkan_b200 as crv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+    log = (lambda s: print(s, file=sys.stderr, flush=True)) if rank == 0 else (lambda s: None)
+
+    ctx = crv.Context(local)
+    W, H, spp = wl.width, wl.height, wl.spp
+    r = crv.make_renderer(ctx, wl, cloud_layout=args.layout)
+    # accumulation buffer owned by torch so that NCCL can reduce it in place
+    accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    img = crv.Image(ctx, W, H, device_ptr=accum.data_ptr())
+    r.resultImage.close()
+    r.resultImage = img
+    r.pathTracingTechnique.SetFrameReferences([img])
+    if args.track_threshold or args.ctas_per_sm:
+        r.pathTracingTechnique.SetTuning(ctas_per_sm=args.ctas_per_sm, track_threshold=args.track_threshold)
+    r.set_cloud_synthetic(wl.n_cloud, wl.fbm_seed, stream)
+    ctx.synchronize(stream)
+    sv_ms = r.shadowVolumeTechnique.last_build_ms()
+
+    all_seeds = crv.msvc_rand_sequence(spp * world)
+    my_seeds = np.ascontiguousarray(all_seeds[rank::world])          # frame f -> rank f mod world
+    mode = crv.ACCUM_RUNNING_MEAN if world == 1 else crv.ACCUM_SUM
+    pt = r.pathTracingTechnique
+
+    def step():
+        img.clear(stream)
+        pt.RenderBatch(my_seeds, 0, mode, stream, 0)
+        if world > 1:
+            dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+            img.scale(1.0 / (spp * world), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    pt.ResetStats(stream)
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    st = pt.GetStats(stream)
+    k_ms, k_n = pt.LastRenderMs()          # tracker launches of the LAST step (events on the launching stream)
+    if world > 1:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+        cnt = torch.tensor([st.paths, st.tracking_steps, st.collisions, st.density_fetches, launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        tot_paths, tot_steps, tot_coll, tot_fetch, launches = [float(x) for x in cnt.tolist()]
+    else:
+        tot_paths, tot_steps, tot_coll, tot_fetch = float(st.paths), float(st.tracking_steps), float(st.collisions), float(st.density_fetches)
+    ms_per_step = dev_ms / args.steps
+    paths_per_step = W * H * spp * world
+    value = paths_per_step / (ms_per_step * 1e-3) / 1e6
+    assert abs(tot_paths - paths_per_step * args.steps) < 0.5, "kernel path counter disagrees with the workload size"
+
+    # ---- roofline of the dominant kernel (the tracker), this rank, last step ----
+    peak, peak_src = _peak()
+    alg_bytes_rank = (32.0 * (st.tracking_steps + st.collisions) + 32.0 * st.paths) / args.steps
+    achieved = alg_bytes_rank / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pt_wavefront_kernel_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "pt_wavefront_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_rank / max(1, k_n), "launches_per_step": k_n,
+                "kernel_ms_per_step": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "steps_per_path": tot_steps / tot_paths, "collisions_per_path": tot_coll / tot_paths,
+                "fetch_fraction": tot_fetch / max(1.0, tot_steps)}
+    sv_bytes = 4.0 * wl.n_sv ** 3 + 4.0 * wl.n_cloud ** 3
+
+    line = None
+    e2e = None
+    parity = None
+    cpu_baseline = None
+    # ---- e2e: host buffers in, host image out (rank-local inputs; all ranks take part in the reduce) ----
+    if not args.no_e2e:
+        host_grid = torch.empty(wl.n_cloud ** 3, dtype=torch.float32).pin_memory()
+        host_img = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        host_grid.numpy()[:] = r.cloudImage.download(stream)      # filled once, outside the timed region
+        hg = host_grid.numpy()
+        hi = host_img.numpy()
+
+        def e2e_step():
+            r.cloudImage.upload(hg, stream)                                   # H2D: the density grid
+            r.SetCloudProperties((wl.n_cloud,) * 3, (1.0 / wl.n_cloud,) * 3, r.cloudImage.majorant(stream))
+            r.UpdateCloudData(stream)                                         # descriptor updates + shadow-volume rebuild
+            pt.RenderBatch(my_seeds, 0, mode, stream, 0)
+            if world > 1:
+                dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+                img.scale(1.0 / (spp * world), stream)
+            img.download(stream, out=hi)                                      # D2H: the result image
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": paths_per_step / e2e_s / 1e6, "unit": "Mpath-samples/s", "h2d_bytes_per_step": int(4 * wl.n_cloud ** 3 + 68 + 60 + 28 + 152 + 24),
+               "d2h_bytes_per_step": int(W * H * 16), "ms_per_step": e2e_s * 1e3,
+               "includes": "pinned-host grid upload, majorant + brick-max, shadow-volume rebuild, render, reduce, image download"}
+
+    # ---- rank 0, N = 1: bounded CPU-oracle baseline + parity of a sample of the same workload ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_binding as orc
+        cloud_h = r.cloudImage.download(stream)
+        sv_h = r.shadowVolumeImage.download(stream)
+        seeds = crv.msvc_rand_sequence(2)
+        p, s = _oracle_rows_step(orc, cloud_h, sv_h, r.cameraProperties, r.cloudProperties, r.parameters,
+                                 r.shadowVolumeProperties, wl, seeds[0], 64)
+        rows = max(1, int(round(H / max(1.0, (12.0 * p / s) / W))))
+        p, s = _oracle_rows_step(orc, cloud_h, sv_h, r.cameraProperties, r.cloudProperties, r.parameters,
+                                 r.shadowVolumeProperties, wl, seeds[1], rows)
+        cpu_baseline = {"value": p / s / 1e6, "unit": "Mpath-samples/s", "cores": orc.max_threads(), "kind": "port",
+                        "sample": f"every {rows}th image row of one {W}x{H} frame ({p} paths, {s:.1f} s)",
+                        "note": "CPU restatement of the shaders (lavapipe / SPIR-V unavailable in this image)"}
+        # parity of one frame's rows against the GPU (same seed, single dispatch)
+        r.reset_accumulation(stream)
+        pt.SetDebugCounters(True)
+        r.pushConstants.seed = int(seeds[1])
+        pt.RecordDrawCommands(stream, 0)
+        g_img = img.download(stream)
+        gs, gc = pt.DownloadDebugCounters(stream)
+        pc = crv.PushConstants(); pc.seed = int(seeds[1]); pc.frameCount = 0
+        ys = list(range(0, H, max(rows, 8)))
+        n_same = n_tot = 0
+        max_err = 0.0
+        for y in ys:
+            c_img = np.zeros((H, W, 4), np.float32)
+            _, cs, cc = orc.path_trace_frame(cloud_h, sv_h, r.cameraProperties, r.cloudProperties, r.parameters,
+                                             r.shadowVolumeProperties, pc, wl.absorption, c_img, rect=(0, y, W, y + 1))
+            same = (gs[y] == cs[y]) & (gc[y] == cc[y])
+            err = np.abs(g_img[y] - c_img[y]) / np.maximum(np.abs(c_img[y]), 1e-3)
+            n_same += int(same.sum()); n_tot += W
+            if same.any():
+                max_err = max(max_err, float(err[same].max()))
+        parity = {"checked_paths": n_tot, "threshold_divergent": n_tot - n_same, "max_rel_err_matching": max_err,
+                  "tolerance": 1e-4}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config_dict(wl, args, world, args.layout),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "sv": {"rebuild_ms": sv_ms, "algorithmic_bytes": sv_bytes, "achieved_gbs": sv_bytes / sv_ms / 1e6,
+                   "frac_of_peak": sv_bytes / sv_ms / 1e6 / peak},
+            "cpu_baseline": cpu_baseline, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--layout", default="linear", choices=["linear", "brick", "tex3d"])
+    ap.add_argument("--spp", type=int, default=0, help="override spp per GPU (the default is the config's)")
+    ap.add_argument("--track-threshold", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    from cloudrendering_vulkan_b200.scene import CONFIGS
+    import dataclasses
+    wl = CONFIGS[args.config]
+    if args.spp:
+        wl = dataclasses.replace(wl, spp=args.spp)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and world != args.gpus and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})", file=sys.stderr)
+        return 2
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    return run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

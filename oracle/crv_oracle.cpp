@@ -319,7 +319,8 @@ bool findScatterPoint(const float* vol, const Cloud& cp, Rng& rng, Ray& ray, Cou
         const float zeta = rng.generateRandomNumber();
         ++cnt.steps;
         t += (-std::log(zeta)) / sigma;
-        if (t >= dist) return false;                       // left the cloud
+        if (!(t < dist)) return false;                     // `t >= dist` (:339): left the cloud.  A NaN also leaves
+                                                           // (the shader would spin forever on it)
 
         currentPoint = ray.pos + t * ray.dir;
         const float extinction = sampleCloud(vol, cp, currentPoint);
@@ -377,7 +378,8 @@ vec4 tracePixel(const float* vol, const float* sv, const Camera& cam, const Clou
 
 void trace_rect(const float* vol, const float* sv, const void* camera68, const void* cloud60, const void* params28,
                 const void* svprops152, const void* push24, float absorption, int accum_sum, int x0, int y0, int x1,
-                int y1, float* image, float* sample, uint32_t* steps, uint32_t* collisions, int num_threads)
+                int y1, float* image, float* sample, uint32_t* steps, uint32_t* collisions, int num_threads,
+                int row_step = 1)
 {
     const Camera cam = load_camera(camera68);
     const Cloud cp = load_cloud(cloud60);
@@ -390,30 +392,33 @@ void trace_rect(const float* vol, const float* sv, const void* camera68, const v
     if (y0 < 0) y0 = 0;
     if (x1 > W) x1 = W;
     if (y1 > H) y1 = H;
+    if (row_step < 1) row_step = 1;
+    const int rw = x1 - x0, rh = (y1 - y0 + row_step - 1) / row_step;     // rows y0, y0+row_step, ...
+    if (rw <= 0 || rh <= 0) return;
+    const int64_t count = static_cast<int64_t>(rw) * rh;
 #ifdef _OPENMP
     if (num_threads <= 0) num_threads = omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads)
+#pragma omp parallel for schedule(dynamic, 64) num_threads(num_threads)
 #endif
-    for (int y = y0; y < y1; ++y) {
-        for (int x = x0; x < x1; ++x) {
-            Counters cnt;
-            const vec4 r = tracePixel(vol, sv, cam, cp, par, sp, pc.seed, absorption, (uint32_t)x, (uint32_t)y, ngx, cnt);
-            const size_t p = static_cast<size_t>(y) * W + x;
-            if (sample) { sample[4 * p] = r.x; sample[4 * p + 1] = r.y; sample[4 * p + 2] = r.z; sample[4 * p + 3] = r.w; }
-            if (steps) steps[p] = cnt.steps;
-            if (collisions) collisions[p] = cnt.collisions;
-            if (image) {
-                float* px = image + 4 * p;
-                const float in[4] = {r.x, r.y, r.z, r.w};
-                for (int c = 0; c < 4; ++c) {
-                    if (accum_sum) {
-                        px[c] = px[c] + in[c];
-                    } else {
-                        // :420-424  result += old * frameCount; result /= frameCount + 1
-                        float v = in[c] + px[c] * static_cast<float>(pc.frameCount);
-                        v = v / static_cast<float>(pc.frameCount + 1u);
-                        px[c] = v;
-                    }
+    for (int64_t idx = 0; idx < count; ++idx) {
+        const int x = x0 + static_cast<int>(idx % rw), y = y0 + static_cast<int>(idx / rw) * row_step;
+        Counters cnt;
+        const vec4 r = tracePixel(vol, sv, cam, cp, par, sp, pc.seed, absorption, (uint32_t)x, (uint32_t)y, ngx, cnt);
+        const size_t p = static_cast<size_t>(y) * W + x;
+        if (sample) { sample[4 * p] = r.x; sample[4 * p + 1] = r.y; sample[4 * p + 2] = r.z; sample[4 * p + 3] = r.w; }
+        if (steps) steps[p] = cnt.steps;
+        if (collisions) collisions[p] = cnt.collisions;
+        if (image) {
+            float* px = image + 4 * p;
+            const float in[4] = {r.x, r.y, r.z, r.w};
+            for (int c = 0; c < 4; ++c) {
+                if (accum_sum) {
+                    px[c] = px[c] + in[c];
+                } else {
+                    // :420-424  result += old * frameCount; result /= frameCount + 1
+                    float v = in[c] + px[c] * static_cast<float>(pc.frameCount);
+                    v = v / static_cast<float>(pc.frameCount + 1u);
+                    px[c] = v;
                 }
             }
         }
@@ -601,6 +606,15 @@ void orc_path_trace_rect(const float* cloud, const float* sv, const void* camera
                sample, steps, collisions, num_threads);
 }
 
+// every row_step-th row of the image (bounded, unbiased sample of a frame for the CPU baseline)
+void orc_path_trace_rows(const float* cloud, const float* sv, const void* camera68, const void* cloud60,
+                         const void* params28, const void* svprops152, const void* push24, float absorption,
+                         int row_step, float* image, float* sample, uint32_t* steps, uint32_t* collisions, int num_threads)
+{
+    trace_rect(cloud, sv, camera68, cloud60, params28, svprops152, push24, absorption, 0, 0, 0, 1 << 30, 1 << 30, image,
+               sample, steps, collisions, num_threads, row_step);
+}
+
 void orc_fbm_generate(uint32_t n, uint32_t seed, float* out, int num_threads)
 {
 #ifdef _OPENMP
@@ -620,6 +634,44 @@ int orc_max_threads(void)
 #else
     return 1;
 #endif
+}
+
+}  // extern "C"
+
+// ---- host-side scene setup that lives in main.cpp rather than in the headers (restated for the reference arm) ----
+extern "C" {
+
+// SetCloudProperties (main.cpp:144-163) on a default CloudProperties (UniformBuffers.h:71-78) with the given
+// densityScaling: size = voxelSize * count * baseScaling (double, narrowed to float), box centred in x/y on z = 0.
+void orc_set_cloud_properties(const uint32_t counts[3], const double voxel_size[3], float majorant, float density_scaling,
+                              void* out60)
+{
+    const float base_scaling = 1000.0f;
+    float size[3];
+    for (int i = 0; i < 3; ++i) size[i] = static_cast<float>(voxel_size[i] * counts[i] * base_scaling);
+    float b0[4] = {-size[0] / 2, -size[1] / 2, 0.0f, 0.0f};
+    const float add[4] = {0.0f, 0.0f, size[2], 0.0f};
+    float b1[4];
+    for (int i = 0; i < 4; ++i) b1[i] = -b0[i] + add[i];
+    const uint32_t vc[4] = {counts[0], counts[1], counts[2], 0u};
+    const float max_ext = majorant > 0.01f ? majorant : 0.01f;
+    char* o = static_cast<char*>(out60);
+    std::memcpy(o, b0, 16);
+    std::memcpy(o + 16, b1, 16);
+    std::memcpy(o + 32, vc, 16);
+    std::memcpy(o + 48, &max_ext, 4);
+    std::memcpy(o + 52, &base_scaling, 4);
+    std::memcpy(o + 56, &density_scaling, 4);
+}
+
+// std::rand() of the MSVC runtime after srand(seed0): the per-frame seed source (main.cpp:722,949)
+void orc_msvc_rand(uint32_t seed0, uint32_t n, int32_t* out)
+{
+    uint32_t s = seed0;
+    for (uint32_t i = 0; i < n; ++i) {
+        s = s * 214013u + 2531011u;
+        out[i] = static_cast<int32_t>((s >> 16) & 0x7fffu);
+    }
 }
 
 }  // extern "C"

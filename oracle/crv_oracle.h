@@ -70,6 +70,12 @@ void orc_path_trace_rect(const float* cloud, const float* sv, const void* camera
                          int accum_sum, int x0, int y0, int x1, int y1, float* image, float* sample,
                          uint32_t* steps, uint32_t* collisions, int num_threads);
 
+/* same, for rows 0, row_step, 2*row_step, ... of the image (bounded, unbiased sample of one frame) */
+void orc_path_trace_rows(const float* cloud, const float* sv, const void* camera68, const void* cloud60,
+                         const void* params28, const void* svprops152, const void* push24, float absorption,
+                         int row_step, float* image, float* sample, uint32_t* steps, uint32_t* collisions,
+                         int num_threads);
+
 /* ---- synthetic fBm cloud (frozen generator, see oracle/crv_oracle.cpp) ---- */
 void orc_fbm_generate(uint32_t n, uint32_t seed, float* out_xfastest, int num_threads);
 
@@ -78,4 +84,14 @@ int orc_max_threads(void);
 #ifdef __cplusplus
 }
 #endif
+#endif
+
+/* ---- scene setup that lives in main.cpp (used by the reference arm of bench.py) ---- */
+#ifdef __cplusplus
+extern "C" {
+#endif
+void orc_set_cloud_properties(const uint32_t counts[3], const double voxel_size[3], float majorant, float density_scaling, void* out60); /* main.cpp:144-163 */
+void orc_msvc_rand(uint32_t seed0, uint32_t n, int32_t* out);   /* main.cpp:722,949 */
+#ifdef __cplusplus
+}
 #endif

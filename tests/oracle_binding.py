@@ -54,6 +54,7 @@ lib.orc_shadow_volume.argtypes = [_vp, _vp, _vp, _vp, C.c_int]
 lib.orc_path_trace_frame.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, C.c_int, _vp, _vp, _vp, _vp, C.c_int]
 lib.orc_path_trace_rect.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     _vp, _vp, _vp, _vp, C.c_int]
+lib.orc_path_trace_rows.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, C.c_int, _vp, _vp, _vp, _vp, C.c_int]
 lib.orc_fbm_generate.argtypes = [_u32, _u32, _vp, C.c_int]
 lib.orc_max_threads.restype = C.c_int
 
@@ -147,18 +148,30 @@ def scatter_ray(params, rng_state, incoming):
 
 
 def shadow_volume(cloud, cloud_props, sv_props, threads=0):
-    n = sv_props.voxelAxisCount
+    n = int(np.frombuffer(bytes(sv_props), np.uint32, 1, 144)[0])
     v = np.ascontiguousarray(cloud, np.float32)
     out = np.empty(n * n * n, np.float32)
     lib.orc_shadow_volume(_ptr(v), _raw(cloud_props), _raw(sv_props), _ptr(out), threads)
     return out
 
 
+def path_trace_rows(cloud, sv, cam, cloud_props, params, sv_props, push, absorption, row_step, image=None,
+                    want_counters=False, threads=0):
+    """Rows 0, row_step, ... of one frame in ONE call (cloud/sv must already be contiguous float32).
+    Returns (n_paths, steps, collisions); counters are None unless requested."""
+    w, h = image_size(cam)
+    steps = np.zeros((h, w), np.uint32) if want_counters else None
+    coll = np.zeros((h, w), np.uint32) if want_counters else None
+    lib.orc_path_trace_rows(_ptr(cloud), _ptr(sv), _raw(cam), _raw(cloud_props), _raw(params), _raw(sv_props), _raw(push),
+                            absorption, int(row_step), _ptr(image), None, _ptr(steps), _ptr(coll), threads)
+    return w * len(range(0, h, int(row_step))), steps, coll
+
+
 def path_trace_frame(cloud, sv, cam, cloud_props, params, sv_props, push, absorption, image, accum_sum=0,
                      want_sample=True, threads=0, rect=None):
     """One dispatch of PathTracer.comp on the CPU. `image` (H,W,4) is updated in place.
     Returns (sample, steps, collisions)."""
-    w, h = cam.halfWidth * 2, cam.halfHeight * 2
+    w, h = image_size(cam)
     v = np.ascontiguousarray(cloud, np.float32)
     s = np.ascontiguousarray(sv, np.float32)
     sample = np.zeros((h, w, 4), np.float32) if want_sample else None
@@ -187,3 +200,53 @@ def ref_structs_lib():
     if not os.path.exists(REF_LIB_PATH):
         return None
     return C.CDLL(REF_LIB_PATH)
+
+
+# ---- scene setup without any product code: reference headers (oracle/_ref) + main.cpp restatements ----------
+lib.orc_set_cloud_properties.argtypes = [C.POINTER(_u32), C.POINTER(C.c_double), _f, _f, _vp]
+lib.orc_msvc_rand.argtypes = [_u32, _u32, _vp]
+
+
+class RawStruct(C.Structure):
+    """a parameter block as raw bytes (what the UBO holds); the oracle reads it at the shaders' offsets"""
+    pass
+
+
+def _raw_buf(nbytes):
+    return (C.c_ubyte * nbytes)()
+
+
+def msvc_rand(n, seed0=0):
+    out = np.empty(n, np.int32)
+    lib.orc_msvc_rand(seed0, n, _ptr(out))
+    return out
+
+
+def image_size(cam):
+    b = bytes(cam)
+    return 2 * int(np.frombuffer(b, np.int32, 1, 12)[0]), 2 * int(np.frombuffer(b, np.int32, 1, 28)[0])
+
+
+def push_constants_bytes(seed, frame_count):
+    import struct
+    return (C.c_ubyte * 24).from_buffer_copy(struct.pack("<diIfI", 0.0, int(seed), int(frame_count), 0.0, 0))
+
+
+def reference_scene_structs(n_cloud, width, height, fov, n_sv, light, density_scaling, phase_g, majorant):
+    """(camera68, cloud60, params28, shadow152) byte buffers made by the REFERENCE's own setters (oracle/_ref) and the
+    restated SetCloudProperties; raises if the shim was never built."""
+    ref = ref_structs_lib()
+    if ref is None:
+        raise RuntimeError("oracle/_ref/libcrv_refstructs.so missing: run `make -C oracle` where /root/reference exists")
+    cam = _raw_buf(68)
+    f = C.c_float(fov)
+    ref.ref_camera(1, int(width), int(height), 0, (C.c_float * 2)(0, 0), 1, C.byref(f), cam)
+    cloud = _raw_buf(60)
+    lib.orc_set_cloud_properties((_u32 * 3)(n_cloud, n_cloud, n_cloud), (C.c_double * 3)(*([1.0 / n_cloud] * 3)),
+                                 _f(majorant), _f(density_scaling), cloud)
+    par = _raw_buf(28)
+    ref.ref_parameters(0 if phase_g is None else 1, C.c_float(phase_g or 0.0), par)
+    b = np.frombuffer(bytes(cloud), np.float32)
+    sh = _raw_buf(152)
+    ref.ref_shadow(int(n_sv), 1, _f3(light), 1, _f3(b[0:3]), _f3(b[4:7]), sh)
+    return cam, cloud, par, sh

@@ -101,7 +101,7 @@ def test_shadow_volume_nonuniform_grid(crv, orc, ctx):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def _frame_parity(crv, orc, r, cloud, seed, absorption, min_match=0.99):
+def _frame_parity(crv, orc, r, cloud, seed, absorption, min_match=0.99, expect_misses=True):
     sv_cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
     r.reset_accumulation()
     r.pathTracingTechnique.SetDebugCounters(True)
@@ -122,7 +122,8 @@ def _frame_parity(crv, orc, r, cloud, seed, absorption, min_match=0.99):
           f"max rel err on matching paths {err[same].max():.2e}; mean steps {cs.mean():.1f}, collisions {cc.mean():.2f}")
     assert same.mean() >= min_match, f"too many divergent paths: {divergent}/{same.size}"
     assert err[same].max() <= 1e-4
-    assert cc.max() > 0 and (cs == 0).any(), "scene must contain both scattering paths and misses"
+    assert cc.max() > 0, "scene must contain scattering paths"
+    assert (cs == 0).any() or not expect_misses, "scene must contain misses"
     return divergent, same.size
 
 
@@ -147,7 +148,7 @@ def test_pt_camera_inside_cloud_and_zero_density(crv, orc, ctx):
     # camera inside the box: entry point moves BACKWARDS to tmin (PathTracer.comp:387)
     r.cameraProperties.position[0], r.cameraProperties.position[1], r.cameraProperties.position[2] = 10.0, -20.0, 480.0
     r.apply_parameters()
-    _frame_parity(crv, orc, r, cloud, 8855, 0.0, min_match=0.98)
+    _frame_parity(crv, orc, r, cloud, 8855, 0.0, min_match=0.98, expect_misses=False)
     # densityScaling <= 0: every pixel is pure background (PathTracer.comp:379)
     r.cloudProperties.densityScaling = 0.0
     r.apply_parameters()
