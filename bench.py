@@ -113,11 +113,35 @@ def _oracle_scene(wl, log):
 
 
 def _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seed, rows):
-    """one bounded sample: every `rows`-th image row of one frame; returns (paths, seconds)"""
+    """every `rows`-th image row of one frame; returns (paths, seconds)"""
     pc = orc.push_constants_bytes(seed, 0)
     t0 = time.perf_counter()
     paths, _, _ = orc.path_trace_rows(cloud, sv, cam, cp, par, sp, pc, wl.absorption, rows)
     return paths, time.perf_counter() - t0
+
+
+def _oracle_plan(orc, cloud, sv, cam, cp, par, sp, wl, seed, target_s):
+    """size a bounded sample of the workload worth ~target_s seconds of CPU time: (frames, row_step)"""
+    p, s = _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seed, 16)
+    frame_s = s * (wl.width * wl.height) / p
+    if frame_s >= target_s:
+        return 1, max(1, int(round(frame_s / target_s)))
+    return max(1, int(round(target_s / frame_s))), 1
+
+
+def _oracle_sample(orc, cloud, sv, cam, cp, par, sp, wl, seeds, frames, rows):
+    """`frames` frames (seeds[0..frames)), every `rows`-th row of each: (paths, seconds)"""
+    paths, secs = 0, 0.0
+    for f in range(frames):
+        p, s = _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seeds[f % len(seeds)], rows)
+        paths += p
+        secs += s
+    return paths, secs
+
+
+def _sample_text(wl, frames, rows, paths, secs):
+    what = "all rows" if rows == 1 else f"every {rows}th image row"
+    return f"{what} of {frames} {wl.width}x{wl.height} frame(s) of this workload ({paths} path samples, {secs:.1f} s)"
 
 
 def run_reference(args, wl):
@@ -130,20 +154,18 @@ def run_reference(args, wl):
     sv = orc.shadow_volume(cloud, cp, sp)
     sv_s = time.perf_counter() - t0
     log(f"[reference] shadow volume {wl.n_sv}^3 on the CPU: {sv_s:.1f}s")
-    seeds = orc.msvc_rand(args.steps + args.warmup)
-    # size the per-step sample to ~2 s of CPU work from a probe of every 64th row
-    p, s = _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seeds[0], 64)
-    rate = p / s
-    rows = max(1, int(round(wl.height / max(1.0, (2.0 * rate) / wl.width))))
+    seeds = orc.msvc_rand(256)
+    # each step is a bounded sample of ~3 s of CPU work on all host cores
+    frames, rows = _oracle_plan(orc, cloud, sv, cam, cp, par, sp, wl, seeds[0], 3.0)
     for i in range(args.warmup):
-        _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seeds[i], rows)
+        _oracle_sample(orc, cloud, sv, cam, cp, par, sp, wl, seeds, 1, max(rows, 4))
     paths, secs = 0, 0.0
     for i in range(args.steps):
-        p, s = _oracle_rows_step(orc, cloud, sv, cam, cp, par, sp, wl, seeds[args.warmup + i], rows)
+        p, s = _oracle_sample(orc, cloud, sv, cam, cp, par, sp, wl, np.roll(seeds, -i * frames), frames, rows)
         paths += p
         secs += s
     value = paths / secs / 1e6
-    sample = f"every {rows}th image row of one {wl.width}x{wl.height} frame per step ({paths // args.steps} paths/step)"
+    sample = "per step: " + _sample_text(wl, frames, rows, paths // args.steps, secs / args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
@@ -314,14 +336,12 @@ def run_ours(args, wl):
         from tests import oracle_binding as orc
         cloud_h = r.cloudImage.download(stream)
         sv_h = r.shadowVolumeImage.download(stream)
-        seeds = crv.msvc_rand_sequence(2)
-        p, s = _oracle_rows_step(orc, cloud_h, sv_h, r.cameraProperties, r.cloudProperties, r.parameters,
-                                 r.shadowVolumeProperties, wl, seeds[0], 64)
-        rows = max(1, int(round(H / max(1.0, (12.0 * p / s) / W))))
-        p, s = _oracle_rows_step(orc, cloud_h, sv_h, r.cameraProperties, r.cloudProperties, r.parameters,
-                                 r.shadowVolumeProperties, wl, seeds[1], rows)
+        seeds = crv.msvc_rand_sequence(256)
+        oargs = (orc, cloud_h, sv_h, r.cameraProperties, r.cloudProperties, r.parameters, r.shadowVolumeProperties, wl)
+        frames, rows = _oracle_plan(*oargs, seeds[0], 12.0)
+        p, s = _oracle_sample(*oargs, seeds, frames, rows)
         cpu_baseline = {"value": p / s / 1e6, "unit": "Mpath-samples/s", "cores": orc.max_threads(), "kind": "port",
-                        "sample": f"every {rows}th image row of one {W}x{H} frame ({p} paths, {s:.1f} s)",
+                        "sample": _sample_text(wl, frames, rows, p, s),
                         "note": "CPU restatement of the shaders (lavapipe / SPIR-V unavailable in this image)"}
         # parity of one frame's rows against the GPU (same seed, single dispatch)
         r.reset_accumulation(stream)
