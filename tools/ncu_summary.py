@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Summarise ncu output brought back in gpurun_out/ into small text files under profiles/ (tracked).
+
+  tools/ncu_summary.py launches gpurun_out/<tag>_launches.csv  > profiles/<tag>_launches.txt
+  tools/ncu_summary.py full     gpurun_out/<tag>_pt.ncu-rep    > profiles/<tag>_pt_ncu.txt
+  tools/ncu_summary.py source   gpurun_out/<tag>_pt.ncu-rep [N] > profiles/<tag>_pt_source.txt   (top-N lines by samples)
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__cycles_active.avg",
+    "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
+    "sm__inst_executed_pipe_lsu.sum",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in data:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
+        a = agg.setdefault(r[ki], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {tot / 1e3:.2f} ms of kernel time (ncu: cold-cache, serialised)")
+    print(f"{'n':>5} {'total_us':>12} {'avg_us':>10} {'share':>7}  kernel")
+    for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+        print(f"{a[0]:5d} {a[1]:12.1f} {a[1] / a[0]:10.1f} {100 * a[1] / tot:6.2f}%  {k}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    h, u = rows[0], rows[1]
+    for v in rows[2:]:
+        print(f"# {path}: {v[h.index('Kernel Name')]}  (ncu --set full --clock-control none)")
+        for w in WANT:
+            if w in h:
+                i = h.index(w)
+                print(f"{w:82s} {v[i]:>18s} {u[i]}")
+        if "dram__bytes_read.sum" in h:
+            def b(name):
+                i = h.index(name)
+                x = float(v[i].replace(",", ""))
+                return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u[i]]
+            print(f"{'traffic = dram__bytes_read.sum + dram__bytes_write.sum':82s} {b('dram__bytes_read.sum') + b('dram__bytes_write.sum'):18.0f} byte")
+
+
+def source(path, top=40):
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr_i = [i for i, r in enumerate(rows) if "Source" in r and any("Samples" in c for c in r)]
+    if not hdr_i:
+        print("no source page")
+        return
+    h = rows[hdr_i[0]]
+    si = [i for i, c in enumerate(h) if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)"]
+    si = si[0] if si else None
+    src = h.index("Source")
+    data = [r for r in rows[hdr_i[0] + 1:] if len(r) == len(h)]
+    def num(x):
+        try:
+            return float(x.replace(",", ""))
+        except Exception:
+            return 0.0
+    tot = sum(num(r[si]) for r in data) or 1.0
+    print(f"# {path}: top {top} source lines by warp-stall samples ({int(tot)} samples)")
+    for r in sorted(data, key=lambda r: -num(r[si]))[:top]:
+        print(f"{100 * num(r[si]) / tot:6.2f}%  {r[src][:150]}")
+
+
+if __name__ == "__main__":
+    mode, path = sys.argv[1], sys.argv[2]
+    if mode == "launches":
+        launches(path)
+    elif mode == "full":
+        full(path)
+    else:
+        source(path, int(sys.argv[3]) if len(sys.argv) > 3 else 40)
