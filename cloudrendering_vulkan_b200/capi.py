@@ -115,6 +115,8 @@ SIGNATURES = {
     "crv_sv_update_descriptor_sets": (C.c_int, [_vp]),
     "crv_sv_record_draw_commands": (C.c_int, [_vp, _vp, C.c_uint]),
     "crv_sv_last_build_ms": (C.c_int, [_vp, _P(C.c_float)]),
+    "crv_sv_set_tuning": (C.c_int, [_vp, C.c_int]),
+    "crv_sv_last_build_mode": (C.c_int, [_vp, _P(C.c_int)]),
     "crv_pt_create": (C.c_int, [_vp, _P(CameraPropertiesPOD), _P(PushConstantsPOD), _P(_vp)]),
     "crv_pt_destroy": (C.c_int, [_vp]),
     "crv_pt_set_frame_references": (C.c_int, [_vp, _P(_vp), C.c_uint]),

@@ -60,6 +60,11 @@ struct crv_sv {
     crv_volume* out = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    float* dist_z = nullptr;         // accumulatedDistance after every slice (two-pass build), rcp_n entries
+    uint32_t rcp_n = 0;              // N the per-N buffers (dist_z, zrange) were sized for
+    ushort2* zrange = nullptr;       // per-column [z_in, z_end) of the two-pass build (rcp_n^2 entries)
+    int mode = CRV_SV_MODE_AUTO;     // crv_sv_mode
+    int last_mode = 0;
 };
 
 struct PTBindings {
@@ -476,6 +481,8 @@ int crv_sv_destroy(crv_sv* sv)
     cudaSetDevice(sv->ctx->device);
     if (sv->ev0) cudaEventDestroy(sv->ev0);
     if (sv->ev1) cudaEventDestroy(sv->ev1);
+    if (sv->dist_z) cudaFree(sv->dist_z);
+    if (sv->zrange) cudaFree(sv->zrange);
     delete sv;
     return CRV_OK;
 }
@@ -556,13 +563,51 @@ int crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned /*image_index
     c.cloud = sv->cloud_vol->view();
     c.out = sv->out->view();
     cudaStream_t s = as_stream(stream);
+    // fast-path extras: host-side IEEE reciprocals (this file is compiled without contraction / fast-math)
+    CRV_TRY(crv_sv_init_tables(sv->ctx));
+    if (sv->rcp_n != n) {
+        if (sv->dist_z) CRV_CUDA(cudaFree(sv->dist_z));
+        if (sv->zrange) CRV_CUDA(cudaFree(sv->zrange));
+        sv->dist_z = nullptr;
+        sv->zrange = nullptr;
+        sv->rcp_n = 0;
+        CRV_CUDA(cudaMalloc(&sv->zrange, sizeof(ushort2) * (size_t)n * n));
+        CRV_CUDA(cudaMalloc(&sv->dist_z, sizeof(float) * n));
+        sv->rcp_n = n;
+    }
+    if (!sv->cloud_vol->brick_max_valid) CRV_TRY(crv_launch_brick_max(sv->ctx, sv->cloud_vol, s));
+    for (int i = 0; i < 3; ++i) c.rcext[i] = 1.0f / c.cext[i];
+    c.rbase = 1.0f / c.base_scaling;
+    c.brick_absmax = sv->cloud_vol->brick_absmax;
+    c.dist_z = sv->dist_z;
+    c.search_iters = 1;
+    while ((1u << c.search_iters) < n + 1u) c.search_iters++;
+    c.zrange = sv->zrange;
+    int mode = sv->mode == CRV_SV_MODE_AUTO ? CRV_SV_MODE_TWO_PASS : sv->mode;
+    if (!crv_sv_fast_path_ok(c)) mode = CRV_SV_MODE_GENERIC;       // preconditions of the fast kernels not met
+    sv->last_mode = mode;
     CRV_CUDA(cudaEventRecord(sv->ev0, s));
-    CRV_TRY(crv_launch_sv_sweep(sv->ctx, c, sv->cloud_vol->layout, sv->out->layout, s));
+    CRV_TRY(crv_launch_sv_sweep(sv->ctx, c, sv->cloud_vol->layout, sv->out->layout, mode, s));
     CRV_CUDA(cudaEventRecord(sv->ev1, s));
     sv->timed = true;
     sv->out->brick_max_valid = false;
     sv->out->majorant_valid = false;
     vol_touch(sv->out);
+    return CRV_OK;
+}
+
+int crv_sv_set_tuning(crv_sv* sv, int mode)
+{
+    CRV_REQUIRE(sv != nullptr, "crv_sv_set_tuning: null technique");
+    CRV_REQUIRE(mode >= CRV_SV_MODE_AUTO && mode <= CRV_SV_MODE_TWO_PASS, "crv_sv_set_tuning: unknown mode");
+    sv->mode = mode;
+    return CRV_OK;
+}
+
+int crv_sv_last_build_mode(crv_sv* sv, int* out)
+{
+    CRV_REQUIRE(sv && out, "crv_sv_last_build_mode: null argument");
+    *out = sv->last_mode;
     return CRV_OK;
 }
 

@@ -54,30 +54,58 @@ struct VolView {
 
 template <int LAYOUT> struct VolAcc;
 
+// The element offset of voxel (i,j,k) is separable in both global layouts: off = off_x(i) + off_y(j) + off_z(k)
+// (< 2^32 elements, guaranteed by crv_volume_create), which lets the 8 texel addresses of a trilinear
+// footprint be formed from 6 per-axis terms and 12 adds instead of 8 full index computations.
 template <> struct VolAcc<CRV_LAYOUT_LINEAR> {
+    static __device__ __forceinline__ unsigned off_x(const VolView&, int i) { return (unsigned)i; }
+    static __device__ __forceinline__ unsigned off_y(const VolView& v, int j) { return (unsigned)j * (unsigned)v.nx; }
+    static __device__ __forceinline__ unsigned off_z(const VolView& v, int k) { return (unsigned)k * ((unsigned)v.nx * (unsigned)v.ny); }
+    // elements between slices k and k+1 while both lie in the same aligned group of 8 slices
+    static __device__ __forceinline__ unsigned z_step(const VolView& v) { return (unsigned)v.nx * (unsigned)v.ny; }
     static __device__ __forceinline__ size_t index(const VolView& v, int i, int j, int k)
     {
-        return static_cast<size_t>(static_cast<unsigned>(i) + static_cast<unsigned>(v.nx) * (static_cast<unsigned>(j) + static_cast<unsigned>(v.ny) * static_cast<unsigned>(k)));
+        return static_cast<size_t>(off_x(v, i) + off_y(v, j) + off_z(v, k));
     }
     static __device__ __forceinline__ float load(const VolView& v, int i, int j, int k) { return __ldg(v.data + index(v, i, j, k)); }
     static __device__ __forceinline__ void store(const VolView& v, int i, int j, int k, float val)
     {
         const_cast<float*>(v.data)[index(v, i, j, k)] = val;
     }
+    // write-once data that another kernel reads later: do not let it displace the sampled volume in L2
+    static __device__ __forceinline__ void store_streaming(const VolView& v, int i, int j, int k, float val)
+    {
+        __stcs(const_cast<float*>(v.data) + index(v, i, j, k), val);
+    }
+    // read of a volume this kernel also writes (coherent path, streaming)
+    static __device__ __forceinline__ float load_rw(const VolView& v, int i, int j, int k) { return __ldcs(v.data + index(v, i, j, k)); }
 };
 
 template <> struct VolAcc<CRV_LAYOUT_BRICK> {
+    static __device__ __forceinline__ unsigned off_x(const VolView&, int i) { return ((unsigned)(i >> CRV_BRICK_SHIFT) << 9) | (unsigned)(i & 7); }
+    static __device__ __forceinline__ unsigned off_y(const VolView& v, int j)
+    {
+        return (unsigned)(j >> CRV_BRICK_SHIFT) * ((unsigned)v.nbx << 9) + ((unsigned)(j & 7) << 3);
+    }
+    static __device__ __forceinline__ unsigned off_z(const VolView& v, int k)
+    {
+        return (unsigned)(k >> CRV_BRICK_SHIFT) * (((unsigned)v.nbx * (unsigned)v.nby) << 9) + ((unsigned)(k & 7) << 6);
+    }
+    static __device__ __forceinline__ unsigned z_step(const VolView&) { return 64u; }
     static __device__ __forceinline__ size_t index(const VolView& v, int i, int j, int k)
     {
-        const unsigned b = (static_cast<unsigned>(k >> CRV_BRICK_SHIFT) * v.nby + static_cast<unsigned>(j >> CRV_BRICK_SHIFT)) * v.nbx + static_cast<unsigned>(i >> CRV_BRICK_SHIFT);
-        const unsigned l = ((k & 7) << 6) | ((j & 7) << 3) | (i & 7);
-        return static_cast<size_t>(b) * CRV_BRICK_VOX + l;
+        return static_cast<size_t>(off_x(v, i) + off_y(v, j) + off_z(v, k));
     }
     static __device__ __forceinline__ float load(const VolView& v, int i, int j, int k) { return __ldg(v.data + index(v, i, j, k)); }
     static __device__ __forceinline__ void store(const VolView& v, int i, int j, int k, float val)
     {
         const_cast<float*>(v.data)[index(v, i, j, k)] = val;
     }
+    static __device__ __forceinline__ void store_streaming(const VolView& v, int i, int j, int k, float val)
+    {
+        __stcs(const_cast<float*>(v.data) + index(v, i, j, k), val);
+    }
+    static __device__ __forceinline__ float load_rw(const VolView& v, int i, int j, int k) { return __ldcs(v.data + index(v, i, j, k)); }
 };
 
 template <> struct VolAcc<CRV_LAYOUT_TEX3D> {
@@ -91,6 +119,11 @@ template <> struct VolAcc<CRV_LAYOUT_TEX3D> {
     {
         surf3Dwrite(val, v.surf, i * static_cast<int>(sizeof(float)), j, k);
     }
+    static __device__ __forceinline__ void store_streaming(const VolView& v, int i, int j, int k, float val) { store(v, i, j, k, val); }
+    static __device__ __forceinline__ float load_rw(const VolView& v, int i, int j, int k)
+    {
+        return surf3Dread<float>(v.surf, i * static_cast<int>(sizeof(float)), j, k);
+    }
 };
 
 // Integer texel footprint + weights of texture(sampler3D, s) with LINEAR / CLAMP_TO_EDGE
@@ -101,22 +134,30 @@ struct Footprint {
     float a, b, c;                // weights along x, y, z
 };
 
+// INSIDE = true: the caller guarantees 0 <= s <= 1 (so -1 <= floor(u) <= n-1) and the clamps shrink to one
+// max and one min; otherwise any float (NaN, +-inf, far outside) is handled.
+template <bool INSIDE = false>
 __device__ __forceinline__ void footprint_axis(float s, float fn, int n, int& i0c, int& i1c, float& a)
 {
     const float u = __fsub_rn(__fmul_rn(s, fn), 0.5f);
-    const float fu = floorf(u);
-    a = __fsub_rn(u, fu);
-    const int i0 = __float2int_rd(u);                 // saturating, NaN -> 0
-    i0c = min(max(i0, 0), n - 1);
-    i1c = max(min(i0, n - 2) + 1, 0);                 // clamp(i0 + 1, 0, n-1) without overflow
+    const int i0 = __float2int_rd(u);                 // floor; saturating, NaN -> 0
+    a = __fsub_rn(u, INSIDE ? (float)i0 : floorf(u));
+    if (INSIDE) {
+        i0c = max(i0, 0);
+        i1c = min(i0 + 1, n - 1);
+    } else {
+        i0c = min(max(i0, 0), n - 1);
+        i1c = max(min(i0, n - 2) + 1, 0);             // clamp(i0 + 1, 0, n-1) without overflow
+    }
 }
 
+template <bool INSIDE = false>
 __device__ __forceinline__ Footprint make_footprint(const VolView& v, float sx, float sy, float sz)
 {
     Footprint f;
-    footprint_axis(sx, v.fnx, v.nx, f.i0, f.i1, f.a);
-    footprint_axis(sy, v.fny, v.ny, f.j0, f.j1, f.b);
-    footprint_axis(sz, v.fnz, v.nz, f.k0, f.k1, f.c);
+    footprint_axis<INSIDE>(sx, v.fnx, v.nx, f.i0, f.i1, f.a);
+    footprint_axis<INSIDE>(sy, v.fny, v.ny, f.j0, f.j1, f.b);
+    footprint_axis<INSIDE>(sz, v.fnz, v.nz, f.k0, f.k1, f.c);
     return f;
 }
 
@@ -125,17 +166,9 @@ __device__ __forceinline__ float lerp_rn(float v0, float v1, float a)
     return __fadd_rn(v0, __fmul_rn(a, __fsub_rn(v1, v0)));      // v0 + a*(v1 - v0), never contracted
 }
 
-template <int LAYOUT>
-__device__ __forceinline__ float trilinear_fetch(const VolView& v, const Footprint& f)
+__device__ __forceinline__ float trilerp(const Footprint& f, float t000, float t100, float t010, float t110, float t001,
+                                         float t101, float t011, float t111)
 {
-    const float t000 = VolAcc<LAYOUT>::load(v, f.i0, f.j0, f.k0);
-    const float t100 = VolAcc<LAYOUT>::load(v, f.i1, f.j0, f.k0);
-    const float t010 = VolAcc<LAYOUT>::load(v, f.i0, f.j1, f.k0);
-    const float t110 = VolAcc<LAYOUT>::load(v, f.i1, f.j1, f.k0);
-    const float t001 = VolAcc<LAYOUT>::load(v, f.i0, f.j0, f.k1);
-    const float t101 = VolAcc<LAYOUT>::load(v, f.i1, f.j0, f.k1);
-    const float t011 = VolAcc<LAYOUT>::load(v, f.i0, f.j1, f.k1);
-    const float t111 = VolAcc<LAYOUT>::load(v, f.i1, f.j1, f.k1);
     const float x00 = lerp_rn(t000, t100, f.a);
     const float x10 = lerp_rn(t010, t110, f.a);
     const float x01 = lerp_rn(t001, t101, f.a);
@@ -143,6 +176,37 @@ __device__ __forceinline__ float trilinear_fetch(const VolView& v, const Footpri
     const float y0 = lerp_rn(x00, x10, f.b);
     const float y1 = lerp_rn(x01, x11, f.b);
     return lerp_rn(y0, y1, f.c);
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ float trilinear_fetch(const VolView& v, const Footprint& f)
+{
+    if constexpr (LAYOUT == CRV_LAYOUT_TEX3D) {
+        const float t000 = VolAcc<LAYOUT>::load(v, f.i0, f.j0, f.k0);
+        const float t100 = VolAcc<LAYOUT>::load(v, f.i1, f.j0, f.k0);
+        const float t010 = VolAcc<LAYOUT>::load(v, f.i0, f.j1, f.k0);
+        const float t110 = VolAcc<LAYOUT>::load(v, f.i1, f.j1, f.k0);
+        const float t001 = VolAcc<LAYOUT>::load(v, f.i0, f.j0, f.k1);
+        const float t101 = VolAcc<LAYOUT>::load(v, f.i1, f.j0, f.k1);
+        const float t011 = VolAcc<LAYOUT>::load(v, f.i0, f.j1, f.k1);
+        const float t111 = VolAcc<LAYOUT>::load(v, f.i1, f.j1, f.k1);
+        return trilerp(f, t000, t100, t010, t110, t001, t101, t011, t111);
+    } else {
+        using A = VolAcc<LAYOUT>;
+        const unsigned x0 = A::off_x(v, f.i0), x1 = A::off_x(v, f.i1);
+        const unsigned y0 = A::off_y(v, f.j0), y1 = A::off_y(v, f.j1);
+        const unsigned z0 = A::off_z(v, f.k0), z1 = A::off_z(v, f.k1);
+        const unsigned r00 = y0 + z0, r10 = y1 + z0, r01 = y0 + z1, r11 = y1 + z1;
+        const float t000 = __ldg(v.data + (r00 + x0));
+        const float t100 = __ldg(v.data + (r00 + x1));
+        const float t010 = __ldg(v.data + (r10 + x0));
+        const float t110 = __ldg(v.data + (r10 + x1));
+        const float t001 = __ldg(v.data + (r01 + x0));
+        const float t101 = __ldg(v.data + (r01 + x1));
+        const float t011 = __ldg(v.data + (r11 + x0));
+        const float t111 = __ldg(v.data + (r11 + x1));
+        return trilerp(f, t000, t100, t010, t110, t001, t101, t011, t111);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -153,6 +217,7 @@ struct crv_ctx {
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     uint64_t launches = 0;          // kernels launched through this context
+    bool sv_tables_ready = false;   // constant tables of sv_sweep.cu uploaded to this device
 };
 
 struct crv_volume {

@@ -17,7 +17,10 @@
 // L1/L2; roofline = HBM.  Algorithmic bytes per voxel: 4 B store + 4*Ncloud^3/N^3 B load.
 // The z loop is processed in chunks of U slices: all trilinear gathers of a chunk are issued before the
 // serial accumulate/exp/store pass, which gives 8*U independent loads in flight per thread.
+#include <cmath>
+
 #include "crv_internal.h"
+#include "exact_div.cuh"
 #include "sv_sweep.h"
 
 namespace {
@@ -85,30 +88,356 @@ __global__ void __launch_bounds__(256) sv_sweep_kernel(const __grid_constant__ S
     }
 }
 
-template <int CL, int OL>
-void launch_sv(const SVConst& c, cudaStream_t s)
+// ------------------------------------------------------------------------------------------------------
+// Fast kernels.  Same results bit for bit as sv_sweep_kernel (test_shadow_volume_modes_bit_identical).
+// The literal kernel is issue- and latency-bound, not memory-bound (profiles/r1a_sv_ncu.txt: 81 warp
+// instructions per 32 voxels, DRAM at 20 %).  Shared ingredients:
+//  * Each coordinate of p(z) = b0 + ((a + z*light) * voxelSize) is a chain of correctly rounded operations that
+//    are each weakly monotonic in z (voxelSize > 0), so per axis the set {z : cb0 <= p(z) <= cb1} is an interval
+//    and the column is inside the cloud AABB exactly for z in [z_in, z_end).  The interval is found once per
+//    column by bisection on the SAME fp32 expressions; the per-voxel position / AABB test disappears outside it
+//    (81 % of the voxels for a cube inside its bounding sphere's cube).
+//  * Before the column meets non-zero density acc == 0 and the shader's value is exp(-0) = 1: store only.
+//  * All divisions have launch-uniform divisors -> exact FMA division with host-computed reciprocals
+//    (exact_div.cuh); the reciprocal of float(z+1) comes from an n-entry table.
+//  * Column tiles are issued centre-out so that the cheap corner tiles (columns that never enter the cloud)
+//    fill the tail of the last wave; stores are streaming (written once, read later by another kernel).
+// ------------------------------------------------------------------------------------------------------
+constexpr int SV_ROWS = 8;
+
+// c_rcp_z[z] = RN(1 / float(z + 1)), filled once per device by crv_sv_init_tables (host IEEE division).  The index is
+// warp-uniform, so the lookup is one constant-bank load.
+__constant__ float c_rcp_z[SV_MAX_FAST_N];
+
+// [z_in, z_end): the z-interval in which column `a` (= x*right + y*up) is inside the cloud AABB (:34-42)
+__device__ __forceinline__ void column_range(const SVConst& c, const float a[3], int& z_in, int& z_end)
 {
-    const dim3 block(32, 8, 1);
-    const dim3 grid((c.n + 31) / 32, (c.n + 7) / 8, 1);
-    sv_sweep_kernel<CL, OL, 4><<<grid, block, 0, s>>>(c);
+    const int N = c.n;
+    z_in = 0;
+    z_end = N;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const bool inc = c.light[ax] >= 0.0f;
+        int lo_a = 0, hi_a = N, lo_b = 0, hi_b = N;
+        for (int it = 0; it < c.search_iters; ++it) {
+            if (lo_a < hi_a) {      // first z with  (inc ? p >= cb0 : p <= cb1)
+                const int mid = (lo_a + hi_a) >> 1;
+                const float p = c.b0[ax] + ((a[ax] + (float)mid * c.light[ax]) * c.voxel_size);
+                const bool t = inc ? !(p < c.cb0[ax]) : !(p > c.cb1[ax]);
+                if (t) hi_a = mid; else lo_a = mid + 1;
+            }
+            if (lo_b < hi_b) {      // first z with  (inc ? p > cb1 : p < cb0)
+                const int mid = (lo_b + hi_b) >> 1;
+                const float p = c.b0[ax] + ((a[ax] + (float)mid * c.light[ax]) * c.voxel_size);
+                const bool t = inc ? (p > c.cb1[ax]) : (p < c.cb0[ax]);
+                if (t) hi_b = mid; else lo_b = mid + 1;
+            }
+        }
+        z_in = max(z_in, lo_a);
+        z_end = min(z_end, lo_b);
+    }
+    if (z_end < z_in) z_end = z_in;
+}
+
+// texture(cloud, p(z)) for column `a` (:44-56), p known to be inside the cloud AABB (so 0 <= s <= 1).
+// SKIP: consult the dilated brick-max table first -- if every texel the footprint can touch is zero the
+// trilinear value is exactly 0 and the 8 loads (and the DRAM traffic of empty space) are skipped.
+template <int CL, bool SKIP>
+__device__ __forceinline__ float column_sample(const SVConst& c, const float a[3], int z)
+{
+    const float fz = (float)z;
+    const float px = c.b0[0] + ((a[0] + fz * c.light[0]) * c.voxel_size);
+    const float py = c.b0[1] + ((a[1] + fz * c.light[1]) * c.voxel_size);
+    const float pz = c.b0[2] + ((a[2] + fz * c.light[2]) * c.voxel_size);
+    // sampleCloud: ((p,0) - b0) / (b1 - b0); a -0 numerator gives +0 here instead of -0: same u = s*size - 0.5
+    const float sx = div_rn_by(px - c.cb0[0], c.cext[0], c.rcext[0]);
+    const float sy = div_rn_by(py - c.cb0[1], c.cext[1], c.rcext[1]);
+    const float sz = div_rn_by(pz - c.cb0[2], c.cext[2], c.rcext[2]);
+    const Footprint f = make_footprint<true>(c.cloud, sx, sy, sz);
+    if (SKIP) {
+        const unsigned b = ((unsigned)(f.k0 >> CRV_BRICK_SHIFT) * c.cloud.nby + (unsigned)(f.j0 >> CRV_BRICK_SHIFT)) * c.cloud.nbx +
+                           (unsigned)(f.i0 >> CRV_BRICK_SHIFT);
+        if (__ldg(c.brick_absmax + b) == 0.0f) return 0.0f;      // lerps of +-0 texels: +-0, and acc + (+-0) = acc
+    }
+    return trilinear_fetch<CL>(c.cloud, f);
+}
+
+// centre-out tile permutation: i = 0,1,2,3,... -> mid, mid-1, mid+1, mid-2, ... (a permutation of [0, n))
+__device__ __forceinline__ int centre_out(int i, int n)
+{
+    const int k = (i + 1) >> 1;
+    return (i & 1) ? (n >> 1) - k : (n >> 1) + k;
+}
+
+// ---- single pass: one thread per column, gathers of U slices batched ahead of the serial scan -------------
+template <int CL, int OL, int U>
+__global__ void __launch_bounds__(32 * SV_ROWS) sv_sweep_fast_kernel(const __grid_constant__ SVConst c)
+{
+    const int N = c.n;
+    const int x = centre_out(blockIdx.x, gridDim.x) * 32 + threadIdx.x;
+    const int y = centre_out(blockIdx.y, gridDim.y) * SV_ROWS + threadIdx.y;
+    const bool live = x < N && y < N;
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+
+    const float fx = (float)x, fy = (float)y;
+    const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
+    int z_in, z_end;
+    column_range(c, a, z_in, z_end);
+
+    float acc = 0.0f;      // accumulatedValue.x
+    float dist = 0.0f;     // accumulatedDistance
+    float fz1 = 0.0f;      // float(z + 1), exact
+    for (int z0 = 0; z0 < N; z0 += U) {
+        float tex[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) tex[u] = 0.0f;
+        // gather pass (skipped by the whole warp when no lane is inside the AABB in this chunk)
+        const bool mine = (z0 + U > z_in) && (z0 < z_end);
+        if (__any_sync(mask, mine)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int z = z0 + u;
+                if (z >= z_in && z < z_end) tex[u] = column_sample<CL, false>(c, a, z);
+            }
+        }
+        // serial pass: running sums, transmittance, store
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int z = z0 + u;
+            if (z < N) {
+                // outside [z_in, z_end) the shader adds nothing; inside, adding (0*ds)/bs = 0 is a no-op too
+                if (tex[u] != 0.0f) acc = acc + div_rn_by(tex[u] * c.density_scaling, c.base_scaling, c.rbase);
+                dist = dist + c.voxel_size;
+                fz1 = fz1 + 1.0f;
+                float t = 1.0f;    // acc == 0: exp(((-dist)*0)/(z+1)) = exp(-0) = 1 exactly
+                if (acc != 0.0f) t = expf(div_rn_by((-dist) * acc, fz1, c_rcp_z[z]));
+                VolAcc<OL>::store_streaming(c.out, x, y, z, t);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Two-pass build.  The single-pass kernels stay latency-bound: every column alternates between a batch of
+// dependent-address gathers and its serial scan, and at N = 512 the whole grid is a single wave
+// (profiles/r1b_svfast_512_ncu.txt: 38 % of the stall samples wait on the gathers, DRAM at 19 %).  The gathers do
+// not depend on the running sum, so they are split off:
+//   pass 0  sv_ranges_kernel : [z_in, z_end) of every column                                  (N^2 threads)
+//   pass 1  sv_gather_kernel : for the voxels inside the cloud AABB only, the addend
+//           (texture*densityScaling)/baseScaling, stored IN PLACE in the output volume.  Fully parallel: one CTA
+//           = one 8x8 column bundle, 8 slices at a time (a compact block of samples, so the texel loads of a
+//           warp share cache lines), all loads independent.
+//   pass 2  sv_scan_kernel   : per column, serial in z: acc += addend (read back only inside the interval,
+//           coalesced and issued U slices ahead of the recurrence), exp, streaming store.  A pure stream.
+// Same operations in the same order per column as the shader => same bits as the literal kernel.
+// Extra traffic over the algorithmic 4 N^3 + 4 Ncloud^3: one write + one read of the in-AABB voxels.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sv_ranges_kernel(const __grid_constant__ SVConst c)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= c.n || y >= c.n) return;
+    if (x == 0 && y == 0) {      // accumulatedDistance after every slice: the shader's repeated addition (:91), once
+        float dist = 0.0f;
+        for (int z = 0; z < c.n; ++z) {
+            dist = dist + c.voxel_size;
+            c.dist_z[z] = dist;
+        }
+    }
+    const float fx = (float)x, fy = (float)y;
+    const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
+    int z_in, z_end;
+    column_range(c, a, z_in, z_end);
+    c.zrange[(size_t)y * c.n + x] = make_ushort2((unsigned short)z_in, (unsigned short)z_end);
+}
+
+template <int CL, int OL>
+__global__ void __launch_bounds__(512) sv_gather_kernel(const __grid_constant__ SVConst c)
+{
+    __shared__ int s_lo, s_hi;
+    const int N = c.n;
+    const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lz = threadIdx.x >> 6;
+    const int x = blockIdx.x * 8 + lx, y = blockIdx.y * 8 + ly;
+    int z_in = 0, z_end = 0;
+    if (x < N && y < N) {
+        const ushort2 r = c.zrange[(size_t)y * N + x];
+        z_in = r.x;
+        z_end = r.y;
+    }
+    if (threadIdx.x == 0) { s_lo = N; s_hi = 0; }
+    __syncthreads();
+    if (lz == 0 && z_in < z_end) {
+        atomicMin(&s_lo, z_in);
+        atomicMax(&s_hi, z_end);
+    }
+    __syncthreads();
+    const int lo = s_lo & ~7, hi = s_hi;
+    if (lo >= hi) return;       // the bundle never enters the cloud
+
+    const float fx = (float)x, fy = (float)y;
+    const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
+    for (int z0 = lo + lz; z0 < hi; z0 += 16) {
+        const int z1 = z0 + 8;
+        const bool in0 = z0 >= z_in && z0 < z_end, in1 = z1 >= z_in && z1 < z_end;
+        float t0 = 0.0f, t1 = 0.0f;
+        if (in0) t0 = column_sample<CL, true>(c, a, z0);
+        if (in1) t1 = column_sample<CL, true>(c, a, z1);
+        if (in0) VolAcc<OL>::store(c.out, x, y, z0, div_rn_by(t0 * c.density_scaling, c.base_scaling, c.rbase));
+        if (in1) VolAcc<OL>::store(c.out, x, y, z1, div_rn_by(t1 * c.density_scaling, c.base_scaling, c.rbase));
+    }
+}
+
+// Column accessor for an aligned chunk of 8 slices: one base pointer + a per-slice step in the global layouts.
+template <int OL>
+struct ColumnChunk {
+    float* p;
+    unsigned step;
+    __device__ __forceinline__ ColumnChunk(const VolView& v, unsigned off_xy, int, int, int z0)
+        : p(const_cast<float*>(v.data) + (off_xy + VolAcc<OL>::off_z(v, z0))), step(VolAcc<OL>::z_step(v)) {}
+    __device__ __forceinline__ void store(const VolView&, int u, float val) const { __stcs(p + u * step, val); }
+    __device__ __forceinline__ float load(const VolView&, int u) const { return __ldcs(p + u * step); }
+};
+template <>
+struct ColumnChunk<CRV_LAYOUT_TEX3D> {
+    int x, y, z0;
+    __device__ __forceinline__ ColumnChunk(const VolView&, unsigned, int x_, int y_, int z0_) : x(x_), y(y_), z0(z0_) {}
+    __device__ __forceinline__ void store(const VolView& v, int u, float val) const { VolAcc<CRV_LAYOUT_TEX3D>::store(v, x, y, z0 + u, val); }
+    __device__ __forceinline__ float load(const VolView& v, int u) const { return VolAcc<CRV_LAYOUT_TEX3D>::load_rw(v, x, y, z0 + u); }
+};
+
+// One thread per column; chunks of 8 slices (one brick row in z).  A chunk in which no lane of the warp has met
+// density yet (acc == 0 everywhere, nobody inside its interval) is all ones: 8 streaming stores and nothing else --
+// the running distance is rebuilt from the dist table when the warp leaves that regime (same repeated-addition values).
+template <int OL, bool FULL>
+__device__ __forceinline__ void scan_chunk(const SVConst& c, const ColumnChunk<OL>& col, int z0, int z_in, int z_end, bool mine,
+                                           float& acc, float& dist, float& fz1)
+{
+    constexpr int U = 8;
+    float inc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) inc[u] = 0.0f;
+    if (mine) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int z = z0 + u;
+            if (z >= z_in && z < z_end) inc[u] = col.load(c.out, u);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (FULL || z0 + u < c.n) {
+            acc = acc + inc[u];        // + 0 outside the interval leaves acc unchanged (acc is never -0)
+            dist = dist + c.voxel_size;
+            fz1 = fz1 + 1.0f;
+            float t = 1.0f;            // acc == 0: exp(((-dist)*0)/(z+1)) = exp(-0) = 1 exactly
+            if (acc != 0.0f) t = expf(div_rn_by((-dist) * acc, fz1, c_rcp_z[z0 + u]));
+            col.store(c.out, u, t);
+        }
+    }
+}
+
+template <int OL>
+__global__ void __launch_bounds__(32 * SV_ROWS) sv_scan_kernel(const __grid_constant__ SVConst c)
+{
+    constexpr int U = 8;
+    const int N = c.n;
+    const int x = centre_out(blockIdx.x, gridDim.x) * 32 + threadIdx.x;
+    const int y = centre_out(blockIdx.y, gridDim.y) * SV_ROWS + threadIdx.y;
+    const bool live = x < N && y < N;
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+    const ushort2 r = c.zrange[(size_t)y * N + x];
+    const int z_in = r.x, z_end = r.y;
+    unsigned off_xy = 0;
+    if constexpr (OL != CRV_LAYOUT_TEX3D) off_xy = VolAcc<OL>::off_x(c.out, x) + VolAcc<OL>::off_y(c.out, y);
+
+    float acc = 0.0f;      // accumulatedValue.x
+    float dist = 0.0f;     // accumulatedDistance
+    float fz1 = 0.0f;      // float(z + 1), exact
+    bool stale = false;    // warp-uniform: dist / fz1 were not advanced through the last all-ones chunks
+    for (int z0 = 0; z0 < N; z0 += U) {
+        const bool full = z0 + U <= N;
+        const bool mine = (z0 + U > z_in) && (z0 < z_end);
+        const ColumnChunk<OL> col(c.out, off_xy, x, y, z0);
+        if (!__any_sync(mask, mine || acc != 0.0f)) {
+            if (full) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) col.store(c.out, u, 1.0f);
+            } else {
+                for (int u = 0; z0 + u < N; ++u) col.store(c.out, u, 1.0f);
+            }
+            stale = true;
+            continue;
+        }
+        if (stale) {       // dist_z[z] = accumulatedDistance after slice z: the same repeated fp32 additions (:91)
+            dist = __ldg(c.dist_z + (z0 - 1));
+            fz1 = (float)z0;
+            stale = false;
+        }
+        if (full) scan_chunk<OL, true>(c, col, z0, z_in, z_end, mine, acc, dist, fz1);
+        else scan_chunk<OL, false>(c, col, z0, z_in, z_end, mine, acc, dist, fz1);
+    }
+}
+
+template <int CL, int OL>
+void launch_sv(const SVConst& c, int mode, int* launches, cudaStream_t s)
+{
+    const dim3 block(32, SV_ROWS, 1);
+    const dim3 grid((c.n + 31) / 32, (c.n + SV_ROWS - 1) / SV_ROWS, 1);
+    if (mode == SV_MODE_TWO_PASS) {
+        sv_ranges_kernel<<<grid, block, 0, s>>>(c);
+        sv_gather_kernel<CL, OL><<<dim3((c.n + 7) / 8, (c.n + 7) / 8, 1), 512, 0, s>>>(c);
+        sv_scan_kernel<OL><<<grid, block, 0, s>>>(c);
+        *launches = 3;
+    } else if (mode == SV_MODE_SINGLE_PASS) {
+        sv_sweep_fast_kernel<CL, OL, 4><<<grid, block, 0, s>>>(c);
+        *launches = 1;
+    } else {
+        sv_sweep_kernel<CL, OL, 4><<<grid, block, 0, s>>>(c);
+        *launches = 1;
+    }
 }
 
 template <int CL>
-void launch_sv_out(const SVConst& c, int out_layout, cudaStream_t s)
+void launch_sv_out(const SVConst& c, int out_layout, int mode, int* launches, cudaStream_t s)
 {
-    if (out_layout == CRV_LAYOUT_BRICK) launch_sv<CL, CRV_LAYOUT_BRICK>(c, s);
-    else if (out_layout == CRV_LAYOUT_TEX3D) launch_sv<CL, CRV_LAYOUT_TEX3D>(c, s);
-    else launch_sv<CL, CRV_LAYOUT_LINEAR>(c, s);
+    if (out_layout == CRV_LAYOUT_BRICK) launch_sv<CL, CRV_LAYOUT_BRICK>(c, mode, launches, s);
+    else if (out_layout == CRV_LAYOUT_TEX3D) launch_sv<CL, CRV_LAYOUT_TEX3D>(c, mode, launches, s);
+    else launch_sv<CL, CRV_LAYOUT_LINEAR>(c, mode, launches, s);
 }
 
 }  // namespace
 
-int crv_launch_sv_sweep(crv_ctx* ctx, const SVConst& c, int cloud_layout, int out_layout, cudaStream_t s)
+bool crv_sv_fast_path_ok(const SVConst& c)
 {
-    if (cloud_layout == CRV_LAYOUT_BRICK) launch_sv_out<CRV_LAYOUT_BRICK>(c, out_layout, s);
-    else if (cloud_layout == CRV_LAYOUT_TEX3D) launch_sv_out<CRV_LAYOUT_TEX3D>(c, out_layout, s);
-    else launch_sv_out<CRV_LAYOUT_LINEAR>(c, out_layout, s);
-    ctx->launches++;
+    auto fin = [](float v) { return std::isfinite(v); };
+    auto div_ok = [&](float d) { return fin(d) && std::fabs(d) >= 1e-12f && std::fabs(d) <= 1e12f; };
+    bool ok = fin(c.voxel_size) && c.voxel_size > 0.0f && c.voxel_size < 1e12f && fin(c.density_scaling) && div_ok(c.base_scaling) &&
+              c.n > 0 && c.n <= SV_MAX_FAST_N && c.zrange != nullptr && c.dist_z != nullptr && c.brick_absmax != nullptr;
+    for (int i = 0; i < 3; ++i)
+        ok = ok && fin(c.b0[i]) && fin(c.right[i]) && fin(c.up[i]) && fin(c.light[i]) && fin(c.cb0[i]) && fin(c.cb1[i]) && div_ok(c.cext[i]) &&
+             std::fabs(c.b0[i]) < 1e12f && std::fabs(c.cb0[i]) < 1e12f;
+    return ok;
+}
+
+int crv_sv_init_tables(crv_ctx* ctx)
+{
+    if (ctx->sv_tables_ready) return CRV_OK;
+    static float tab[SV_MAX_FAST_N];
+    for (int z = 0; z < SV_MAX_FAST_N; ++z) tab[z] = 1.0f / (float)(z + 1);      // host IEEE division
+    CRV_CUDA(cudaMemcpyToSymbol(c_rcp_z, tab, sizeof(tab)));
+    ctx->sv_tables_ready = true;
+    return CRV_OK;
+}
+
+int crv_launch_sv_sweep(crv_ctx* ctx, const SVConst& c, int cloud_layout, int out_layout, int mode, cudaStream_t s)
+{
+    int launches = 0;
+    if (cloud_layout == CRV_LAYOUT_BRICK) launch_sv_out<CRV_LAYOUT_BRICK>(c, out_layout, mode, &launches, s);
+    else if (cloud_layout == CRV_LAYOUT_TEX3D) launch_sv_out<CRV_LAYOUT_TEX3D>(c, out_layout, mode, &launches, s);
+    else launch_sv_out<CRV_LAYOUT_LINEAR>(c, out_layout, mode, &launches, s);
+    ctx->launches += launches;
     CRV_CUDA(cudaGetLastError());
     return CRV_OK;
 }

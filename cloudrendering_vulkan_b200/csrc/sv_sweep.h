@@ -13,6 +13,23 @@ struct SVConst {
     float density_scaling, base_scaling;
     VolView cloud;      // sampled (binding 2)
     VolView out;        // stored  (binding 0)
+    // ---- fast path only (sv_sweep_fast_kernel) ----
+    float rcext[3];             // RN(1 / cext[i])            (host, IEEE)
+    float rbase;                // RN(1 / base_scaling)
+    const float* brick_absmax;  // dilated per-brick max |v| of the cloud (volume.cu), to skip empty-space gathers
+    float* dist_z;              // dist_z[z] = accumulatedDistance after slice z (n entries, device; written by pass 0)
+    int search_iters;           // ceil(log2(n + 1)): trip count of the per-column z-interval bisection
+    ushort2* zrange;            // two-pass build: [z_in, z_end) of every column, n*n entries (device)
 };
 
-int crv_launch_sv_sweep(crv_ctx* ctx, const SVConst& c, int cloud_layout, int out_layout, cudaStream_t s);
+constexpr int SV_MAX_FAST_N = 4096;   // entries of the constant reciprocal table (4096^3 floats = 275 GB: beyond HBM anyway)
+
+// fills the constant reciprocal table of the fast kernels, once per device
+int crv_sv_init_tables(crv_ctx* ctx);
+// true when the parameter block satisfies the fast kernel's preconditions (finite values, voxelSize > 0,
+// divisors in the range where the FMA division of exact_div.cuh is exact)
+bool crv_sv_fast_path_ok(const SVConst& c);
+
+// crv_sv_mode of crv_c_api.h (AUTO is resolved by the caller)
+enum { SV_MODE_GENERIC = 1, SV_MODE_SINGLE_PASS = 2, SV_MODE_TWO_PASS = 3 };
+int crv_launch_sv_sweep(crv_ctx* ctx, const SVConst& c, int cloud_layout, int out_layout, int mode, cudaStream_t s);

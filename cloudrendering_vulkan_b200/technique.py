@@ -246,6 +246,17 @@ class RenderTechniqueSV(RenderTechnique):
         check(lib.crv_sv_last_build_ms(self.handle, C.byref(ms)))
         return ms.value
 
+    SV_MODES = {"auto": 0, "generic": 1, "single_pass": 2, "two_pass": 3}
+
+    def SetTuning(self, mode="auto"):
+        """which kernels build the volume (crv_sv_mode); every mode produces the same bits"""
+        check(lib.crv_sv_set_tuning(self.handle, self.SV_MODES[mode] if isinstance(mode, str) else int(mode)))
+
+    def last_build_mode(self) -> str:
+        v = C.c_int()
+        check(lib.crv_sv_last_build_mode(self.handle, C.byref(v)))
+        return {v: k for k, v in self.SV_MODES.items()}[v.value]
+
     def close(self):
         if self.handle:
             lib.crv_sv_destroy(self.handle)

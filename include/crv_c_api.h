@@ -129,6 +129,13 @@ typedef enum crv_accum_mode {
     CRV_ACCUM_SUM          = 1   /* out = old + sample (multi-GPU spp split; divide after the reduce)       */
 } crv_accum_mode;
 
+typedef enum crv_sv_mode {
+    CRV_SV_MODE_AUTO        = 0,
+    CRV_SV_MODE_GENERIC     = 1,   /* one thread per column, AABB test + sample per voxel: ShadowVolume.comp literally */
+    CRV_SV_MODE_SINGLE_PASS = 2,   /* per-column z-interval by bisection + exact FMA division, still one kernel        */
+    CRV_SV_MODE_TWO_PASS    = 3    /* parallel gather of the in-AABB addends, then a streaming per-column scan         */
+} crv_sv_mode;
+
 typedef struct crv_ctx    crv_ctx;      /* one per GPU  (~ VulkanDevice)                       */
 typedef struct crv_volume crv_volume;   /* R32_SFLOAT 3D image + sampler (cloud or shadow)     */
 typedef struct crv_image  crv_image;    /* R32G32B32A32_SFLOAT 2D storage image (result)       */
@@ -197,6 +204,10 @@ int  crv_sv_update_descriptor_sets(crv_sv* sv);
 int  crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned image_index);
 /* device time of the last recorded build in ms (CUDA events on `stream`); syncs the stream */
 int  crv_sv_last_build_ms(crv_sv* sv, float* ms);
+/* Which kernels build the volume; every mode produces the same bits (tests/test_gpu_parity.py).  AUTO picks the
+ * fastest mode whose preconditions hold (finite parameters, voxelSize > 0, N < 65536), else GENERIC. */
+int  crv_sv_set_tuning(crv_sv* sv, int mode /* crv_sv_mode */);
+int  crv_sv_last_build_mode(crv_sv* sv, int* out);
 
 /* ---- RenderTechniquePT (RenderTechniquePT.h:8-40, .cpp:12-168) ---------------------------- */
 int  crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push_constants* pc, crv_pt** out);

@@ -100,6 +100,37 @@ def test_shadow_volume_nonuniform_grid(crv, orc, ctx):
     r.close()
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_shadow_volume_modes_bit_identical(crv, orc, ctx, layout):
+    """the single-pass (interval + exact FMA division) and two-pass (parallel gather + streaming scan) builds are pure
+    re-schedulings of the literal kernel: identical bits, for axis-aligned, oblique and upward light directions, ragged N
+    and a non-cubic grid with a non-zero boundary"""
+    rng = np.random.default_rng(11)
+    cases = [((40, 40, 40), None, (1.0, -1.0, 0.0), 70, 50.0), ((40, 40, 40), None, (0.0, 0.0, 1.0), 33, 400.0),
+             ((40, 40, 40), None, (-0.3, 0.8, -0.5), 61, 120.0), ((21, 34, 13), "rand", (0.2, -1.0, 0.1), 45, 120.0),
+             ((8, 8, 8), "rand", (0.0, -1.0, 0.0), 129, 30.0)]
+    for shape, kind, light, nsv, ds in cases:
+        n = shape[0] * shape[1] * shape[2]
+        cloud = rng.random(n, dtype=np.float32) if kind == "rand" else orc.fbm_generate(shape[0], 1234)
+        wl = crv.Workload("t", 0, 64, 64, 1, nsv, ds, 0.0, None, light)
+        r = crv.make_renderer(ctx, wl, cloud_layout=layout)
+        vs = (0.01, 0.02, 0.03) if kind == "rand" else (1.0 / shape[0],) * 3
+        r.set_cloud_host(cloud, shape, vs)
+        sv = r.shadowVolumeTechnique
+        assert sv.last_build_mode() == "two_pass"            # what AUTO resolves to
+        out = {}
+        for mode in ["generic", "single_pass", "two_pass"]:
+            sv.SetTuning(mode)
+            r.shadowVolumeImage.upload(np.full(nsv ** 3, -7.0, np.float32))     # poison: every voxel must be rewritten
+            r.UpdateShadowVolume()
+            assert sv.last_build_mode() == mode
+            out[mode] = r.shadowVolumeImage.download()
+        for mode in ["single_pass", "two_pass"]:
+            assert np.array_equal(_bits(out[mode]), _bits(out["generic"])), f"{mode} differs from the literal kernel ({shape}, {light}, N={nsv})"
+        _sv_check(out["generic"], orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties))
+        r.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 def _frame_parity(crv, orc, r, cloud, seed, absorption, min_match=0.99, expect_misses=True):
     sv_cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)

@@ -79,26 +79,34 @@ def full(path):
 
 
 def source(path, top=40):
+    """per source line: share of warp-stall samples and of executed warp instructions (file:line, both sorted lists)"""
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr_i = [i for i, r in enumerate(rows) if "Source" in r and any("Samples" in c for c in r)]
-    if not hdr_i:
-        print("no source page")
-        return
-    h = rows[hdr_i[0]]
-    si = [i for i, c in enumerate(h) if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)"]
-    si = si[0] if si else None
-    src = h.index("Source")
-    data = [r for r in rows[hdr_i[0] + 1:] if len(r) == len(h)]
-    def num(x):
-        try:
-            return float(x.replace(",", ""))
-        except Exception:
-            return 0.0
-    tot = sum(num(r[si]) for r in data) or 1.0
-    print(f"# {path}: top {top} source lines by warp-stall samples ({int(tot)} samples)")
-    for r in sorted(data, key=lambda r: -num(r[si]))[:top]:
-        print(f"{100 * num(r[si]) / tot:6.2f}%  {r[src][:150]}")
+    fname, h, lines = "?", None, []
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fname = r[1].split("/")[-1]
+        elif r[0] == "Line No":
+            h = r
+        elif h is not None and len(r) == len(h) and r[0].isdigit():
+            def num(name):
+                try:
+                    return float(r[h.index(name)].replace(",", ""))
+                except Exception:
+                    return 0.0
+            lines.append((fname, int(r[0]), r[1].strip(), num("# Samples"), num("Instructions Executed"), num("Avg. Threads Executed"),
+                          num("stall_long_sb"), num("stall_lg"), num("stall_wait"), num("stall_math")))
+    ts = sum(l[3] for l in lines) or 1.0
+    ti = sum(l[4] for l in lines) or 1.0
+    print(f"# {path}: {int(ts)} warp-stall samples, {int(ti)} warp instructions executed")
+    print(f"## top {top} source lines by stall samples   (share, long_sb/lg/wait/math samples, file:line, source)")
+    for l in sorted(lines, key=lambda l: -l[3])[:top]:
+        print(f"{100 * l[3] / ts:6.2f}%  {int(l[6]):6d} {int(l[7]):6d} {int(l[8]):6d} {int(l[9]):6d}  {l[0]}:{l[1]:<4d} {l[2][:110]}")
+    print(f"## top {top} source lines by executed warp instructions   (share, avg active threads, file:line, source)")
+    for l in sorted(lines, key=lambda l: -l[4])[:top]:
+        print(f"{100 * l[4] / ti:6.2f}%  {l[5]:5.1f}  {l[0]}:{l[1]:<4d} {l[2][:110]}")
 
 
 if __name__ == "__main__":
