@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(32 * SV_ROWS) sv_sweep_fast_kernel(const __gri
 // dependent-address gathers and its serial scan, and at N = 512 the whole grid is a single wave
 // (profiles/r1b_svfast_512_ncu.txt: 38 % of the stall samples wait on the gathers, DRAM at 19 %).  The gathers do
 // not depend on the running sum, so they are split off:
-//   pass 0  sv_ranges_kernel : [z_in, z_end) of every column                                  (N^2 threads)
+//   pass 0  (prologue of sv_gather_kernel) [z_in, z_end) of the CTA's 64 columns, kept for pass 2
 //   pass 1  sv_gather_kernel : for the voxels inside the cloud AABB only, the addend
 //           (texture*densityScaling)/baseScaling, stored IN PLACE in the output volume.  Fully parallel: one CTA
 //           = one 8x8 column bundle, 8 slices at a time (a compact block of samples, so the texel loads of a
@@ -233,48 +233,70 @@ __global__ void __launch_bounds__(32 * SV_ROWS) sv_sweep_fast_kernel(const __gri
 // Same operations in the same order per column as the shader => same bits as the literal kernel.
 // Extra traffic over the algorithmic 4 N^3 + 4 Ncloud^3: one write + one read of the in-AABB voxels.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sv_ranges_kernel(const __grid_constant__ SVConst c)
+// one of the six monotone predicates of column_range: first z in [0, N] at which it becomes true
+__device__ __forceinline__ int range_bisect(const SVConst& c, float a_ax, int ax, bool leave)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= c.n || y >= c.n) return;
-    if (x == 0 && y == 0) {      // accumulatedDistance after every slice: the shader's repeated addition (:91), once
-        float dist = 0.0f;
-        for (int z = 0; z < c.n; ++z) {
-            dist = dist + c.voxel_size;
-            c.dist_z[z] = dist;
+    const int N = c.n;
+    const bool inc = c.light[ax] >= 0.0f;
+    int lo = 0, hi = N;
+    for (int it = 0; it < c.search_iters; ++it) {
+        if (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const float p = c.b0[ax] + ((a_ax + (float)mid * c.light[ax]) * c.voxel_size);
+            const bool t = leave ? (inc ? (p > c.cb1[ax]) : (p < c.cb0[ax])) : (inc ? !(p < c.cb0[ax]) : !(p > c.cb1[ax]));
+            if (t) hi = mid; else lo = mid + 1;
         }
     }
-    const float fx = (float)x, fy = (float)y;
-    const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
-    int z_in, z_end;
-    column_range(c, a, z_in, z_end);
-    c.zrange[(size_t)y * c.n + x] = make_ushort2((unsigned short)z_in, (unsigned short)z_end);
+    return lo;
 }
 
 template <int CL, int OL>
 __global__ void __launch_bounds__(512) sv_gather_kernel(const __grid_constant__ SVConst c)
 {
     __shared__ int s_lo, s_hi;
+    __shared__ int s_search[6][64];
+    __shared__ int s_zin[64], s_zend[64];
     const int N = c.n;
-    const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lz = threadIdx.x >> 6;
-    const int x = blockIdx.x * 8 + lx, y = blockIdx.y * 8 + ly;
-    int z_in = 0, z_end = 0;
-    if (x < N && y < N) {
-        const ushort2 r = c.zrange[(size_t)y * N + x];
-        z_in = r.x;
-        z_end = r.y;
+    const int t = threadIdx.x;
+
+    // ---- pass 0 fused: [z_in, z_end) of the bundle's 64 columns, 6 bisections per column spread over 384 threads ----
+    if (t == 0) { s_lo = N; s_hi = 0; }
+    if (t < 384) {
+        const int col = t & 63, search = t >> 6;
+        const int cx = blockIdx.x * 8 + (col & 7), cy = blockIdx.y * 8 + (col >> 3);
+        const int ax = search >> 1;
+        const float a_ax = (float)cx * c.right[ax] + (float)cy * c.up[ax];
+        s_search[search][col] = range_bisect(c, a_ax, ax, (search & 1) != 0);
+    } else if (t == 511 && blockIdx.x == 0 && blockIdx.y == 0) {
+        float dist = 0.0f;      // accumulatedDistance after every slice: the shader's repeated addition (:91), once
+        for (int z = 0; z < N; ++z) {
+            dist = dist + c.voxel_size;
+            c.dist_z[z] = dist;
+        }
     }
-    if (threadIdx.x == 0) { s_lo = N; s_hi = 0; }
     __syncthreads();
-    if (lz == 0 && z_in < z_end) {
-        atomicMin(&s_lo, z_in);
-        atomicMax(&s_hi, z_end);
+    if (t < 64) {
+        const int cx = blockIdx.x * 8 + (t & 7), cy = blockIdx.y * 8 + (t >> 3);
+        int z_in = max(max(s_search[0][t], s_search[2][t]), s_search[4][t]);
+        int z_end = min(min(s_search[1][t], s_search[3][t]), s_search[5][t]);
+        if (z_end < z_in) z_end = z_in;
+        if (cx >= N || cy >= N) z_in = z_end = 0;
+        else c.zrange[(size_t)cy * N + cx] = make_ushort2((unsigned short)z_in, (unsigned short)z_end);
+        s_zin[t] = z_in;
+        s_zend[t] = z_end;
+        if (z_in < z_end) {
+            atomicMin(&s_lo, z_in);
+            atomicMax(&s_hi, z_end);
+        }
     }
     __syncthreads();
     const int lo = s_lo & ~7, hi = s_hi;
     if (lo >= hi) return;       // the bundle never enters the cloud
 
+    // ---- pass 1: the in-AABB addends, 8x8 columns x 8 slices per step (two steps in flight) ----
+    const int lx = t & 7, ly = (t >> 3) & 7, lz = t >> 6;
+    const int x = blockIdx.x * 8 + lx, y = blockIdx.y * 8 + ly;
+    const int z_in = s_zin[t & 63], z_end = s_zend[t & 63];
     const float fx = (float)x, fy = (float)y;
     const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
     for (int z0 = lo + lz; z0 < hi; z0 += 16) {
@@ -330,9 +352,9 @@ __device__ __forceinline__ void scan_chunk(const SVConst& c, const ColumnChunk<O
             acc = acc + inc[u];        // + 0 outside the interval leaves acc unchanged (acc is never -0)
             dist = dist + c.voxel_size;
             fz1 = fz1 + 1.0f;
-            float t = 1.0f;            // acc == 0: exp(((-dist)*0)/(z+1)) = exp(-0) = 1 exactly
-            if (acc != 0.0f) t = expf(div_rn_by((-dist) * acc, fz1, c_rcp_z[z0 + u]));
-            col.store(c.out, u, t);
+            // no branch on acc == 0 (it would serialise the 8 independent exp chains): ((-dist)*0)/(z+1) = +-0 and
+            // expf(+-0) = 1 exactly, the value the shader stores there
+            col.store(c.out, u, expf(div_rn_by((-dist) * acc, fz1, c_rcp_z[z0 + u])));
         }
     }
 }
@@ -386,10 +408,9 @@ void launch_sv(const SVConst& c, int mode, int* launches, cudaStream_t s)
     const dim3 block(32, SV_ROWS, 1);
     const dim3 grid((c.n + 31) / 32, (c.n + SV_ROWS - 1) / SV_ROWS, 1);
     if (mode == SV_MODE_TWO_PASS) {
-        sv_ranges_kernel<<<grid, block, 0, s>>>(c);
         sv_gather_kernel<CL, OL><<<dim3((c.n + 7) / 8, (c.n + 7) / 8, 1), 512, 0, s>>>(c);
         sv_scan_kernel<OL><<<grid, block, 0, s>>>(c);
-        *launches = 3;
+        *launches = 2;
     } else if (mode == SV_MODE_SINGLE_PASS) {
         sv_sweep_fast_kernel<CL, OL, 4><<<grid, block, 0, s>>>(c);
         *launches = 1;
