@@ -5,6 +5,7 @@
 // resources per image index, vkCmdDispatch becomes a kernel launch on the caller's stream.
 // All host arithmetic that feeds the kernels is fp32 in the shader's evaluation order (compiled with
 // -ffp-contract=off), because the kernels take these values as if the shader had computed them.
+#include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <new>
@@ -90,7 +91,12 @@ struct crv_pt {
     std::vector<crv_image*> images;
     std::vector<PTBindings> sets;
     crv_pt_extensions ext{};
+    // hit list of the last classification (pixels whose camera ray enters the box)
+    uint32_t* hitlist = nullptr;
+    uint32_t* nhit = nullptr;
+    size_t hitlist_elems = 0;
     // q-table cache
+    float* qtable_wide = nullptr;
     float* qtable = nullptr;
     size_t qtable_elems = 0;
     const crv_volume* q_for_vol = nullptr;
@@ -265,6 +271,7 @@ int crv_volume_destroy(crv_volume* v)
     if (v->data) cudaFree(v->data);
     if (v->brick_max) cudaFree(v->brick_max);
     if (v->brick_absmax) cudaFree(v->brick_absmax);
+    if (v->brick_absmax_wide) cudaFree(v->brick_absmax_wide);
     vol_forget(v);
     delete v;
     return CRV_OK;
@@ -637,6 +644,7 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
     pt->pc = pc;
     pt->sets.resize(1);
     CRV_CUDA(cudaMalloc(&pt->job_counter, sizeof(unsigned int)));
+    CRV_CUDA(cudaMalloc(&pt->nhit, sizeof(uint32_t)));
     CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
     CRV_CUDA(cudaMemset(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT));
     *out = pt;
@@ -648,6 +656,9 @@ int crv_pt_destroy(crv_pt* pt)
     if (!pt) return CRV_OK;
     cudaSetDevice(pt->ctx->device);
     if (pt->qtable) cudaFree(pt->qtable);
+    if (pt->qtable_wide) cudaFree(pt->qtable_wide);
+    if (pt->hitlist) cudaFree(pt->hitlist);
+    if (pt->nhit) cudaFree(pt->nhit);
     if (pt->samples) cudaFree(pt->samples);
     if (pt->job_counter) cudaFree(pt->job_counter);
     if (pt->stats) cudaFree(pt->stats);
@@ -830,17 +841,46 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
     if (pt->q_for_vol != cv || pt->q_for_generation != vol_generation(cv) || pt->q_for_max_ext != c.max_ext || pt->qtable_elems != nbricks) {
         if (pt->qtable_elems != nbricks) {
             if (pt->qtable) CRV_CUDA(cudaFree(pt->qtable));
-            pt->qtable = nullptr;
+            if (pt->qtable_wide) CRV_CUDA(cudaFree(pt->qtable_wide));
+            pt->qtable = pt->qtable_wide = nullptr;
+            pt->qtable_elems = 0;
             CRV_CUDA(cudaMalloc(&pt->qtable, nbricks * sizeof(float)));
+            CRV_CUDA(cudaMalloc(&pt->qtable_wide, nbricks * sizeof(float)));
             pt->qtable_elems = nbricks;
         }
         CRV_TRY(crv_launch_qtable(pt->ctx, cv->brick_absmax, pt->qtable, (long long)nbricks, c.max_ext, s));
-        pt->launches++;
+        CRV_TRY(crv_launch_qtable(pt->ctx, cv->brick_absmax_wide, pt->qtable_wide, (long long)nbricks, c.max_ext, s));
+        pt->launches += 2;
         pt->q_for_vol = cv;
         pt->q_for_generation = vol_generation(cv);
         pt->q_for_max_ext = c.max_ext;
     }
     c.qtable = pt->qtable;
+    c.qtable_wide = pt->qtable_wide;
+
+    // exact FMA division (exact_div.cuh): reciprocals by IEEE division on the host; the divisors must be ordinary numbers
+    {
+        auto ordinary = [](float v) { return std::isfinite(v) && std::fabs(v) >= 1e-18f && std::fabs(v) <= 1e18f; };
+        bool ok = ordinary(c.sigma) && ordinary(c.max_ext);
+        for (int i = 0; i < 3; ++i) ok = ok && ordinary(c.cext[i]) && ordinary(c.sden[i]);
+        CRV_REQUIRE(ok || !(c.density_scaling > 0.0f),
+                    "RenderTechniquePT: extinction scale, cloud extent and shadow-volume extent must be finite and within 1e-18..1e18");
+        c.r_sigma = 1.0f / c.sigma;
+        c.r_max_ext = 1.0f / c.max_ext;
+        // approximate brick pre-test: u'' = q*asc + aof ~ ((q - cb0)/cext)*size - 1, evaluated with one FMA.  Its error is
+        // a few ulps of the largest term, |cb0/cext|*size; the wide table tolerates 1 texel, we allow 1/4.
+        c.use_wide = 1;
+        for (int i = 0; i < 3; ++i) {
+            c.rcext[i] = 1.0f / c.cext[i];
+            c.rsden[i] = 1.0f / c.sden[i];
+            const double n = i == 0 ? c.cloud.nx : i == 1 ? c.cloud.ny : c.cloud.nz;
+            const double sc = n / (double)c.cext[i], of = -(double)c.cb0[i] * sc - 1.0;
+            c.asc[i] = (float)sc;
+            c.aof[i] = (float)of;
+            const double span = std::fabs((double)c.cb0[i]) + std::fabs((double)c.cb1[i]);
+            if (!(span * std::fabs(sc) * 4.0 * 1.1920929e-07 < 0.25) || !(n < 2097152.0)) c.use_wide = 0;
+        }
+    }
 
     c.npix = (uint32_t)W * (uint32_t)H;
     c.image = reinterpret_cast<float4*>(img->rgba);
@@ -875,31 +915,48 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
     c.accum_mode = mode;
     pt->ev_used = 0;
 
+    // debug counters (single-frame renders only)
+    if (n == 1 && pt->dbg_enabled) {
+        if (pt->dbg_elems != c.npix) {
+            if (pt->dbg_steps) CRV_CUDA(cudaFree(pt->dbg_steps));
+            if (pt->dbg_coll) CRV_CUDA(cudaFree(pt->dbg_coll));
+            pt->dbg_steps = pt->dbg_coll = nullptr;
+            pt->dbg_elems = 0;
+            CRV_CUDA(cudaMalloc(&pt->dbg_steps, sizeof(uint32_t) * c.npix));
+            CRV_CUDA(cudaMalloc(&pt->dbg_coll, sizeof(uint32_t) * c.npix));
+            pt->dbg_elems = c.npix;
+        }
+        c.dbg_steps = pt->dbg_steps;
+        c.dbg_collisions = pt->dbg_coll;
+    }
+
+    // classification: miss pixels get all n background samples folded now, hit pixels go to the hit list
+    if (pt->hitlist_elems < c.npix) {
+        if (pt->hitlist) CRV_CUDA(cudaFree(pt->hitlist));
+        pt->hitlist = nullptr;
+        pt->hitlist_elems = 0;
+        CRV_CUDA(cudaMalloc(&pt->hitlist, sizeof(uint32_t) * c.npix));
+        pt->hitlist_elems = c.npix;
+    }
+    c.hitlist = pt->hitlist;
+    c.nhit = pt->nhit;
+    c.first_frame_count = first_fc;
+    CRV_CUDA(cudaMemsetAsync(pt->nhit, 0, sizeof(uint32_t), s));
+    CRV_TRY(crv_launch_classify(pt->ctx, c, n, pt->hitlist, pt->nhit, s));
+    pt->launches++;
+
     if (n == 1) {
         // single dispatch: fold straight into the image (PathTracer.comp:420-424)
-        if (pt->dbg_enabled) {
-            if (pt->dbg_elems != c.npix) {
-                if (pt->dbg_steps) CRV_CUDA(cudaFree(pt->dbg_steps));
-                if (pt->dbg_coll) CRV_CUDA(cudaFree(pt->dbg_coll));
-                pt->dbg_steps = pt->dbg_coll = nullptr;
-                CRV_CUDA(cudaMalloc(&pt->dbg_steps, sizeof(uint32_t) * c.npix));
-                CRV_CUDA(cudaMalloc(&pt->dbg_coll, sizeof(uint32_t) * c.npix));
-                pt->dbg_elems = c.npix;
-            }
-            c.dbg_steps = pt->dbg_steps;
-            c.dbg_collisions = pt->dbg_coll;
-        }
         c.direct = 1;
         c.nframes = 1;
         c.seeds[0] = seeds[0];
-        c.first_frame_count = first_fc;
         CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
         CRV_TRY(pt_timed_launch(pt, c, b, s));
         pt->launches++;
         return CRV_OK;
     }
 
-    // rounds of `per_round` frames through the sample buffer
+    // rounds of `per_round` frames through the sample buffer (sized for the worst case: every pixel hits)
     const size_t frame_bytes = (size_t)c.npix * sizeof(float4);
     uint64_t per_round = pt->sample_budget / frame_bytes;
     if (per_round < 1) per_round = 1;
@@ -917,6 +974,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
     }
     c.direct = 0;
     c.samples = pt->samples;
+    c.dbg_steps = c.dbg_collisions = nullptr;
     for (unsigned f0 = 0; f0 < n; f0 += (unsigned)per_round) {
         const unsigned nf = (n - f0 < per_round) ? (n - f0) : (unsigned)per_round;
         c.nframes = nf;
@@ -927,6 +985,8 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         FoldConst fc{};
         fc.image = c.image;
         fc.samples = pt->samples;
+        fc.hitlist = pt->hitlist;
+        fc.nhit = pt->nhit;
         fc.npix = c.npix;
         fc.nframes = nf;
         fc.first_frame_count = first_fc + f0;

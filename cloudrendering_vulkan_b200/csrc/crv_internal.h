@@ -232,6 +232,7 @@ struct crv_volume {
     cudaSurfaceObject_t surf = 0;
     float* brick_max = nullptr;            // nbx*nby*nbz: max(v, 0) over each brick's dilated voxel set
     float* brick_absmax = nullptr;         // nbx*nby*nbz: max |v| over the same set (feeds the q-table)
+    float* brick_absmax_wide = nullptr;    // nbx*nby*nbz: max |v| over voxels [8b-1, 8b+9]^3 (approximate brick test)
     bool brick_max_valid = false;
     float majorant = 0.0f;
     bool majorant_valid = false;

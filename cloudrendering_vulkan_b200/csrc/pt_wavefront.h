@@ -22,6 +22,9 @@ struct PTConst {
     float max_ext;                     // maxExtinction
     float sigma;                       // (maxExtinction * densityScaling) / baseScaling   (:338)
     float density_scaling;
+    float r_sigma, r_max_ext, rcext[3]; // RN(1/x) of the divisors above (host IEEE division) for exact_div.cuh
+    int use_wide;                      // 1: approximate brick pre-test enabled (its error bound holds for this geometry)
+    float asc[3], aof[3];              // approximate texel coordinate: q*asc + aof ~ ((q - cb0)/cext)*size - 1
 
     // ---- Parameters (:68-78) ----
     float light_intensity;             // 1.0f * lightIntensity
@@ -37,10 +40,14 @@ struct PTConst {
     float sb0[4];                      // bounds[0]
     float m0[3], m1[3], m2[3], m3[3];  // basisChange columns (.xyz)
     float sden[3];                     // (basisChange * (bounds[1] - bounds[0])).xyz
+    float rsden[3];                    // RN(1 / sden[i])
 
     // ---- resources ----
     VolView cloud, sv;
-    const float* qtable;               // per 8^3 brick: upper bound of ext/maxExtinction over the dilated brick
+    const float* qtable;               // per 8^3 brick: upper bound of ext/maxExtinction over voxels [8b, 8b+8]^3
+    const float* qtable_wide;          // same over voxels [8b-1, 8b+9]^3: valid for a brick index that is off by < 1 texel
+    const uint32_t* hitlist;           // pixels whose camera ray enters the box (pt_classify_kernel), *nhit entries
+    const uint32_t* nhit;
 
     // ---- job description ----
     uint32_t npix;                     // width*height
@@ -50,7 +57,7 @@ struct PTConst {
     int accum_mode;                    // crv_accum_mode
     int direct;                        // 1: accumulate straight into `image` (nframes == 1); 0: write `samples`
     float4* image;                     // W*H rgba32f result image (binding 0)
-    float4* samples;                   // nframes * npix samples (direct == 0)
+    float4* samples;                   // nframes * nhit samples, index = job (direct == 0)
     unsigned int* job_counter;         // next unclaimed job of this launch
     unsigned long long* stats;         // PT_STAT_COUNT u64 (may be null)
     uint32_t* dbg_steps;               // per-pixel counters (direct mode only, may be null)
@@ -61,11 +68,14 @@ struct PTConst {
 struct FoldConst {
     float4* image;
     const float4* samples;
+    const uint32_t* hitlist;
+    const uint32_t* nhit;
     uint32_t npix, nframes, first_frame_count;
     int accum_mode;
 };
 
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
+int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, uint32_t* hitlist, uint32_t* nhit, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
 int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);

@@ -77,6 +77,31 @@ __global__ void brick_max_kernel(VolView v, float* __restrict__ out_abs, float* 
     if (lane == 0) { out_abs[brick] = ma; out_max[brick] = m; }
 }
 
+// Wider dilation for the path tracer's APPROXIMATE brick test (pt_wavefront.cu): max |v| over voxels
+// [8b-1, 8b+9] per axis (clamped).  If an approximate texel coordinate (off by < 1 texel) has its lower footprint
+// corner in brick b, every texel of the exact footprint lies in this set.  11^3 = 1331 voxels, 42 per lane.
+template <int LAYOUT>
+__global__ void brick_absmax_wide_kernel(VolView v, float* __restrict__ out_abs)
+{
+    const int warps_per_block = blockDim.x >> 5;
+    const long long brick = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const long long nbricks = (long long)v.nbx * v.nby * v.nbz;
+    if (brick >= nbricks) return;
+    const int lane = threadIdx.x & 31;
+    const int bx = (int)(brick % v.nbx);
+    const int by = (int)((brick / v.nbx) % v.nby);
+    const int bz = (int)(brick / ((long long)v.nbx * v.nby));
+    float ma = 0.0f;
+    for (int t = lane; t < 1331; t += 32) {
+        const int lx = t % 11 - 1, ly = (t / 11) % 11 - 1, lz = t / 121 - 1;
+        const int i = min(max(bx * 8 + lx, 0), v.nx - 1), j = min(max(by * 8 + ly, 0), v.ny - 1), k = min(max(bz * 8 + lz, 0), v.nz - 1);
+        ma = fmaxf(ma, fabsf(VolAcc<LAYOUT>::load(v, i, j, k)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    if (lane == 0) out_abs[brick] = ma;
+}
+
 // majorant = max over the brick-max grid (each voxel belongs to at least one brick's set)
 __global__ void majorant_kernel(const float* __restrict__ brick_max, long long n, float* __restrict__ out)
 {
@@ -137,7 +162,14 @@ int crv_launch_brick_max(crv_ctx* ctx, crv_volume* vol, cudaStream_t s)
         brick_max_kernel<CRV_LAYOUT_TEX3D><<<blocks, threads, 0, s>>>(v, vol->brick_absmax, vol->brick_max);
     else
         brick_max_kernel<CRV_LAYOUT_LINEAR><<<blocks, threads, 0, s>>>(v, vol->brick_absmax, vol->brick_max);
-    ctx->launches++;
+    if (!vol->brick_absmax_wide) CRV_CUDA(cudaMalloc(&vol->brick_absmax_wide, sizeof(float) * nbricks));
+    if (vol->layout == CRV_LAYOUT_BRICK)
+        brick_absmax_wide_kernel<CRV_LAYOUT_BRICK><<<blocks, threads, 0, s>>>(v, vol->brick_absmax_wide);
+    else if (vol->layout == CRV_LAYOUT_TEX3D)
+        brick_absmax_wide_kernel<CRV_LAYOUT_TEX3D><<<blocks, threads, 0, s>>>(v, vol->brick_absmax_wide);
+    else
+        brick_absmax_wide_kernel<CRV_LAYOUT_LINEAR><<<blocks, threads, 0, s>>>(v, vol->brick_absmax_wide);
+    ctx->launches += 2;
     CRV_CUDA(cudaGetLastError());
     vol->brick_max_valid = true;
     return CRV_OK;
