@@ -93,6 +93,7 @@ struct crv_pt {
     crv_pt_extensions ext{};
     // hit list of the last classification (pixels whose camera ray enters the box)
     uint32_t* hitlist = nullptr;
+    float* start = nullptr;             // per hit pixel start state (7 floats, SoA)
     uint32_t* nhit = nullptr;
     size_t hitlist_elems = 0;
     // q-table cache
@@ -103,7 +104,7 @@ struct crv_pt {
     float q_for_max_ext = -1.0f;
     uint64_t q_for_generation = 0;
     // per-launch buffers
-    float4* samples = nullptr;
+    float2* samples = nullptr;
     size_t samples_bytes = 0;
     unsigned int* job_counter = nullptr;
     unsigned long long* stats = nullptr;
@@ -117,7 +118,7 @@ struct crv_pt {
     size_t ev_used = 0;
     // tuning
     int ctas_per_sm = 0;
-    int track_threshold = 12;
+    int track_threshold = 20;
     uint64_t sample_budget = 2ull << 30;
 };
 
@@ -658,6 +659,7 @@ int crv_pt_destroy(crv_pt* pt)
     if (pt->qtable) cudaFree(pt->qtable);
     if (pt->qtable_wide) cudaFree(pt->qtable_wide);
     if (pt->hitlist) cudaFree(pt->hitlist);
+    if (pt->start) cudaFree(pt->start);
     if (pt->nhit) cudaFree(pt->nhit);
     if (pt->samples) cudaFree(pt->samples);
     if (pt->job_counter) cudaFree(pt->job_counter);
@@ -931,33 +933,27 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
     }
 
     // classification: miss pixels get all n background samples folded now, hit pixels go to the hit list
-    if (pt->hitlist_elems < c.npix) {
+    CRV_REQUIRE(c.width < 65536 && c.height < 65536, "RenderTechniquePT: resolution above 65535 is not supported");
+    if (pt->hitlist_elems != c.npix) {
         if (pt->hitlist) CRV_CUDA(cudaFree(pt->hitlist));
+        if (pt->start) CRV_CUDA(cudaFree(pt->start));
         pt->hitlist = nullptr;
+        pt->start = nullptr;
         pt->hitlist_elems = 0;
         CRV_CUDA(cudaMalloc(&pt->hitlist, sizeof(uint32_t) * c.npix));
+        CRV_CUDA(cudaMalloc(&pt->start, sizeof(float) * 7 * (size_t)c.npix));
         pt->hitlist_elems = c.npix;
     }
     c.hitlist = pt->hitlist;
+    c.start = pt->start;
     c.nhit = pt->nhit;
     c.first_frame_count = first_fc;
     CRV_CUDA(cudaMemsetAsync(pt->nhit, 0, sizeof(uint32_t), s));
-    CRV_TRY(crv_launch_classify(pt->ctx, c, n, pt->hitlist, pt->nhit, s));
+    CRV_TRY(crv_launch_classify(pt->ctx, c, n, pt->hitlist, pt->start, pt->nhit, s));
     pt->launches++;
 
-    if (n == 1) {
-        // single dispatch: fold straight into the image (PathTracer.comp:420-424)
-        c.direct = 1;
-        c.nframes = 1;
-        c.seeds[0] = seeds[0];
-        CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
-        CRV_TRY(pt_timed_launch(pt, c, b, s));
-        pt->launches++;
-        return CRV_OK;
-    }
-
     // rounds of `per_round` frames through the sample buffer (sized for the worst case: every pixel hits)
-    const size_t frame_bytes = (size_t)c.npix * sizeof(float4);
+    const size_t frame_bytes = (size_t)c.npix * sizeof(float2);
     uint64_t per_round = pt->sample_budget / frame_bytes;
     if (per_round < 1) per_round = 1;
     const uint64_t max_jobs_frames = 0xffffffffull / c.npix;       // job ids are 32-bit
@@ -972,9 +968,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         CRV_CUDA(cudaMalloc(&pt->samples, need));
         pt->samples_bytes = need;
     }
-    c.direct = 0;
     c.samples = pt->samples;
-    c.dbg_steps = c.dbg_collisions = nullptr;
     for (unsigned f0 = 0; f0 < n; f0 += (unsigned)per_round) {
         const unsigned nf = (n - f0 < per_round) ? (n - f0) : (unsigned)per_round;
         c.nframes = nf;
@@ -988,6 +982,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         fc.hitlist = pt->hitlist;
         fc.nhit = pt->nhit;
         fc.npix = c.npix;
+        fc.width = (uint32_t)c.width;
         fc.nframes = nf;
         fc.first_frame_count = first_fc + f0;
         fc.accum_mode = mode;

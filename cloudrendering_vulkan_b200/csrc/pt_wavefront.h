@@ -6,6 +6,10 @@
 enum { PT_STAT_PATHS = 0, PT_STAT_STEPS = 1, PT_STAT_COLLISIONS = 2, PT_STAT_FETCHES = 3, PT_STAT_COUNT = 4 };
 
 constexpr int PT_MAX_FRAMES_PER_LAUNCH = 256;
+constexpr int PT_THREADS = 256;
+// y-slot of a sample record that carries no background term (absorbed path): a quiet NaN with a payload that fp32
+// arithmetic never generates (it produces the canonical 0x7fffffff)
+constexpr int PT_NO_BACKGROUND_BITS = 0x7fc0dead;
 
 struct PTConst {
     // ---- CameraProperties (PathTracer.comp:43-55), products precomputed on the host in the shader's order ----
@@ -46,8 +50,9 @@ struct PTConst {
     VolView cloud, sv;
     const float* qtable;               // per 8^3 brick: upper bound of ext/maxExtinction over voxels [8b, 8b+8]^3
     const float* qtable_wide;          // same over voxels [8b-1, 8b+9]^3: valid for a brick index that is off by < 1 texel
-    const uint32_t* hitlist;           // pixels whose camera ray enters the box (pt_classify_kernel), *nhit entries
+    const uint32_t* hitlist;           // pixels whose camera ray enters the box (pt_classify_kernel), x | y << 16, *nhit entries
     const uint32_t* nhit;
+    const float* start;                // per hit pixel, SoA with stride npix: entry point xyz, direction xyz, exit distance
 
     // ---- job description ----
     uint32_t npix;                     // width*height
@@ -55,27 +60,26 @@ struct PTConst {
     int32_t seeds[PT_MAX_FRAMES_PER_LAUNCH];   // pushConstants.seed of every frame of this launch (by value: no staging copy)
     uint32_t first_frame_count;        // pushConstants.frameCount of frame 0 of this launch
     int accum_mode;                    // crv_accum_mode
-    int direct;                        // 1: accumulate straight into `image` (nframes == 1); 0: write `samples`
-    float4* image;                     // W*H rgba32f result image (binding 0)
-    float4* samples;                   // nframes * nhit samples, index = job (direct == 0)
+    float4* image;                     // W*H rgba32f result image (binding 0); written by pt_classify_kernel / fold_kernel
+    float2* samples;                   // nframes * nhit records (S, dir.y), index = job
     unsigned int* job_counter;         // next unclaimed job of this launch
     unsigned long long* stats;         // PT_STAT_COUNT u64 (may be null)
-    uint32_t* dbg_steps;               // per-pixel counters (direct mode only, may be null)
+    uint32_t* dbg_steps;               // per-pixel counters (single-frame renders, both null or both set)
     uint32_t* dbg_collisions;
     int track_threshold;               // service collisions/regeneration once fewer lanes than this are tracking
 };
 
 struct FoldConst {
     float4* image;
-    const float4* samples;
+    const float2* samples;
     const uint32_t* hitlist;
     const uint32_t* nhit;
-    uint32_t npix, nframes, first_frame_count;
+    uint32_t npix, nframes, first_frame_count, width;
     int accum_mode;
 };
 
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
-int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, uint32_t* hitlist, uint32_t* nhit, cudaStream_t s);
+int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, uint32_t* hitlist, float* start, uint32_t* nhit, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
 int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);
