@@ -85,7 +85,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--layout", default="linear", choices=["linear", "brick", "tex3d"])
+    ap.add_argument("--layout", default="brick", choices=["linear", "brick", "tex3d"])
     ap.add_argument("--spp", type=int, default=0, help="override spp per GPU (the default is the config's)")
     ap.add_argument("--track-threshold", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)

@@ -20,6 +20,6 @@ timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --
 # full capture of the hot kernels (short command: 16 spp)
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:pt_wavefront -s 3 -c 1 -f -o $OUT/${TAG}_pt \
     python bench.py --spp 16 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_pt.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sv_sweep -c 1 -f -o $OUT/${TAG}_sv \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sv_ -s 8 -c 2 -f -o $OUT/${TAG}_sv \
     python bench.py --spp 1 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_sv.log 2>&1
 ls -la $OUT
