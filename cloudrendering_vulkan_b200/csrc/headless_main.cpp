@@ -1,0 +1,224 @@
+// headless_main.cpp -- crv_headless: the reference's main.cpp around the PathTracer/ShadowVolume hot path, headless.
+//
+// Same call order as the interactive app, on the C++ RenderTechnique classes of include/crv/render_technique.h:
+//   StartSimulation (main.cpp:927-944): SetCloudProperties, SetFOV, techniques, LoadCloudFile, UpdateCloudData
+//   UpdateCloudData (main.cpp:266-335): upload, QueueUpdateCloudData(+Sampler), UpdateDescriptorSets, UpdateShadowVolume
+//   UpdateShadowVolume (main.cpp:223-264): SetLightDirection, SetOrigin, SV RecordDrawCommands, rebind on PT
+//   RenderLoop / DrawFrame (main.cpp:714-736, 603-712): seed = rand(), RecordDrawCommands, frameCount++
+// minus window, swapchain, ImGui and the blit.  One zero-cleared result image, frameCount starting at 0
+// (SURVEY.md 3.3).  No Vulkan, no GLFW; every computation runs in libcrv_b200.so on the GPU.
+//
+//   crv_headless [--xyz file | --fbm N] [--width W --height H] [--spp S] [--nsv N] [--g G] [--absorption A]
+//                [--density-scaling D] [--light x,y,z] [--per-frame] [--device i] [--pfm out.pfm]
+// prints one JSON line: resolution, spp, ms, Mpath-samples/s, SV build ms, FNV-1a hash of the RGBA32F image.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/crv/grid3d.h"
+#include "../../include/crv/render_technique.h"
+
+namespace {
+
+struct Options {
+    std::string xyz, pfm;
+    unsigned fbm = 128;
+    int width = 512, height = 512, device = 0;
+    unsigned spp = 16, nsv = 500;
+    float g = 0.85f, absorption = 0.0f, density_scaling = 50.0f, fov = 90.0f;
+    float light[3] = {1.0f, -1.0f, 0.0f};
+    bool isotropic = false, per_frame = false;
+};
+
+bool parse(int argc, char** argv, Options& o)
+{
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { std::fprintf(stderr, "crv_headless: %s needs a value\n", name); std::exit(2); }
+            return argv[++i];
+        };
+        if (a == "--xyz") o.xyz = next("--xyz");
+        else if (a == "--fbm") o.fbm = (unsigned)std::atoi(next("--fbm"));
+        else if (a == "--width") o.width = std::atoi(next("--width"));
+        else if (a == "--height") o.height = std::atoi(next("--height"));
+        else if (a == "--spp") o.spp = (unsigned)std::atoi(next("--spp"));
+        else if (a == "--nsv") o.nsv = (unsigned)std::atoi(next("--nsv"));
+        else if (a == "--g") o.g = (float)std::atof(next("--g"));
+        else if (a == "--isotropic") o.isotropic = true;
+        else if (a == "--absorption") o.absorption = (float)std::atof(next("--absorption"));
+        else if (a == "--density-scaling") o.density_scaling = (float)std::atof(next("--density-scaling"));
+        else if (a == "--fov") o.fov = (float)std::atof(next("--fov"));
+        else if (a == "--light") { if (std::sscanf(next("--light"), "%f,%f,%f", &o.light[0], &o.light[1], &o.light[2]) != 3) return false; }
+        else if (a == "--per-frame") o.per_frame = true;
+        else if (a == "--device") o.device = std::atoi(next("--device"));
+        else if (a == "--pfm") o.pfm = next("--pfm");
+        else return false;
+    }
+    return o.width > 0 && o.height > 0 && o.spp > 0 && o.nsv > 0;
+}
+
+uint64_t fnv1a(const void* data, size_t n)
+{
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// the g_* globals of main.cpp that the hot path touches (main.cpp:31-97)
+struct App {
+    crv::PushConstants pushConstants;
+    crv::CameraProperties cameraProperties;
+    crv::CloudProperties cloudProperties;
+    crv::Parameters parameters;
+    crv::ShadowVolumeProperties shadowVolumeProperties;
+    float lightDirection[3] = {1, -1, 0};
+
+    std::unique_ptr<crv::Device> device;
+    std::unique_ptr<crv::Volume> cloudImage, shadowVolumeImage;
+    std::unique_ptr<crv::Image> resultImage;
+    std::unique_ptr<crv::RenderTechniqueSV> shadowVolumeTechnique;
+    std::unique_ptr<crv::RenderTechniquePT> pathTracingTechnique;
+
+    // main.cpp:223-264
+    void UpdateShadowVolume()
+    {
+        shadowVolumeProperties.SetLightDirection(lightDirection);
+        shadowVolumeProperties.SetOrigin(cloudProperties.bounds[0], cloudProperties.bounds[1]);
+        crv::DescriptorBufferInfo svInfo{&shadowVolumeProperties, sizeof(shadowVolumeProperties)};
+        shadowVolumeTechnique->QueueUpdateShadowVolume(svInfo, 0);
+        shadowVolumeTechnique->UpdateDescriptorSets();
+        device->WaitIdle();
+        shadowVolumeTechnique->RecordDrawCommands(nullptr, 0);
+        device->WaitIdle();
+        pathTracingTechnique->QueueUpdateShadowVolume(svInfo, 0);
+        pathTracingTechnique->UpdateDescriptorSets();
+        pushConstants.frameCount = 0;      // headless: zero-cleared image, plain mean
+        resultImage->Clear();
+    }
+
+    // main.cpp:266-335 (after the grid is in cloudImage)
+    void UpdateCloudData()
+    {
+        crv::DescriptorBufferInfo cloudInfo{&cloudProperties, sizeof(cloudProperties)};
+        crv::DescriptorImageInfo cloudImageInfo{cloudImage.get()};
+        pathTracingTechnique->QueueUpdateCloudData(cloudInfo, 0);
+        pathTracingTechnique->QueueUpdateCloudDataSampler(cloudImageInfo, 0);
+        shadowVolumeTechnique->QueueUpdateCloudData(cloudInfo, 0);
+        shadowVolumeTechnique->QueueUpdateCloudDataSampler(cloudImageInfo, 0);
+        pathTracingTechnique->UpdateDescriptorSets();
+        shadowVolumeTechnique->UpdateDescriptorSets();
+        UpdateShadowVolume();
+    }
+};
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    Options o;
+    if (!parse(argc, argv, o)) {
+        std::fprintf(stderr, "usage: crv_headless [--xyz file | --fbm N] [--width W --height H] [--spp S] [--nsv N] [--g G | --isotropic]\n"
+                             "                    [--absorption A] [--density-scaling D] [--light x,y,z] [--fov F] [--per-frame] [--device i] [--pfm out]\n");
+        return 2;
+    }
+    try {
+        App app;
+        app.device = std::make_unique<crv::Device>(o.device);
+        std::memcpy(app.lightDirection, o.light, sizeof(o.light));
+        app.shadowVolumeProperties.voxelAxisCount = o.nsv;
+        app.pushConstants.frameCount = 0;
+        // SetResolution before SetFOV (main.cpp:383-384)
+        app.cameraProperties.SetResolution(o.width, o.height);
+        app.cameraProperties.SetFOV(o.fov);
+        app.cloudProperties.densityScaling = o.density_scaling;
+        if (!o.isotropic) app.parameters.SetPhaseG(o.g);
+
+        // ---- InitializeVulkan (main.cpp:765-910), minus Vulkan ----
+        app.shadowVolumeImage = std::make_unique<crv::Volume>(app.device.get(), o.nsv, o.nsv, o.nsv);
+        app.resultImage = std::make_unique<crv::Image>(app.device.get(), (uint32_t)o.width, (uint32_t)o.height);
+        app.shadowVolumeTechnique = std::make_unique<crv::RenderTechniqueSV>(app.device.get(), &app.shadowVolumeProperties, &app.pushConstants);
+        app.pathTracingTechnique = std::make_unique<crv::RenderTechniquePT>(app.device.get(), &app.cameraProperties, &app.pushConstants);
+        std::vector<crv::FrameImage> svFrames{crv::FrameImage(app.shadowVolumeImage.get())};
+        std::vector<crv::FrameImage> ptFrames{crv::FrameImage(app.resultImage.get())};
+        app.shadowVolumeTechnique->SetFrameReferences(svFrames);
+        app.pathTracingTechnique->SetFrameReferences(ptFrames);
+        crv::DescriptorBufferInfo paramInfo{&app.parameters, sizeof(app.parameters)};
+        crv::DescriptorBufferInfo cameraInfo{&app.cameraProperties, sizeof(app.cameraProperties)};
+        crv::DescriptorImageInfo svImageInfo{app.shadowVolumeImage.get()};
+        app.pathTracingTechnique->QueueUpdateParameters(paramInfo, 0);
+        app.pathTracingTechnique->QueueUpdateCameraProperties(cameraInfo, 0);
+        app.pathTracingTechnique->QueueUpdateShadowVolumeSampler(svImageInfo, 0);
+        app.pathTracingTechnique->UpdateDescriptorSets();
+        crv::PathTracerExtensions ext;
+        ext.absorption = o.absorption;
+        app.pathTracingTechnique->SetExtensions(ext);
+
+        // ---- LoadCloudFile (main.cpp:166-190) or the synthetic fBm scene, then SetCloudProperties (main.cpp:144-163) ----
+        uint32_t counts[3];
+        double voxel[3];
+        if (!o.xyz.empty()) {
+            std::unique_ptr<crv::Grid3D<float>> grid(crv::Grid3D<float>::Load(o.xyz));
+            if (!grid) { std::fprintf(stderr, "crv_headless: cannot open %s\n", o.xyz.c_str()); return 1; }
+            const auto c = grid->GetVoxelCount();
+            const auto v = grid->GetVoxelSize();
+            for (int i = 0; i < 3; ++i) { counts[i] = c[i]; voxel[i] = v[i]; }
+            app.cloudImage = std::make_unique<crv::Volume>(app.device.get(), counts[0], counts[1], counts[2]);
+            app.cloudImage->Upload(grid->data());
+            app.device->WaitIdle();
+        } else {
+            for (int i = 0; i < 3; ++i) { counts[i] = o.fbm; voxel[i] = 1.0 / o.fbm; }
+            app.cloudImage = std::make_unique<crv::Volume>(app.device.get(), o.fbm, o.fbm, o.fbm);
+            app.cloudImage->GenerateFbm(1234);
+        }
+        app.cloudProperties.SetFromGrid(counts, voxel, app.cloudImage->GetMajorant());
+        app.UpdateCloudData();
+        const float sv_ms = app.shadowVolumeTechnique->LastBuildMs();
+
+        // ---- RenderLoop (main.cpp:714-736): srand(0); per frame seed = rand() ----
+        std::vector<int32_t> seeds(o.spp);
+        crv::MsvcRandSequence(0, o.spp, seeds.data());
+        app.device->WaitIdle();
+        const auto t0 = std::chrono::steady_clock::now();
+        if (o.per_frame) {
+            for (unsigned f = 0; f < o.spp; ++f) {
+                app.pushConstants.seed = seeds[f];
+                app.pathTracingTechnique->RecordDrawCommands(nullptr, 0);
+                app.pushConstants.frameCount++;
+            }
+        } else {
+            app.pathTracingTechnique->RenderBatch(seeds.data(), o.spp, 0, CRV_ACCUM_RUNNING_MEAN, nullptr, 0);
+            app.pushConstants.frameCount += o.spp;
+        }
+        app.device->WaitIdle();
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+        std::vector<float> rgba((size_t)o.width * o.height * 4);
+        app.resultImage->Download(rgba.data());
+        const crv_pt_stats st = app.pathTracingTechnique->GetStats();
+        if (!o.pfm.empty()) {
+            // PFM: RGB float, bottom-up rows, little endian
+            FILE* f = std::fopen(o.pfm.c_str(), "wb");
+            if (!f) { std::fprintf(stderr, "crv_headless: cannot write %s\n", o.pfm.c_str()); return 1; }
+            std::fprintf(f, "PF\n%d %d\n-1.0\n", o.width, o.height);
+            for (int y = o.height - 1; y >= 0; --y)
+                for (int x = 0; x < o.width; ++x) std::fwrite(&rgba[((size_t)y * o.width + x) * 4], sizeof(float), 3, f);
+            std::fclose(f);
+        }
+        std::printf("{\"width\": %d, \"height\": %d, \"spp\": %u, \"mode\": \"%s\", \"render_ms\": %.3f, \"mpath_samples_per_s\": %.1f, "
+                    "\"sv_build_ms\": %.4f, \"paths\": %llu, \"tracking_steps\": %llu, \"collisions\": %llu, \"kernel_launches\": %llu, "
+                    "\"image_fnv1a\": \"%016llx\"}\n",
+                    o.width, o.height, o.spp, o.per_frame ? "per-frame" : "batch", ms, (double)o.width * o.height * o.spp / ms / 1e3, sv_ms,
+                    (unsigned long long)st.paths, (unsigned long long)st.tracking_steps, (unsigned long long)st.collisions,
+                    (unsigned long long)app.device->LaunchCount(), (unsigned long long)fnv1a(rgba.data(), rgba.size() * sizeof(float)));
+        return 0;
+    } catch (const crv::Error& e) {
+        std::fprintf(stderr, "crv_headless: error %d: %s\n", e.code(), e.what());
+        return e.code() == CRV_ERR_NO_DEVICE ? 3 : 1;
+    }
+}

@@ -1,0 +1,56 @@
+"""The C++ host side (include/crv/render_technique.h + crv_headless, the reference's main.cpp role) over the C ABI."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "cloudrendering_vulkan_b200", "bin", "crv_headless")
+
+
+def _run(args):
+    return subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, timeout=300)
+
+
+def _fnv1a(buf: bytes) -> str:
+    h = 1469598103934665603
+    for b in buf:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+def test_cpp_driver_is_built_and_fails_loudly_without_a_gpu(crv):
+    assert os.path.exists(BIN), "crv_headless was not built (make -C cloudrendering_vulkan_b200/csrc)"
+    if crv.capi.lib.crv_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = _run(["--fbm", 16, "--width", 32, "--height", 32, "--nsv", 16])
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def test_cpp_driver_rejects_bad_arguments():
+    assert _run(["--no-such-flag"]).returncode == 2
+
+
+@pytest.mark.gpu
+def test_cpp_driver_matches_the_python_host_bitwise(crv, ctx):
+    """same scene through the C++ RenderTechnique classes (batch and frame-by-frame) and through the Python mirror:
+    identical image bits -- both are thin hosts over the same C ABI"""
+    n, w, h, nsv, spp = 40, 96, 64, 56, 5
+    args = ["--fbm", n, "--width", w, "--height", h, "--nsv", nsv, "--spp", spp, "--g", 0.85, "--absorption", 0.1]
+    out = {}
+    for mode in ([], ["--per-frame"]):
+        r = _run(args + mode)
+        assert r.returncode == 0, r.stderr
+        out[bool(mode)] = json.loads(r.stdout)
+    assert out[False]["image_fnv1a"] == out[True]["image_fnv1a"]
+    assert out[False]["paths"] == w * h * spp and out[False]["collisions"] > 0
+    wl = crv.Workload("t", n, w, h, spp, nsv, 50.0, 0.1, 0.85)
+    r = crv.make_renderer(ctx, wl, cloud_layout="brick")
+    r.set_cloud_synthetic(n, 1234)
+    seeds = crv.msvc_rand_sequence(spp)
+    r.pathTracingTechnique.RenderBatch(seeds, 0, crv.ACCUM_RUNNING_MEAN, 0, 0)
+    img = np.ascontiguousarray(r.resultImage.download(), np.float32)
+    assert _fnv1a(img.tobytes()) == out[False]["image_fnv1a"]
+    r.close()
