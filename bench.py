@@ -176,7 +176,7 @@ def run_reference(args, wl):
                          "note": "CPU restatement of the shaders (lavapipe / SPIR-V unavailable in this image)"},
         "e2e": {"value": value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -384,11 +384,28 @@ def run_ours(args, wl):
                    "frac_of_peak": sv_bytes / sv_ms / 1e6 / peak, "peak_source": peak_src},
             "cpu_baseline": cpu_baseline, "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Route everything C libraries print on fd 1 (NCCL's version banner) to stderr; the JSON line keeps the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -416,6 +433,7 @@ def main():
     if args.impl == "ours" and world != args.gpus and args.gpus > 1:
         print(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})", file=sys.stderr)
         return 2
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args, wl)
     return run_ours(args, wl)
