@@ -220,8 +220,9 @@ def run_ours(args, wl):
     r.resultImage.close()
     r.resultImage = img
     r.pathTracingTechnique.SetFrameReferences([img])
-    if args.track_threshold or args.ctas_per_sm:
-        r.pathTracingTechnique.SetTuning(ctas_per_sm=args.ctas_per_sm, track_threshold=args.track_threshold)
+    if args.track_threshold or args.ctas_per_sm or args.steps_per_decision:
+        r.pathTracingTechnique.SetTuning(ctas_per_sm=args.ctas_per_sm, track_threshold=args.track_threshold,
+                                         steps_per_decision=args.steps_per_decision)
     r.set_cloud_synthetic(wl.n_cloud, wl.fbm_seed, stream)
     ctx.synchronize(stream)
     # shadow-volume rebuild: 3 warm rebuilds, then the median of 7 (CUDA events on the launching stream, around the kernel)
@@ -419,6 +420,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override spp per GPU (the default is the config's)")
     ap.add_argument("--track-threshold", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--steps-per-decision", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

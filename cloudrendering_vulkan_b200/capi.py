@@ -136,8 +136,9 @@ SIGNATURES = {
     "crv_pt_last_render_ms": (C.c_int, [_vp, _P(C.c_float), _P(C.c_uint)]),
     "crv_pt_set_debug_counters": (C.c_int, [_vp, C.c_int]),
     "crv_pt_download_debug_counters": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "crv_pt_selftest_log": (C.c_int, [_vp, _P(C.c_uint64), _vp]),
     "crv_pt_rng_tap": (C.c_int, [_vp, _i32, _u32, _u32, _u32, _vp, _vp]),
-    "crv_pt_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64]),
+    "crv_pt_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "crv_push_constants_init": (None, [_P(PushConstantsPOD)]),
     "crv_camera_init": (None, [_P(CameraPropertiesPOD)]),
     "crv_camera_set_resolution": (None, [_P(CameraPropertiesPOD), C.c_int, C.c_int]),

@@ -7,6 +7,7 @@
 // -ffp-contract=off), because the kernels take these values as if the shader had computed them.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -119,6 +120,7 @@ struct crv_pt {
     // tuning
     int ctas_per_sm = 0;
     int track_threshold = 20;
+    int steps_per_decision = 6;
     uint64_t sample_budget = 2ull << 30;
 };
 
@@ -760,11 +762,12 @@ int crv_pt_set_extensions(crv_pt* pt, const crv_pt_extensions* ext)
     return CRV_OK;
 }
 
-int crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes)
+int crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes, int steps_per_decision)
 {
     CRV_REQUIRE(pt != nullptr, "crv_pt_set_tuning: null technique");
     pt->ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 0;
     if (track_threshold > 0) pt->track_threshold = track_threshold > 32 ? 32 : track_threshold;
+    if (steps_per_decision > 0) pt->steps_per_decision = steps_per_decision > 64 ? 64 : steps_per_decision;
     if (sample_buffer_bytes > 0) pt->sample_budget = sample_buffer_bytes;
     return CRV_OK;
 }
@@ -889,6 +892,7 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
     c.job_counter = pt->job_counter;
     c.stats = pt->stats;
     c.track_threshold = pt->track_threshold;
+    c.steps_per_decision = pt->steps_per_decision;
     return CRV_OK;
 }
 
@@ -1065,6 +1069,23 @@ int crv_pt_download_debug_counters(crv_pt* pt, uint32_t* steps, uint32_t* collis
     if (collisions) CRV_CUDA(cudaMemcpyAsync(collisions, pt->dbg_coll, sizeof(uint32_t) * pt->dbg_elems, cudaMemcpyDeviceToHost, s));
     CRV_CUDA(cudaStreamSynchronize(s));
     return CRV_OK;
+}
+
+int crv_pt_selftest_log(crv_ctx* ctx, uint64_t* mismatches, void* stream)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(mismatches != nullptr, "crv_pt_selftest_log: null argument");
+    cudaStream_t s = as_stream(stream);
+    unsigned long long* d = nullptr;
+    CRV_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    CRV_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));
+    int rc = crv_launch_log_selftest(ctx, d, s);
+    unsigned long long h = 0;
+    if (rc == CRV_OK && cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = CRV_ERR_CUDA;
+    cudaStreamSynchronize(s);
+    cudaFree(d);
+    *mismatches = h;
+    return rc;
 }
 
 int crv_pt_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t width, uint32_t height, uint32_t n_draws, uint32_t* host_out, void* stream)

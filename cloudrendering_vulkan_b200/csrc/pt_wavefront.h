@@ -67,6 +67,7 @@ struct PTConst {
     uint32_t* dbg_steps;               // per-pixel counters (single-frame renders, both null or both set)
     uint32_t* dbg_collisions;
     int track_threshold;               // service collisions/regeneration once fewer lanes than this are tracking
+    int steps_per_decision;            // tracking steps between two scheduling decisions
 };
 
 struct FoldConst {
@@ -83,4 +84,5 @@ int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, u
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
 int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);
+int crv_launch_log_selftest(crv_ctx* ctx, unsigned long long* d_mismatches, cudaStream_t s);
 int crv_launch_scale(crv_ctx* ctx, float* data, size_t n, float scale, cudaStream_t s);

@@ -354,8 +354,9 @@ class RenderTechniquePT(RenderTechnique):
                                                  coll.ctypes.data_as(C.c_void_p), _stream(stream)))
         return steps, coll
 
-    def SetTuning(self, ctas_per_sm: int = 0, track_threshold: int = 0, sample_buffer_bytes: int = 0):
-        check(lib.crv_pt_set_tuning(self.handle, int(ctas_per_sm), int(track_threshold), C.c_uint64(sample_buffer_bytes)))
+    def SetTuning(self, ctas_per_sm: int = 0, track_threshold: int = 0, sample_buffer_bytes: int = 0, steps_per_decision: int = 0):
+        check(lib.crv_pt_set_tuning(self.handle, int(ctas_per_sm), int(track_threshold), C.c_uint64(sample_buffer_bytes),
+                                    int(steps_per_decision)))
 
     def close(self):
         if self.handle:

@@ -248,9 +248,12 @@ int  crv_pt_download_debug_counters(crv_pt* pt, uint32_t* steps, uint32_t* colli
  * with dispatch stride 32*(W/32+1) (PathTracer.comp:220-241,368): bit-exact RNG tap. */
 int  crv_pt_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t width, uint32_t height, uint32_t n_draws,
                     uint32_t* host_out, void* stream);
+/* Self-test: the tracker's -log(zeta) (the math library's logf algorithm restricted to zeta in {0} U [2^-32, 1]) against
+ * logf for EVERY float of that set; returns the number of inputs whose results differ in any bit (expected 0). */
+int  crv_pt_selftest_log(crv_ctx* ctx, uint64_t* mismatches, void* stream);
 /* tuning knobs (0 = library default): CTAs per SM, min tracking lanes before servicing, max
- * bytes of the per-round sample buffer */
-int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes);
+ * bytes of the per-round sample buffer, tracking steps between two scheduling decisions */
+int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes, int steps_per_decision);
 
 /* ---- host-side helpers with the reference's setter semantics (UniformBuffers.h) ------------ */
 void crv_push_constants_init(crv_push_constants* p);                                   /* :6-13   */

@@ -41,6 +41,14 @@ def test_rng_tap_bit_exact(crv, orc, ctx):
             assert np.array_equal(gpu, cpu), f"RNG stream differs for seed {seed} at {w}x{h}"
 
 
+def test_tracker_log_equals_logf_exhaustively(crv, ctx):
+    """the tracker's trimmed -log(zeta) gives the same bits as -logf(zeta) for every float in {0} U [2^-32, 1]"""
+    import ctypes as C
+    n = C.c_uint64(123)
+    crv.capi.check(crv.capi.lib.crv_pt_selftest_log(ctx.handle, C.byref(n), None))
+    assert n.value == 0, f"{n.value} inputs differ from logf"
+
+
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_volume_roundtrip_and_majorant(crv, ctx, layout):
     rng = np.random.default_rng(7)

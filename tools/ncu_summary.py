@@ -109,11 +109,64 @@ def source(path, top=40):
         print(f"{100 * l[4] / ti:6.2f}%  {l[5]:5.1f}  {l[0]}:{l[1]:<4d} {l[2][:110]}")
 
 
+def functions(path):
+    """warp instructions and average active lanes per source function (inlined device functions keep their own lines)"""
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    fpath, h, lines = "?", None, []
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fpath = r[1]
+        elif r[0] == "Line No":
+            h = r
+        elif h is not None and len(r) == len(h) and r[0].isdigit():
+            g = lambda n: float(r[h.index(n)].replace(",", "") or 0)
+            lines.append((fpath, int(r[0]), g("Instructions Executed"), g("Thread Instructions Executed"), g("# Samples")))
+    cache = {}
+
+    def region(f, l):
+        if f not in cache:
+            try:
+                cache[f] = open(f).read().split("\n")
+            except Exception:
+                cache[f] = None
+        src = cache[f]
+        if src is None:
+            return f.split("/")[-1]
+        for i in range(min(l, len(src)) - 1, -1, -1):
+            if "__device__" in src[i] or "__global__" in src[i]:
+                j = i
+                while j < len(src) and "(" not in src[j].split("__launch_bounds__")[-1].split("__forceinline__")[-1]:
+                    j += 1
+                m = re.search(r"(\w+)\s*\(", src[j].split("__forceinline__")[-1].split("__launch_bounds__(PT_THREADS)")[-1])
+                return f.split("/")[-1] + ":" + (m.group(1) if m else "?")
+        return f.split("/")[-1]
+
+    agg = {}
+    for f, l, wi, thi, smp in lines:
+        a = agg.setdefault(region(f, l), [0.0, 0.0, 0.0])
+        a[0] += wi
+        a[1] += thi
+        a[2] += smp
+    ti = sum(a[0] for a in agg.values()) or 1.0
+    tt = sum(a[1] for a in agg.values())
+    ts = sum(a[2] for a in agg.values()) or 1.0
+    print(f"# {path}: {int(ti)} warp instructions, {tt / ti:.2f} of 32 lanes active on average")
+    print(f"{'function':44s} {'warp-inst':>9s} {'lanes':>6s} {'stall samples':>13s}")
+    for k, a in sorted(agg.items(), key=lambda x: -x[1][0]):
+        print(f"{k:44s} {100 * a[0] / ti:8.2f}% {a[1] / max(a[0], 1):6.1f} {100 * a[2] / ts:12.2f}%")
+
+
 if __name__ == "__main__":
     mode, path = sys.argv[1], sys.argv[2]
     if mode == "launches":
         launches(path)
     elif mode == "full":
         full(path)
+    elif mode == "functions":
+        functions(path)
     else:
         source(path, int(sys.argv[3]) if len(sys.argv) > 3 else 40)
