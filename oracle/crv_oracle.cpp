@@ -2,8 +2,9 @@
 //
 // Function-for-function scalar fp32 restatement of the reference shaders; every function cites the shader
 // lines it follows.  Build: g++ -O2 -ffp-contract=off -fno-fast-math -fopenmp (oracle/Makefile).
-// PARITY STATUS: parity unpinned by the reference (no SPIR-V, no golden vectors, no Vulkan in this image);
-// the shader text is the specification.  Driver-defined behaviour is fixed as documented in crv_oracle.h.
+// PARITY STATUS: pinned bit for bit against the reference's own shader sources compiled by g++ (oracle/_ref/
+// libcrv_refshaders.so, tests/test_ref_shaders.py); driver-defined behaviour (no SPIR-V / Vulkan in this image) is
+// unpinned and fixed as documented in crv_oracle.h.
 #include "crv_oracle.h"
 
 #include <cmath>

@@ -1,0 +1,124 @@
+// oracle/ref_shaders_host.cpp -- CPU dispatch of the reference's OWN compute shaders.  TEST INFRASTRUCTURE ONLY.
+//
+// The two #include lines below pull in /root/reference/shaders/PathTracer.comp and ShadowVolume.comp after the
+// lexical rewrite of oracle/glsl_to_cpp.py (generated into the git-ignored oracle/_ref/, never committed); the GLSL
+// types and built-ins come from oracle/glsl_compat.h.  This file is only the "driver": it binds the descriptor set
+// (RenderTechniquePT.cpp:20-35 bindings 0-6, RenderTechniqueSV.cpp:13-22 bindings 0-3), pushes the constants
+// (RenderTechniquePT.cpp:132) and runs one shader_main() per invocation of the dispatch grid
+// (RenderTechniquePT.cpp:141: (W/32+1) x (H/32+1) groups of 32x32; RenderTechniqueSV.cpp:110: (N/32+1)^2 groups).
+//
+// Built by oracle/Makefile into oracle/_ref/libcrv_refshaders.so only where /root/reference exists; the GPU box uses
+// the prebuilt file.  It pins the restatement (crv_oracle.cpp): tests/test_ref_shaders.py demands bit-identical
+// images, shadow volumes and per-pixel iteration counts between the two.
+#include <omp.h>
+
+#include <cstring>
+
+#include "glsl_compat.h"
+
+namespace glsl {
+namespace pt {
+#include "_ref/PathTracer.comp.inc"
+}
+namespace sv {
+#include "_ref/ShadowVolume.comp.inc"
+}
+}  // namespace glsl
+
+namespace {
+
+template <class Block> void bind_block(Block& dst, const void* src, size_t nbytes, size_t declared)
+{
+    static_assert(sizeof(Block) >= 20, "uniform block unexpectedly small");
+    std::memset(&dst, 0, sizeof(Block));
+    std::memcpy(&dst, src, nbytes < declared ? nbytes : declared);
+}
+
+int resolve_threads(int n) { return n > 0 ? n : omp_get_max_threads(); }
+
+}  // namespace
+
+extern "C" {
+
+// sizes of the uniform blocks as the SHADER declares them (std140 / push-constant layout reproduced by the C++ structs
+// the rewrite emits): checked against the host structs of UniformBuffers.h by tests/test_ref_shaders.py
+void refsh_block_sizes(uint32_t out[7])
+{
+    out[0] = sizeof(glsl::pt::CameraProperties_block);
+    out[1] = sizeof(glsl::pt::CloudProperties_block);
+    out[2] = sizeof(glsl::pt::Parameters_block);
+    out[3] = sizeof(glsl::pt::ShadowVolumeProperties_block);
+    out[4] = offsetof(glsl::pt::PushConstants_block, pmRadius) + sizeof(float);
+    out[5] = sizeof(glsl::sv::ShadowVolumeProperties_block);
+    out[6] = sizeof(glsl::sv::CloudProperties_block);
+}
+
+// One vkCmdDispatch of PathTracer.comp.  image = W*H rgba32f, updated in place by the shader's own accumulate.
+// Only invocations with x in [x0,x1), y in [y0,y1), (y - y0) % row_step == 0 run (x1/y1 may extend into the
+// off-image part of the dispatch grid, whose stores are discarded as on the GPU).
+// steps / collisions (optional, W*H): calls of log() (one per delta-tracking iteration, :338) and of
+// texture(shadowSampler) (one per real collision, :126) made by the invocation -- counted by the compat layer,
+// the shader text is not instrumented.
+void refsh_path_trace(const float* cloud, int nx, int ny, int nz, const float* shadow, int nsv, const void* camera68,
+                      const void* cloud60, const void* params28, const void* svprops152, const void* push24, float* image,
+                      int x0, int y0, int x1, int y1, int row_step, uint32_t* steps, uint32_t* collisions, int num_threads)
+{
+    using namespace glsl::pt;
+    bind_block(cameraProperties, camera68, 68, sizeof(cameraProperties));
+    bind_block(cloudProperties, cloud60, 60, sizeof(cloudProperties));
+    bind_block(parameters, params28, 28, sizeof(parameters));
+    bind_block(shadowVolumeProperties, svprops152, 152, sizeof(shadowVolumeProperties));
+    bind_block(pushConstants, push24, 20, sizeof(pushConstants));
+    const int W = cameraProperties.halfWidth * 2, H = cameraProperties.halfHeight * 2;      // CameraProperties::GetWidth/Height
+    cloudSampler.texels = cloud; cloudSampler.nx = nx; cloudSampler.ny = ny; cloudSampler.nz = nz; cloudSampler.slot = 0;
+    shadowSampler.texels = shadow; shadowSampler.nx = shadowSampler.ny = shadowSampler.nz = nsv; shadowSampler.slot = 1;
+    resultImage.texels = image; resultImage.width = W; resultImage.height = H;
+    const glsl::uvec3 groups((uint32_t)(W / 32 + 1), (uint32_t)(H / 32 + 1), 1u);
+    const int gx_end = (int)(groups.x * 32u), gy_end = (int)(groups.y * 32u);
+    if (x1 > gx_end) x1 = gx_end;
+    if (y1 > gy_end) y1 = gy_end;
+    if (row_step < 1) row_step = 1;
+    const int nrows = y1 > y0 ? (y1 - y0 + row_step - 1) / row_step : 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(resolve_threads(num_threads))
+    for (int r = 0; r < nrows; ++r) {
+        const int y = y0 + r * row_step;
+        for (int x = x0; x < x1; ++x) {
+            glsl::invocation().global_id = glsl::uvec3((uint32_t)x, (uint32_t)y, 0u);
+            glsl::invocation().num_groups = groups;
+            glsl::Counters& c = glsl::counters();
+            const uint64_t l0 = c.log_calls, t0 = c.texture_calls[1];
+            shader_main();
+            if (x < W && y < H) {
+                if (steps) steps[(size_t)y * W + x] = (uint32_t)(c.log_calls - l0);
+                if (collisions) collisions[(size_t)y * W + x] = (uint32_t)(c.texture_calls[1] - t0);
+            }
+        }
+    }
+}
+
+// One vkCmdDispatch of ShadowVolume.comp; out = N*N*N r32f, x fastest.
+void refsh_shadow_volume(const float* cloud, int nx, int ny, int nz, const void* cloud60, const void* svprops152, float* out,
+                         int num_threads)
+{
+    using namespace glsl::sv;
+    bind_block(cloudProperties, cloud60, 60, sizeof(cloudProperties));
+    bind_block(shadowVolumeProperties, svprops152, 152, sizeof(shadowVolumeProperties));
+    const int N = (int)shadowVolumeProperties.voxelAxisCount;
+    cloudSampler.texels = cloud; cloudSampler.nx = nx; cloudSampler.ny = ny; cloudSampler.nz = nz; cloudSampler.slot = 0;
+    shadowVolume.texels = out; shadowVolume.nx = shadowVolume.ny = shadowVolume.nz = N;
+    const glsl::uvec3 groups((uint32_t)(N / 32 + 1), (uint32_t)(N / 32 + 1), 1u);
+    const int g_end = (int)(groups.x * 32u);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(resolve_threads(num_threads))
+    for (int y = 0; y < g_end; ++y) {
+        for (int x = 0; x < g_end; ++x) {
+            if (x >= N || y >= N) continue;      // every store of an off-volume column is discarded: skip its work
+            glsl::invocation().global_id = glsl::uvec3((uint32_t)x, (uint32_t)y, 0u);
+            glsl::invocation().num_groups = groups;
+            shader_main();
+        }
+    }
+}
+
+int refsh_max_threads(void) { return omp_get_max_threads(); }
+
+}  // extern "C"

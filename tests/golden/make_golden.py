@@ -6,7 +6,8 @@ Two sources:
     These pin the product's struct mirrors and .xyz reader/writer to real reference behaviour.
   * the CPU oracle (oracle/libcrv_oracle.so): known-answer vectors derived from the shader text, frozen so
     that later edits of the oracle cannot drift silently.  -> oracle_kat.json, oracle_small.npz
-    (The reference itself pins nothing on this path: "parity unpinned", see oracle/crv_oracle.h.)
+    (The reference's own tests pin nothing on this path; the oracle is pinned against the reference's shader
+    sources by make_golden_refshaders.py / tests/test_ref_shaders.py, see oracle/crv_oracle.h.)
 
 Run in the build container (needs /root/reference for the first group):  python tests/golden/make_golden.py
 """

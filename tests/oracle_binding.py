@@ -250,3 +250,59 @@ def reference_scene_structs(n_cloud, width, height, fov, n_sv, light, density_sc
     sh = _raw_buf(152)
     ref.ref_shadow(int(n_sv), 1, _f3(light), 1, _f3(b[0:3]), _f3(b[4:7]), sh)
     return cam, cloud, par, sh
+
+
+# ---- the reference's OWN shaders compiled by g++ (oracle/_ref/libcrv_refshaders.so; see oracle/ref_shaders_host.cpp) ----
+REF_SHADERS_PATH = os.path.join(ORACLE_DIR, "_ref", "libcrv_refshaders.so")
+_refsh = None
+
+
+def ref_shaders_lib():
+    """PathTracer.comp / ShadowVolume.comp themselves, compiled where they lie; None when never built."""
+    global _refsh
+    if _refsh is None and os.path.exists(REF_SHADERS_PATH):
+        _refsh = C.CDLL(REF_SHADERS_PATH)
+        _refsh.refsh_path_trace.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int]
+        _refsh.refsh_shadow_volume.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]
+        _refsh.refsh_block_sizes.argtypes = [_vp]
+        _refsh.refsh_max_threads.restype = C.c_int
+    return _refsh
+
+
+def refsh_block_sizes():
+    out = np.zeros(7, np.uint32)
+    ref_shaders_lib().refsh_block_sizes(_ptr(out))
+    return [int(v) for v in out]
+
+
+def _cloud_dims(cloud_props):
+    return [int(v) for v in np.frombuffer(bytes(cloud_props), np.uint32, 3, 32)]
+
+
+def refsh_shadow_volume(cloud, cloud_props, sv_props, threads=0):
+    """one dispatch of the reference's ShadowVolume.comp on the CPU"""
+    n = int(np.frombuffer(bytes(sv_props), np.uint32, 1, 144)[0])
+    nx, ny, nz = _cloud_dims(cloud_props)
+    v = np.ascontiguousarray(cloud, np.float32)
+    out = np.empty(n * n * n, np.float32)
+    ref_shaders_lib().refsh_shadow_volume(_ptr(v), nx, ny, nz, _raw(cloud_props), _raw(sv_props), _ptr(out), threads)
+    return out
+
+
+def refsh_path_trace(cloud, sv, cam, cloud_props, params, sv_props, push, image, rect=None, row_step=1, want_counters=True,
+                     threads=0):
+    """one dispatch of the reference's PathTracer.comp on the CPU; `image` (H,W,4) is accumulated in place by the
+    shader itself.  Returns (steps, collisions) as counted by the compat layer (log() / texture(shadowSampler) calls)."""
+    w, h = image_size(cam)
+    n = int(np.frombuffer(bytes(sv_props), np.uint32, 1, 144)[0])
+    nx, ny, nz = _cloud_dims(cloud_props)
+    assert cloud.dtype == np.float32 and cloud.flags["C_CONTIGUOUS"] and sv.dtype == np.float32 and sv.flags["C_CONTIGUOUS"]
+    assert image.dtype == np.float32 and image.flags["C_CONTIGUOUS"] and image.size == w * h * 4
+    x0, y0, x1, y1 = rect if rect is not None else (0, 0, w, h)
+    steps = np.zeros((h, w), np.uint32) if want_counters else None
+    coll = np.zeros((h, w), np.uint32) if want_counters else None
+    ref_shaders_lib().refsh_path_trace(_ptr(cloud), nx, ny, nz, _ptr(sv), n, _raw(cam), _raw(cloud_props), _raw(params),
+                                       _raw(sv_props), _raw(push), _ptr(image), x0, y0, x1, y1, int(row_step),
+                                       _ptr(steps), _ptr(coll), threads)
+    return steps, coll

@@ -337,3 +337,82 @@ def test_error_behaviour(crv, ctx):
     sv.close()
     pt.close()
     img.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# against the reference's OWN shaders (tests/golden/refshader_small.*: outputs of PathTracer.comp / ShadowVolume.comp
+# compiled by g++, see tests/test_ref_shaders.py) -- no hand restatement between the CUDA path and the reference here
+# ---------------------------------------------------------------------------------------------------------
+def _refshader_renderer(crv, orc, ctx, case, layout):
+    import json
+    import os
+    from tests.refshader_cases import case_cloud
+    here = os.path.dirname(os.path.abspath(__file__))
+    meta = json.load(open(os.path.join(here, "golden", "refshader_small.json")))[case["name"]]
+    w, h = case["res"]
+    wl = crv.Workload("t", 0, w, h, 1, case["nsv"], case["density_scaling"], 0.0, case["g"], case["light"], case["fov"])
+    r = crv.make_renderer(ctx, wl, cloud_layout=layout)
+    if case["cam_pos"] is not None:
+        for i in range(3):
+            r.cameraProperties.position[i] = case["cam_pos"][i]
+        r.apply_parameters()
+    cloud = case_cloud(orc, case)
+    r.set_cloud_host(cloud, case["grid"], case["voxel"])
+    # the product's own setters must have produced the very bytes the reference's setters did
+    assert bytes(r.cameraProperties).hex() == meta["camera"] and bytes(r.cloudProperties).hex() == meta["cloud"]
+    assert bytes(r.parameters).hex() == meta["parameters"] and bytes(r.shadowVolumeProperties).hex() == meta["shadow"]
+    return r, cloud, meta
+
+
+@pytest.mark.parametrize("layout", ["linear", "brick"])
+@pytest.mark.parametrize("name", ["iso", "hg_dense", "inside", "ragged"])
+def test_cuda_path_against_reference_shader_goldens(crv, orc, ctx, layout, name):
+    import os
+    from tests.refshader_cases import CASES
+    case = [c for c in CASES if c["name"] == name][0]
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refshader_small.npz"))
+    r, cloud, meta = _refshader_renderer(crv, orc, ctx, case, layout)
+    rel = _sv_check(r.shadowVolumeImage.download(), gold[f"{name}_sv"])
+    r.reset_accumulation()
+    pt = r.pathTracingTechnique
+    pt.SetDebugCounters(True)
+    for f, seed in enumerate(meta["seeds"]):          # progressive frames, as RenderLoop issues them
+        r.pushConstants.seed = seed
+        r.pushConstants.frameCount = f
+        pt.RecordDrawCommands(0, 0)
+    gpu = r.resultImage.download()
+    gs, gc = pt.DownloadDebugCounters()
+    ref_img, rs, rc = gold[f"{name}_image"], gold[f"{name}_steps"], gold[f"{name}_coll"]
+    same = (gs == rs) & (gc == rc)
+    err = np.abs(gpu - ref_img) / np.maximum(np.abs(ref_img), 1e-3)
+    ok = same & (err.max(axis=2) <= 1e-4)
+    print(f"{name}/{layout}: sv max rel {rel:.2e}; {int((~same).sum())}/{same.size} threshold-divergent in the last frame; "
+          f"{int(ok.sum())}/{same.size} pixels within 1e-4 of PathTracer.comp's accumulated image")
+    # a path that diverged in an EARLIER frame also moves the accumulated pixel: both kinds are bounded together
+    assert ok.mean() >= 0.97, f"{name}: only {ok.mean():.4f} of the pixels match the reference shader's image"
+    assert same.mean() >= 0.97
+    r.close()
+
+
+def test_cuda_path_against_live_reference_shaders(crv, orc, ctx):
+    """a bigger scene through the compiled reference shaders themselves (prebuilt oracle/_ref/libcrv_refshaders.so)"""
+    if orc.ref_shaders_lib() is None:
+        pytest.skip("oracle/_ref/libcrv_refshaders.so not present")
+    r, cloud = make_scene(crv, orc, ctx, n=64, w=160, h=96, nsv=80, layout="brick", g=0.85, density_scaling=80.0)
+    sv_ref = orc.refsh_shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+    _sv_check(r.shadowVolumeImage.download(), sv_ref)
+    r.reset_accumulation()
+    pt = r.pathTracingTechnique
+    pt.SetDebugCounters(True)
+    r.pushConstants.seed = 7719
+    pt.RecordDrawCommands(0, 0)
+    gpu = r.resultImage.download()
+    gs, gc = pt.DownloadDebugCounters()
+    ref = np.zeros_like(gpu)
+    rs, rc = orc.refsh_path_trace(cloud, sv_ref, r.cameraProperties, r.cloudProperties, r.parameters,
+                                  r.shadowVolumeProperties, orc.push_constants_bytes(7719, 0), ref)
+    same = (gs == rs) & (gc == rc)
+    err = np.abs(gpu - ref) / np.maximum(np.abs(ref), 1e-3)
+    print(f"live reference shaders: {int((~same).sum())}/{same.size} threshold-divergent, max rel err {err[same].max():.2e}")
+    assert same.mean() >= 0.99 and err[same].max() <= 1e-4 and rc.sum() > 1000
+    r.close()
