@@ -176,6 +176,15 @@ int crv_ctx_create(int device, crv_ctx** out)
         return CRV_ERR_NO_DEVICE;
     }
     CRV_CUDA(cudaSetDevice(device));
+    {   // staging buffers (cudaMallocAsync) are re-used across calls instead of going back to the driver at every sync:
+        // a 537 MB upload otherwise pays a fresh device allocation per call
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     crv_ctx* c = new (std::nothrow) crv_ctx();
     if (!c) return CRV_ERR_OOM;
     c->device = device;
@@ -850,11 +859,11 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             pt->qtable = pt->qtable_wide = nullptr;
             pt->qtable_elems = 0;
             CRV_CUDA(cudaMalloc(&pt->qtable, nbricks * sizeof(float)));
-            CRV_CUDA(cudaMalloc(&pt->qtable_wide, nbricks * sizeof(float)));
+            CRV_CUDA(cudaMalloc(&pt->qtable_wide, (size_t)(cv->nbx + 2) * (cv->nby + 2) * (cv->nbz + 2) * sizeof(float)));
             pt->qtable_elems = nbricks;
         }
         CRV_TRY(crv_launch_qtable(pt->ctx, cv->brick_absmax, pt->qtable, (long long)nbricks, c.max_ext, s));
-        CRV_TRY(crv_launch_qtable(pt->ctx, cv->brick_absmax_wide, pt->qtable_wide, (long long)nbricks, c.max_ext, s));
+        CRV_TRY(crv_launch_qtable_padded(pt->ctx, cv->brick_absmax_wide, pt->qtable_wide, (int)cv->nbx, (int)cv->nby, (int)cv->nbz, c.max_ext, s));
         pt->launches += 2;
         pt->q_for_vol = cv;
         pt->q_for_generation = vol_generation(cv);
@@ -872,19 +881,24 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
                     "RenderTechniquePT: extinction scale, cloud extent and shadow-volume extent must be finite and within 1e-18..1e18");
         c.r_sigma = 1.0f / c.sigma;
         c.r_max_ext = 1.0f / c.max_ext;
-        // approximate brick pre-test: u'' = q*asc + aof ~ ((q - cb0)/cext)*size - 1, evaluated with one FMA.  Its error is
-        // a few ulps of the largest term, |cb0/cext|*size; the wide table tolerates 1 texel, we allow 1/4.
+        // approximate brick pre-test: v = q*asc8 + aof8 ~ ((((q - cb0)/cext)*size - 0.5) / 8) + 1, the padded brick
+        // coordinate, evaluated with FMAs.  Its error is a few ulps of the largest term, |cb0/cext|*size (in texels);
+        // the wide table tolerates 1 texel, we allow 1/4.
         c.use_wide = 1;
         for (int i = 0; i < 3; ++i) {
             c.rcext[i] = 1.0f / c.cext[i];
             c.rsden[i] = 1.0f / c.sden[i];
             const double n = i == 0 ? c.cloud.nx : i == 1 ? c.cloud.ny : c.cloud.nz;
-            const double sc = n / (double)c.cext[i], of = -(double)c.cb0[i] * sc - 1.0;
-            c.asc[i] = (float)sc;
-            c.aof[i] = (float)of;
+            const double sc = n / (double)c.cext[i], of = -(double)c.cb0[i] * sc - 0.5;
+            c.asc8[i] = (float)(sc / 8.0);
+            c.aof8[i] = (float)(of / 8.0 + 1.0);
             const double span = std::fabs((double)c.cb0[i]) + std::fabs((double)c.cb1[i]);
             if (!(span * std::fabs(sc) * 4.0 * 1.1920929e-07 < 0.25) || !(n < 2097152.0)) c.use_wide = 0;
         }
+        c.pnbx = (uint32_t)c.cloud.nbx + 2u;
+        c.pnbxy = c.pnbx * ((uint32_t)c.cloud.nby + 2u);
+        c.pbias = 0x4B000000u * (1u + c.pnbx + c.pnbxy);          // mod 2^32, like the device-side sum it cancels
+        c.pmax = c.pnbxy * ((uint32_t)c.cloud.nbz + 2u) - 1u;
     }
 
     c.npix = (uint32_t)W * (uint32_t)H;

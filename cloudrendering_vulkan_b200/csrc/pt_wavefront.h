@@ -28,7 +28,10 @@ struct PTConst {
     float density_scaling;
     float r_sigma, r_max_ext, rcext[3]; // RN(1/x) of the divisors above (host IEEE division) for exact_div.cuh
     int use_wide;                      // 1: approximate brick pre-test enabled (its error bound holds for this geometry)
-    float asc[3], aof[3];              // approximate texel coordinate: q*asc + aof ~ ((q - cb0)/cext)*size - 1
+    // approximate PADDED brick coordinate: q*asc8 + aof8 ~ (((q - cb0)/cext)*size - 0.5)/8 + 1, floored by a round-down
+    // magic add; (pnbx, pnbxy) are the strides of the padded table and pbias removes the three magic exponents
+    float asc8[3], aof8[3];
+    uint32_t pnbx, pnbxy, pbias, pmax;
 
     // ---- Parameters (:68-78) ----
     float light_intensity;             // 1.0f * lightIntensity
@@ -49,7 +52,8 @@ struct PTConst {
     // ---- resources ----
     VolView cloud, sv;
     const float* qtable;               // per 8^3 brick: upper bound of ext/maxExtinction over voxels [8b, 8b+8]^3
-    const float* qtable_wide;          // same over voxels [8b-1, 8b+9]^3: valid for a brick index that is off by < 1 texel
+    const float* qtable_wide;          // same over voxels [8b-1, 8b+9]^3: valid for a brick index that is off by < 1 texel;
+                                       // stored with one brick of clamp-to-edge padding on every side ((nbx+2)(nby+2)(nbz+2))
     const uint32_t* hitlist;           // pixels whose camera ray enters the box (pt_classify_kernel), x | y << 16, *nhit entries
     const uint32_t* nhit;
     const float* start;                // per hit pixel, SoA with stride npix: entry point xyz, direction xyz, exit distance
@@ -83,6 +87,7 @@ int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layou
 int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, uint32_t* hitlist, float* start, uint32_t* nhit, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
+int crv_launch_qtable_padded(crv_ctx* ctx, const float* absmax_wide, float* qpad, int nbx, int nby, int nbz, float max_ext, cudaStream_t s);
 int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);
 int crv_launch_log_selftest(crv_ctx* ctx, unsigned long long* d_mismatches, cudaStream_t s);
 int crv_launch_scale(crv_ctx* ctx, float* data, size_t n, float scale, cudaStream_t s);
