@@ -213,7 +213,7 @@ def _config_dict(wl, args, world, layout):
                         f"densityScaling {wl.density_scaling:g}, absorption {wl.absorption:g}, "
                         f"g {wl.phase_g if wl.phase_g is not None else 'isotropic'}, N_sv {wl.n_sv}",
             "spp_total": wl.spp * world, "parallelism": f"spp-split x{world} (grid replicated, fp32 sum all-reduce)",
-            "layout": layout,
+            "layout": layout, "math": "libm" if layout == "cpu" else getattr(args, "math", "strict"),
             "l2": "inputs larger than L2 (grid + shadow volume >= 1 GB vs 126 MB)"}
 
 
@@ -241,7 +241,8 @@ def run_ours(args, wl):
 
     ctx = crv.Context(local)
     W, H, spp = wl.width, wl.height, wl.spp
-    r = crv.make_renderer(ctx, wl, cloud_layout=args.layout)
+    math_mode = crv.PT_MATH_DRIVER if args.math == "driver" else crv.PT_MATH_STRICT
+    r = crv.make_renderer(ctx, wl, cloud_layout=args.layout, math_mode=math_mode)
     # accumulation buffer owned by torch so that NCCL can reduce it in place
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     img = crv.Image(ctx, W, H, device_ptr=accum.data_ptr())
@@ -452,6 +453,10 @@ def main():
     ap.add_argument("--track-threshold", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--steps-per-decision", type=int, default=0)
+    ap.add_argument("--math", default="driver", choices=["strict", "driver"],
+                    help="free-flight update t += -log(zeta)/sigma: 'strict' = logf-accurate log, IEEE divide, IEEE add; "
+                         "'driver' = lg2 on the SFU * (-ln2/sigma) in one FMA, the latitude GLSL gives a Vulkan driver "
+                         "(crv_c_api.h: crv_pt_math_mode)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -25,6 +25,8 @@ LAYOUTS = {"linear": LAYOUT_LINEAR, "brick": LAYOUT_BRICK, "tex3d": LAYOUT_TEX3D
 
 ACCUM_RUNNING_MEAN = 0
 ACCUM_SUM = 1
+PT_MATH_STRICT = 0
+PT_MATH_DRIVER = 1
 
 
 # ---- parameter blocks: byte-for-byte UniformBuffers.h:6-167 ---------------------------------------------
@@ -57,7 +59,7 @@ class ShadowVolumePropertiesPOD(C.Structure):
 
 
 class PTExtensionsPOD(C.Structure):
-    _fields_ = [("absorption", C.c_float), ("reserved", C.c_uint32 * 3)]
+    _fields_ = [("absorption", C.c_float), ("math_mode", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class PTStats(C.Structure):

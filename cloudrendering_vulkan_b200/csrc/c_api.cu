@@ -767,6 +767,7 @@ int crv_pt_set_extensions(crv_pt* pt, const crv_pt_extensions* ext)
 {
     CRV_REQUIRE(pt && ext, "crv_pt_set_extensions: null argument");
     CRV_REQUIRE(ext->absorption >= 0.0f && ext->absorption <= 1.0f, "crv_pt_set_extensions: absorption must be in [0,1]");
+    CRV_REQUIRE(ext->math_mode == CRV_PT_MATH_STRICT || ext->math_mode == CRV_PT_MATH_DRIVER, "crv_pt_set_extensions: unknown math_mode");
     pt->ext = *ext;
     return CRV_OK;
 }
@@ -859,7 +860,7 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             pt->qtable = pt->qtable_wide = nullptr;
             pt->qtable_elems = 0;
             CRV_CUDA(cudaMalloc(&pt->qtable, nbricks * sizeof(float)));
-            CRV_CUDA(cudaMalloc(&pt->qtable_wide, (size_t)(cv->nbx + 2) * (cv->nby + 2) * (cv->nbz + 2) * sizeof(float)));
+            CRV_CUDA(cudaMalloc(&pt->qtable_wide, ((size_t)(cv->nbx + 2) * (cv->nby + 2) * (cv->nbz + 2) + 1) * sizeof(float)));   // + the +inf entry
             pt->qtable_elems = nbricks;
         }
         CRV_TRY(crv_launch_qtable(pt->ctx, cv->brick_absmax, pt->qtable, (long long)nbricks, c.max_ext, s));
@@ -880,6 +881,8 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
         CRV_REQUIRE(ok || !(c.density_scaling > 0.0f),
                     "RenderTechniquePT: extinction scale, cloud extent and shadow-volume extent must be finite and within 1e-18..1e18");
         c.r_sigma = 1.0f / c.sigma;
+        c.neg_ln2_over_sigma = (float)(-0.69314718055994530942 / (double)c.sigma);
+        c.math_mode = (int)pt->ext.math_mode;
         c.r_max_ext = 1.0f / c.max_ext;
         // approximate brick pre-test: v = q*asc8 + aof8 ~ ((((q - cb0)/cext)*size - 0.5) / 8) + 1, the padded brick
         // coordinate, evaluated with FMAs.  Its error is a few ulps of the largest term, |cb0/cext|*size (in texels);
@@ -899,6 +902,13 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
         c.pnbxy = c.pnbx * ((uint32_t)c.cloud.nby + 2u);
         c.pbias = 0x4B000000u * (1u + c.pnbx + c.pnbxy);          // mod 2^32, like the device-side sum it cancels
         c.pmax = c.pnbxy * ((uint32_t)c.cloud.nbz + 2u) - 1u;
+        if (!c.use_wide) {
+            // every approximate coordinate collapses to 0 and the bias moves the index to the +inf entry behind the
+            // table: the pre-test never rejects and every tentative collision goes through the exact sampler
+            for (int i = 0; i < 3; ++i) c.asc8[i] = c.aof8[i] = 0.0f;
+            c.pmax += 1u;
+            c.pbias -= c.pmax;
+        }
     }
 
     c.npix = (uint32_t)W * (uint32_t)H;

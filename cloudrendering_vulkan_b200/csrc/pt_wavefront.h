@@ -27,7 +27,10 @@ struct PTConst {
     float sigma;                       // (maxExtinction * densityScaling) / baseScaling   (:338)
     float density_scaling;
     float r_sigma, r_max_ext, rcext[3]; // RN(1/x) of the divisors above (host IEEE division) for exact_div.cuh
-    int use_wide;                      // 1: approximate brick pre-test enabled (its error bound holds for this geometry)
+    float neg_ln2_over_sigma;          // CRV_PT_MATH_DRIVER: t += lg2(zeta) * (-ln2 / sigma)
+    int math_mode;                     // crv_pt_math_mode
+    int use_wide;                      // 1: approximate brick pre-test enabled (its error bound holds for this geometry);
+                                       // 0: asc8 = aof8 = 0 and pbias selects the +inf entry behind the table
     // approximate PADDED brick coordinate: q*asc8 + aof8 ~ (((q - cb0)/cext)*size - 0.5)/8 + 1, floored by a round-down
     // magic add; (pnbx, pnbxy) are the strides of the padded table and pbias removes the three magic exponents
     float asc8[3], aof8[3];
@@ -53,7 +56,8 @@ struct PTConst {
     VolView cloud, sv;
     const float* qtable;               // per 8^3 brick: upper bound of ext/maxExtinction over voxels [8b, 8b+8]^3
     const float* qtable_wide;          // same over voxels [8b-1, 8b+9]^3: valid for a brick index that is off by < 1 texel;
-                                       // stored with one brick of clamp-to-edge padding on every side ((nbx+2)(nby+2)(nbz+2))
+                                       // stored TIMES 2^32 with one brick of clamp-to-edge padding on every side
+                                       // ((nbx+2)(nby+2)(nbz+2) entries) and one +inf entry behind them
     const uint32_t* hitlist;           // pixels whose camera ray enters the box (pt_classify_kernel), x | y << 16, *nhit entries
     const uint32_t* nhit;
     const float* start;                // per hit pixel, SoA with stride npix: entry point xyz, direction xyz, exit distance

@@ -189,13 +189,15 @@ class HeadlessRenderer:
 
 
 def make_renderer(ctx: Context, w: Workload, cloud_layout="linear", sv_layout=None, n_cloud: Optional[int] = None,
-                  width: Optional[int] = None, height: Optional[int] = None, n_sv: Optional[int] = None) -> HeadlessRenderer:
+                  width: Optional[int] = None, height: Optional[int] = None, n_sv: Optional[int] = None,
+                  math_mode: int = capi.PT_MATH_STRICT) -> HeadlessRenderer:
     """Renderer configured for a BASELINE workload (optionally shrunk for tests); the cloud is NOT set yet."""
     r = HeadlessRenderer(ctx, width or w.width, height or w.height, n_sv or w.n_sv, cloud_layout, sv_layout, w.fov)
     r.cloudProperties.densityScaling = w.density_scaling
     if w.phase_g is not None:
         r.parameters.SetPhaseG(w.phase_g)
     r.extensions.absorption = w.absorption
+    r.extensions.math_mode = math_mode
     r.lightDirection = w.light_dir
     r.pathTracingTechnique.QueueUpdateParameters(r.parameters, 0)
     r.pathTracingTechnique.UpdateDescriptorSets()

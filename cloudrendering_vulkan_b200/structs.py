@@ -106,11 +106,13 @@ class ShadowVolumeProperties(capi.ShadowVolumePropertiesPOD):
 
 
 class PathTracerExtensions(capi.PTExtensionsPOD):
-    """Not in the reference: absorption (1 - albedo); 0 keeps the reference's RNG stream untouched."""
+    """Not in the reference: absorption (1 - albedo); 0 keeps the reference's RNG stream untouched.
+    math_mode: capi.PT_MATH_STRICT (default) or capi.PT_MATH_DRIVER (crv_c_api.h: crv_pt_math_mode)."""
 
-    def __init__(self, absorption: float = 0.0):
+    def __init__(self, absorption: float = 0.0, math_mode: int = 0):
         super().__init__()
         self.absorption = absorption
+        self.math_mode = math_mode
 
 
 def msvc_rand_sequence(n: int, seed0: int = 0) -> np.ndarray:

@@ -345,7 +345,8 @@ struct PathTracerExtensions : crv_pt_extensions {
     PathTracerExtensions()
     {
         absorption = 0.0f;
-        reserved[0] = reserved[1] = reserved[2] = 0;
+        math_mode = CRV_PT_MATH_STRICT;
+        reserved[0] = reserved[1] = 0;
     }
 };
 

@@ -102,8 +102,26 @@ typedef struct crv_shadow_volume_properties {
  * stream is exactly the reference's. */
 typedef struct crv_pt_extensions {
     float    absorption;      /* 0 = reference semantics */
-    uint32_t reserved[3];
+    uint32_t math_mode;       /* crv_pt_math_mode; 0 = CRV_PT_MATH_STRICT */
+    uint32_t reserved[2];
 } crv_pt_extensions;
+
+/* How the tracker evaluates the one transcendental on its decision path, the free-flight update
+ * `t += -log(zeta) / sigma` (PathTracer.comp:338).  GLSL leaves the precision of log(), of `/` and
+ * the contraction of the add to the driver (no `precise` qualifier in the shader); the two modes
+ * are the two ends of that latitude.  Nothing else differs: RNG stream, draw order, sampler,
+ * phase function and accumulation are the same code.
+ *   STRICT : three separately rounded operations -- logf-accurate log (<= 1 ulp), IEEE division,
+ *            IEEE add -- the evaluation the CPU oracle performs with libm.
+ *   DRIVER : log as lg2 on the special-function unit (absolute error < 2^-22, inside Vulkan's
+ *            bound for Log), multiplication by the reciprocal, FMA-contracted add: the code a GPU
+ *            Vulkan driver emits for this line.  t differs from STRICT in its last bits; a few
+ *            paths per million take a different branch ("threshold-divergent", counted by the
+ *            parity tests and by bench.py), all others agree within the 1e-4 radiance tolerance. */
+typedef enum crv_pt_math_mode {
+    CRV_PT_MATH_STRICT = 0,
+    CRV_PT_MATH_DRIVER = 1
+} crv_pt_math_mode;
 
 /* ------------------------------------------------------------------------------------------ */
 
