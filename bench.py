@@ -252,6 +252,7 @@ def run_ours(args, wl):
     if args.track_threshold or args.ctas_per_sm or args.steps_per_decision:
         r.pathTracingTechnique.SetTuning(ctas_per_sm=args.ctas_per_sm, track_threshold=args.track_threshold,
                                          steps_per_decision=args.steps_per_decision)
+    r.pathTracingTechnique.SetScheduler(args.scheduler)
     r.set_cloud_synthetic(wl.n_cloud, wl.fbm_seed, stream)
     ctx.synchronize(stream)
     # shadow-volume rebuild: 3 warm rebuilds, then the median of 7 (CUDA events on the launching stream, around the kernel)
@@ -457,6 +458,7 @@ def main():
                     help="free-flight update t += -log(zeta)/sigma: 'strict' = logf-accurate log, IEEE divide, IEEE add; "
                          "'driver' = lg2 on the SFU * (-ln2/sigma) in one FMA, the latitude GLSL gives a Vulkan driver "
                          "(crv_c_api.h: crv_pt_math_mode)")
+    ap.add_argument("--scheduler", default="pool", choices=["pool", "lanes"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

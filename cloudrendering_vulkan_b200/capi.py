@@ -141,6 +141,7 @@ SIGNATURES = {
     "crv_pt_selftest_log": (C.c_int, [_vp, _P(C.c_uint64), _vp]),
     "crv_pt_rng_tap": (C.c_int, [_vp, _i32, _u32, _u32, _u32, _vp, _vp]),
     "crv_pt_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "crv_pt_set_scheduler": (C.c_int, [_vp, C.c_int]),
     "crv_push_constants_init": (None, [_P(PushConstantsPOD)]),
     "crv_camera_init": (None, [_P(CameraPropertiesPOD)]),
     "crv_camera_set_resolution": (None, [_P(CameraPropertiesPOD), C.c_int, C.c_int]),

@@ -101,6 +101,9 @@ struct crv_pt {
     float* qtable_wide = nullptr;
     float* qtable = nullptr;
     size_t qtable_elems = 0;
+    uint8_t* qcoarse = nullptr;       // pool scheduler: byte thresholds per coarse cell (shared-memory resident)
+    uint32_t qcoarse_bytes = 0;       // padded to 16
+    int qcoarse_shift = 0;            // coarse cell = (8 << shift)^3 voxels
     const crv_volume* q_for_vol = nullptr;
     float q_for_max_ext = -1.0f;
     uint64_t q_for_generation = 0;
@@ -121,6 +124,7 @@ struct crv_pt {
     int ctas_per_sm = 0;
     int track_threshold = 20;
     int steps_per_decision = 6;
+    int scheduler = CRV_PT_SCHED_POOL;
     uint64_t sample_budget = 2ull << 30;
 };
 
@@ -669,6 +673,7 @@ int crv_pt_destroy(crv_pt* pt)
     cudaSetDevice(pt->ctx->device);
     if (pt->qtable) cudaFree(pt->qtable);
     if (pt->qtable_wide) cudaFree(pt->qtable_wide);
+    if (pt->qcoarse) cudaFree(pt->qcoarse);
     if (pt->hitlist) cudaFree(pt->hitlist);
     if (pt->start) cudaFree(pt->start);
     if (pt->nhit) cudaFree(pt->nhit);
@@ -782,6 +787,14 @@ int crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t
     return CRV_OK;
 }
 
+int crv_pt_set_scheduler(crv_pt* pt, int scheduler)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_set_scheduler: null technique");
+    CRV_REQUIRE(scheduler == CRV_PT_SCHED_POOL || scheduler == CRV_PT_SCHED_LANES, "crv_pt_set_scheduler: unknown scheduler");
+    pt->scheduler = scheduler;
+    return CRV_OK;
+}
+
 // Build the kernel-parameter block from the committed bindings.  fp32, shader evaluation order.
 static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
 {
@@ -857,12 +870,28 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
         if (pt->qtable_elems != nbricks) {
             if (pt->qtable) CRV_CUDA(cudaFree(pt->qtable));
             if (pt->qtable_wide) CRV_CUDA(cudaFree(pt->qtable_wide));
+            if (pt->qcoarse) CRV_CUDA(cudaFree(pt->qcoarse));
+            pt->qcoarse = nullptr;
             pt->qtable = pt->qtable_wide = nullptr;
             pt->qtable_elems = 0;
             CRV_CUDA(cudaMalloc(&pt->qtable, nbricks * sizeof(float)));
             CRV_CUDA(cudaMalloc(&pt->qtable_wide, ((size_t)(cv->nbx + 2) * (cv->nby + 2) * (cv->nbz + 2) + 1) * sizeof(float)));   // + the +inf entry
+            // coarse table: the smallest cell size whose padded table fits the pool scheduler's shared-memory budget
+            int shift = 0;
+            size_t cells = 0;
+            for (;; ++shift) {
+                const size_t ncx = ((cv->nbx - 1) >> shift) + 1, ncy = ((cv->nby - 1) >> shift) + 1, ncz = ((cv->nbz - 1) >> shift) + 1;
+                cells = (ncx + 2) * (ncy + 2) * (ncz + 2);
+                if (cells + 1 <= (size_t)crv_pt_pool_smem_budget()) break;
+            }
+            pt->qcoarse_shift = shift;
+            pt->qcoarse_bytes = (uint32_t)((cells + 1 + 15) / 16 * 16);
+            CRV_CUDA(cudaMalloc(&pt->qcoarse, pt->qcoarse_bytes));
             pt->qtable_elems = nbricks;
         }
+        CRV_CUDA(cudaMemsetAsync(pt->qcoarse, 128, pt->qcoarse_bytes, s));
+        CRV_TRY(crv_launch_qcoarse(pt->ctx, cv->brick_absmax_wide, pt->qcoarse, (int)cv->nbx, (int)cv->nby, (int)cv->nbz, pt->qcoarse_shift, c.max_ext, s));
+        pt->launches += 1;
         CRV_TRY(crv_launch_qtable(pt->ctx, cv->brick_absmax, pt->qtable, (long long)nbricks, c.max_ext, s));
         CRV_TRY(crv_launch_qtable_padded(pt->ctx, cv->brick_absmax_wide, pt->qtable_wide, (int)cv->nbx, (int)cv->nby, (int)cv->nbz, c.max_ext, s));
         pt->launches += 2;
@@ -872,6 +901,8 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
     }
     c.qtable = pt->qtable;
     c.qtable_wide = pt->qtable_wide;
+    c.qcoarse = pt->qcoarse;
+    c.qcoarse_bytes = pt->qcoarse_bytes;
 
     // exact FMA division (exact_div.cuh): reciprocals by IEEE division on the host; the divisors must be ordinary numbers
     {
@@ -895,6 +926,9 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             const double sc = n / (double)c.cext[i], of = -(double)c.cb0[i] * sc - 0.5;
             c.asc8[i] = (float)(sc / 8.0);
             c.aof8[i] = (float)(of / 8.0 + 1.0);
+            const double cell = 8.0 * (double)(1 << pt->qcoarse_shift);
+            c.ascc[i] = (float)(sc / cell);
+            c.aofc[i] = (float)(of / cell + 1.0);
             const double span = std::fabs((double)c.cb0[i]) + std::fabs((double)c.cb1[i]);
             if (!(span * std::fabs(sc) * 4.0 * 1.1920929e-07 < 0.25) || !(n < 2097152.0)) c.use_wide = 0;
         }
@@ -902,12 +936,23 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
         c.pnbxy = c.pnbx * ((uint32_t)c.cloud.nby + 2u);
         c.pbias = 0x4B000000u * (1u + c.pnbx + c.pnbxy);          // mod 2^32, like the device-side sum it cancels
         c.pmax = c.pnbxy * ((uint32_t)c.cloud.nbz + 2u) - 1u;
+        {
+            const int sh = pt->qcoarse_shift;
+            c.cnx = (((uint32_t)c.cloud.nbx - 1u) >> sh) + 3u;
+            const uint32_t cny = (((uint32_t)c.cloud.nby - 1u) >> sh) + 3u, cnz = (((uint32_t)c.cloud.nbz - 1u) >> sh) + 3u;
+            c.cnxy = c.cnx * cny;
+            c.cbias = 0x4B000000u * (1u + c.cnx + c.cnxy);
+            c.cmax = c.cnxy * cnz - 1u;
+        }
         if (!c.use_wide) {
             // every approximate coordinate collapses to 0 and the bias moves the index to the +inf entry behind the
             // table: the pre-test never rejects and every tentative collision goes through the exact sampler
             for (int i = 0; i < 3; ++i) c.asc8[i] = c.aof8[i] = 0.0f;
             c.pmax += 1u;
             c.pbias -= c.pmax;
+            for (int i = 0; i < 3; ++i) c.ascc[i] = c.aofc[i] = 0.0f;
+            c.cmax += 1u;
+            c.cbias -= c.cmax;
         }
     }
 
@@ -917,6 +962,7 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
     c.stats = pt->stats;
     c.track_threshold = pt->track_threshold;
     c.steps_per_decision = pt->steps_per_decision;
+    c.scheduler = pt->scheduler;
     return CRV_OK;
 }
 
@@ -958,6 +1004,9 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         }
         c.dbg_steps = pt->dbg_steps;
         c.dbg_collisions = pt->dbg_coll;
+        // the pool scheduler accumulates per-path counts round by round
+        CRV_CUDA(cudaMemsetAsync(pt->dbg_steps, 0, sizeof(uint32_t) * c.npix, s));
+        CRV_CUDA(cudaMemsetAsync(pt->dbg_coll, 0, sizeof(uint32_t) * c.npix, s));
     }
 
     // classification: miss pixels get all n background samples folded now, hit pixels go to the hit list

@@ -3,6 +3,7 @@
 #include "crv_internal.h"
 
 // stats slots (u64 each)
+enum { CRV_PT_SCHED_POOL = 0, CRV_PT_SCHED_LANES = 1 };
 enum { PT_STAT_PATHS = 0, PT_STAT_STEPS = 1, PT_STAT_COLLISIONS = 2, PT_STAT_FETCHES = 3, PT_STAT_COUNT = 4 };
 
 constexpr int PT_MAX_FRAMES_PER_LAUNCH = 256;
@@ -58,6 +59,13 @@ struct PTConst {
     const float* qtable_wide;          // same over voxels [8b-1, 8b+9]^3: valid for a brick index that is off by < 1 texel;
                                        // stored TIMES 2^32 with one brick of clamp-to-edge padding on every side
                                        // ((nbx+2)(nby+2)(nbz+2) entries) and one +inf entry behind them
+    // Pool scheduler: the same bound at a coarser granularity, small enough to live in shared memory.  One byte per cell
+    // of (8 << coarse_shift)^3 voxels (+ the one-texel dilation), padded by one cell on every side like qtable_wide:
+    // thr = ceil(128 * q) clamped to 128, so that (u >> 25) >= thr implies float(u) * 2^-32 >= q for the raw draw u.
+    const uint8_t* qcoarse;
+    uint32_t qcoarse_bytes;            // padded cell count + 1 (the last byte, 128 = never reject, is the disabled-test target)
+    float ascc[3], aofc[3];            // approximate padded CELL coordinate, like asc8/aof8
+    uint32_t cnx, cnxy, cbias, cmax;   // like pnbx/pnbxy/pbias/pmax for the coarse table
     const uint32_t* hitlist;           // pixels whose camera ray enters the box (pt_classify_kernel), x | y << 16, *nhit entries
     const uint32_t* nhit;
     const float* start;                // per hit pixel, SoA with stride npix: entry point xyz, direction xyz, exit distance
@@ -74,8 +82,9 @@ struct PTConst {
     unsigned long long* stats;         // PT_STAT_COUNT u64 (may be null)
     uint32_t* dbg_steps;               // per-pixel counters (single-frame renders, both null or both set)
     uint32_t* dbg_collisions;
-    int track_threshold;               // service collisions/regeneration once fewer lanes than this are tracking
-    int steps_per_decision;            // tracking steps between two scheduling decisions
+    int scheduler;                     // CRV_PT_SCHED_POOL (default) or CRV_PT_SCHED_LANES
+    int track_threshold;               // LANES: service collisions/regeneration once fewer lanes than this are tracking
+    int steps_per_decision;            // tracking steps between two scheduling decisions (POOL: steps per tracking round)
 };
 
 struct FoldConst {
@@ -91,6 +100,8 @@ int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layou
 int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, uint32_t* hitlist, float* start, uint32_t* nhit, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
+int crv_launch_qcoarse(crv_ctx* ctx, const float* absmax_wide, uint8_t* qc, int nbx, int nby, int nbz, int shift, float max_ext, cudaStream_t s);
+int crv_pt_pool_smem_budget();     // bytes of shared memory the pool scheduler leaves for the coarse table
 int crv_launch_qtable_padded(crv_ctx* ctx, const float* absmax_wide, float* qpad, int nbx, int nby, int nbz, float max_ext, cudaStream_t s);
 int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);
 int crv_launch_log_selftest(crv_ctx* ctx, unsigned long long* d_mismatches, cudaStream_t s);

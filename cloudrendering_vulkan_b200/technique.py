@@ -358,6 +358,12 @@ class RenderTechniquePT(RenderTechnique):
         check(lib.crv_pt_set_tuning(self.handle, int(ctas_per_sm), int(track_threshold), C.c_uint64(sample_buffer_bytes),
                                     int(steps_per_decision)))
 
+    SCHEDULERS = {"pool": 0, "lanes": 1}
+
+    def SetScheduler(self, scheduler="pool"):
+        """which persistent-thread scheduler runs the tracker; both produce the same bits"""
+        check(lib.crv_pt_set_scheduler(self.handle, self.SCHEDULERS[scheduler] if isinstance(scheduler, str) else int(scheduler)))
+
     def close(self):
         if self.handle:
             lib.crv_pt_destroy(self.handle)

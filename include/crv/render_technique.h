@@ -290,6 +290,8 @@ public:
         return s;
     }
     void ResetStats(CommandStream stream = nullptr) { Check(crv_pt_reset_stats(m_pt, stream)); }
+    // 0 = pool scheduler (default), 1 = lane-owned scheduler; identical results
+    void SetScheduler(int scheduler) { Check(crv_pt_set_scheduler(m_pt, scheduler)); }
     float LastRenderMs(unsigned* launches = nullptr)
     {
         float ms = 0.0f;

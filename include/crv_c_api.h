@@ -272,6 +272,10 @@ int  crv_pt_selftest_log(crv_ctx* ctx, uint64_t* mismatches, void* stream);
 /* tuning knobs (0 = library default): CTAs per SM, min tracking lanes before servicing, max
  * bytes of the per-round sample buffer, tracking steps between two scheduling decisions */
 int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes, int steps_per_decision);
+/* which persistent-thread scheduler runs the tracker (identical results, bit for bit):
+ *   0 = pool  (default) every warp owns 128 paths in shared memory and runs one kind of work at a time on 32 of them
+ *   1 = lanes every lane owns one path plus one in reserve (kept for A/B measurements) */
+int  crv_pt_set_scheduler(crv_pt* pt, int scheduler);
 
 /* ---- host-side helpers with the reference's setter semantics (UniformBuffers.h) ------------ */
 void crv_push_constants_init(crv_push_constants* p);                                   /* :6-13   */
