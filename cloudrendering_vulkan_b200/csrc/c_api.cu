@@ -930,7 +930,7 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             c.ascc[i] = (float)(sc / cell);
             c.aofc[i] = (float)(of / cell + 1.0);
             const double span = std::fabs((double)c.cb0[i]) + std::fabs((double)c.cb1[i]);
-            if (!(span * std::fabs(sc) * 4.0 * 1.1920929e-07 < 0.25) || !(n < 2097152.0)) c.use_wide = 0;
+            if (!(span * std::fabs(sc) * 8.0 * 1.1920929e-07 < 0.25) || !(n < 2097152.0)) c.use_wide = 0;
         }
         c.pnbx = (uint32_t)c.cloud.nbx + 2u;
         c.pnbxy = c.pnbx * ((uint32_t)c.cloud.nby + 2u);
