@@ -313,6 +313,25 @@ def run_ours(args, wl):
     value = paths_per_step / (ms_per_step * 1e-3) / 1e6
     assert abs(tot_paths - paths_per_step * args.steps) < 0.5, "kernel path counter disagrees with the workload size"
 
+    # ---- the same steps in the other math mode (N = 1): both ends of the latitude GLSL leaves the driver are on record ----
+    math_modes = {args.math: value}
+    if world == 1:
+        other = "strict" if args.math == "driver" else "driver"
+        r.extensions.math_mode = crv.PT_MATH_STRICT if other == "strict" else crv.PT_MATH_DRIVER
+        pt.SetExtensions(r.extensions)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            step()
+        a1.record()
+        torch.cuda.synchronize()
+        math_modes[other] = paths_per_step / (a0.elapsed_time(a1) / args.steps * 1e-3) / 1e6
+        r.extensions.math_mode = math_mode
+        pt.SetExtensions(r.extensions)
+
     # ---- roofline of the dominant kernel (the tracker), this rank, last step ----
     peak, peak_src = _peak()
     alg_bytes_rank = (32.0 * (st.tracking_steps + st.collisions) + 32.0 * st.paths) / args.steps
@@ -327,7 +346,11 @@ def run_ours(args, wl):
                 "algorithmic_bytes_per_launch": alg_bytes_rank / max(1, k_n), "launches_per_step": k_n,
                 "kernel_ms_per_step": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "steps_per_path": tot_steps / tot_paths, "collisions_per_path": tot_coll / tot_paths,
-                "fetch_fraction": tot_fetch / max(1.0, tot_steps)}
+                "fetch_fraction": tot_fetch / max(1.0, tot_steps),
+                "note": "algorithmic bytes = the reference's texel reads (32 B per tracking step and per collision + 32 B of "
+                        "accumulator per path, SURVEY 8d); the proof-based skip tables avoid ~98 % of the step reads, so "
+                        "`achieved` can exceed what DRAM could deliver -- `traffic` is the measured DRAM bytes per launch and "
+                        "the kernel's real limiter is instruction issue (ncu: profiles/*_pt_ncu.txt)"}
     sv_bytes = 4.0 * wl.n_sv ** 3 + 4.0 * wl.n_cloud ** 3
 
     line = None
@@ -416,6 +439,10 @@ def run_ours(args, wl):
                    "rebuild_ms": sv_ms, "rebuild_ms_min": float(min(sv_times)), "n_sv": wl.n_sv, "n_cloud": wl.n_cloud,
                    "algorithmic_bytes": sv_bytes, "achieved_gbs": sv_bytes / sv_ms / 1e6,
                    "frac_of_peak": sv_bytes / sv_ms / 1e6 / peak, "peak_source": peak_src},
+            "math_modes": {"unit": "Mpath-samples/s", **math_modes,
+                           "note": "free-flight update t += -log(zeta)/sigma: 'strict' = logf-accurate log, IEEE divide, IEEE add "
+                                   "(the CPU oracle's evaluation); 'driver' = lg2 on the SFU and one FMA, inside the precision "
+                                   "Vulkan grants a driver for the same GLSL; `value` and `parity` are the --math mode's"},
             "cpu_baseline": cpu_baseline, "parity": parity,
         }
         _emit(line)

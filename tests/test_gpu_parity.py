@@ -256,6 +256,88 @@ def test_layouts_and_scheduling_are_bit_identical(crv, orc, ctx):
         assert np.array_equal(_bits(imgs[0]), _bits(im))
 
 
+def test_schedulers_are_bit_identical(crv, orc, ctx):
+    """the pool scheduler (paths in shared memory, one kind of work at a time) and the lane-owned scheduler run the same
+    per-path arithmetic: identical image bits, identical counters, for every round length, in both math modes"""
+    cloud = orc.fbm_generate(40, 1234)
+    for math in [crv.PT_MATH_STRICT, crv.PT_MATH_DRIVER]:
+        imgs, stats = [], []
+        for sched, rounds in [("lanes", 0), ("pool", 0), ("pool", 1), ("pool", 3), ("pool", 16)]:
+            r, _ = make_scene(crv, orc, ctx, layout="brick", g=0.85, absorption=0.05, cloud=cloud, density_scaling=120.0)
+            r.extensions.math_mode = math
+            r.apply_parameters()
+            pt = r.pathTracingTechnique
+            pt.SetScheduler(sched)
+            pt.SetTuning(steps_per_decision=rounds)
+            pt.ResetStats()
+            r.render(5)
+            imgs.append(r.resultImage.download().copy())
+            st = pt.GetStats()
+            stats.append((st.paths, st.tracking_steps, st.collisions))
+            r.close()
+        for im, st in zip(imgs[1:], stats[1:]):
+            assert np.array_equal(_bits(imgs[0]), _bits(im)), f"scheduler changed the image (math mode {math})"
+            assert st == stats[0], f"scheduler changed the counters: {st} vs {stats[0]}"
+
+
+@pytest.mark.parametrize("g,absorption,ds", [(None, 0.0, 50.0), (0.85, 0.1, 50.0), (0.85, 0.01, 200.0)])
+def test_driver_math_mode_parity(crv, orc, ctx, g, absorption, ds):
+    """CRV_PT_MATH_DRIVER (lg2 on the SFU, reciprocal multiply, contracted add for t += -log(zeta)/sigma): the same bars as
+    the strict mode -- <= 1e-4 relative on paths whose counters match the oracle, divergent paths counted and bounded"""
+    r, cloud = make_scene(crv, orc, ctx, layout="brick", g=g, absorption=absorption, density_scaling=ds)
+    r.extensions.math_mode = crv.PT_MATH_DRIVER
+    r.apply_parameters()
+    tot_d = tot_n = 0
+    for seed in [38, 7719, 21238, 2437]:
+        d, n = _frame_parity(crv, orc, r, cloud, seed, absorption, min_match=0.97 if ds > 100 else 0.99)
+        tot_d += d
+        tot_n += n
+    print(f"driver math: {tot_d}/{tot_n} threshold-divergent paths over 4 frames")
+    r.close()
+
+
+def test_driver_math_mode_converged(crv, orc, ctx):
+    """32 frames in driver mode against the strict mode on the same seeds: the means agree far inside the Monte-Carlo noise"""
+    spp = 32
+    out = {}
+    for math in [crv.PT_MATH_STRICT, crv.PT_MATH_DRIVER]:
+        r, cloud = make_scene(crv, orc, ctx, n=32, w=64, h=48, nsv=40, layout="brick", g=0.85, absorption=0.1)
+        r.extensions.math_mode = math
+        r.apply_parameters()
+        r.render(spp)
+        out[math] = r.resultImage.download().copy()
+        r.close()
+    a, b = out[crv.PT_MATH_STRICT], out[crv.PT_MATH_DRIVER]
+    rel = np.abs(a - b) / np.maximum(np.abs(a), 1e-3)
+    print(f"driver vs strict, {spp} spp: {(rel > 1e-4).mean():.2e} of the pixels differ by more than 1e-4, max {rel.max():.2e}")
+    assert (rel <= 1e-4).mean() > 0.97
+
+
+def test_far_away_box_disables_the_approximate_pretest(crv, orc, ctx):
+    """a cloud box ten million units from the origin: the FMA coordinate of the brick pre-test can no longer be bounded to a
+    quarter texel, the host switches it off (every tentative collision goes through the exact sampler) and the image must
+    still be the oracle's -- in both schedulers, with identical bits"""
+    n, w, h, nsv = 24, 48, 40, 32
+    cloud = orc.fbm_generate(n, 1234)
+    imgs = []
+    for sched in ["pool", "lanes"]:
+        wl = crv.Workload("t", n, w, h, 1, nsv, 50.0, 0.0, 0.85, (1.0, -1.0, 0.0))
+        r = crv.make_renderer(ctx, wl, cloud_layout="brick")
+        r.set_cloud_host(cloud, (n, n, n), (1.0 / n,) * 3)
+        off = 1.0e7
+        cp = r.cloudProperties
+        cp.bounds[0][0] += off
+        cp.bounds[1][0] += off
+        r.cameraProperties.position[0] += off
+        r.apply_parameters()
+        r.UpdateShadowVolume()                      # SetOrigin from the moved bounds, rebuild, rebind
+        r.pathTracingTechnique.SetScheduler(sched)
+        _frame_parity(crv, orc, r, cloud, 38, 0.0, min_match=0.98)
+        imgs.append(r.resultImage.download().copy())
+        r.close()
+    assert np.array_equal(_bits(imgs[0]), _bits(imgs[1]))
+
+
 def test_sum_mode_matches_mean(crv, orc, ctx):
     r, _ = make_scene(crv, orc, ctx, g=0.85)
     seeds = crv.msvc_rand_sequence(8)
