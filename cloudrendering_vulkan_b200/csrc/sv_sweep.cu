@@ -402,9 +402,174 @@ __global__ void __launch_bounds__(32 * SV_ROWS) sv_scan_kernel(const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Fused build (the default).  The two-pass form pays for its parallel gathers with a write + read of every
+// in-AABB addend and leaves the scan with one thread per column -- 0.86 waves at N = 512, DRAM at 53 %
+// (profiles/r1n_sv_ncu.txt).  Here one CTA owns an 8x8 column bundle from z = 0 to N and walks it in chunks of
+// 8 slices, 512 threads = one voxel each:
+//   * chunks before any column of the bundle enters the cloud AABB are all ones: one coalesced 2 KiB store;
+//   * inside, every thread gathers its voxel's addend (same code as sv_gather_kernel) into shared memory, 64
+//     threads add the 8 addends of their column IN THE SHADER'S SERIAL ORDER and leave the 8 running sums
+//     there, then every thread does exp + store for its voxel with its own sum;
+//   * after the last column has left the AABB the sums are final: exp + store only.
+// Nothing is written twice and nothing is read back, the output is stored in whole 8x8x8 blocks (exactly one
+// brick of the BRICK layout, 32-byte rows otherwise), and the parallelism is n^2/64 CTAs of 512 threads at any N.
+// accumulatedDistance comes from the dist_z table: the shader's repeated fp32 addition (:91), done once per
+// (N, voxelSize) by sv_dist_kernel.  Per column: the same operations in the same order => the same bits.
+// ------------------------------------------------------------------------------------------------------
+// Store cursor of one thread of the fused build: voxel (x, y, z0 + lz) of successive 8-slice chunks.
+template <int OL>
+struct ChunkCursor {
+    float* p;
+    unsigned step;
+    __device__ __forceinline__ ChunkCursor(const VolView& v, int x, int y, int lz)
+        : p(const_cast<float*>(v.data) + (VolAcc<OL>::off_x(v, x) + VolAcc<OL>::off_y(v, y) + VolAcc<OL>::off_z(v, lz))),
+          step(VolAcc<OL>::off_z(v, 8)) {}
+    __device__ __forceinline__ void store(const VolView&, int, float val) const { __stcs(p, val); }
+    __device__ __forceinline__ void advance() { p += step; }
+};
+template <>
+struct ChunkCursor<CRV_LAYOUT_TEX3D> {
+    int x, y, lz;
+    __device__ __forceinline__ ChunkCursor(const VolView&, int x_, int y_, int lz_) : x(x_), y(y_), lz(lz_) {}
+    __device__ __forceinline__ void store(const VolView& v, int z0, float val) const { VolAcc<CRV_LAYOUT_TEX3D>::store(v, x, y, z0 + lz, val); }
+    __device__ __forceinline__ void advance() {}
+};
+
+__global__ void sv_dist_kernel(float* __restrict__ dist_z, int n, float voxel_size)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float dist = 0.0f;
+    for (int z = 0; z < n; ++z) {
+        dist = dist + voxel_size;
+        dist_z[z] = dist;
+    }
+}
+
+template <int CL, int OL>
+__global__ void __launch_bounds__(512) sv_fused_kernel(const __grid_constant__ SVConst c)
+{
+    __shared__ int s_lo, s_hi;
+    __shared__ int s_search[6][64];
+    __shared__ int s_zin[64], s_zend[64];
+    __shared__ float s_add[8][64];      // the chunk's addends, then the running sums after each slice
+    __shared__ float s_acc[64];         // running sum of every column after the previous chunk
+    const int N = c.n;
+    const int t = threadIdx.x;
+    const int bx = centre_out(blockIdx.x, gridDim.x), by = centre_out(blockIdx.y, gridDim.y);
+
+    // ---- [z_in, z_end) of the bundle's 64 columns: 6 bisections per column spread over 384 threads ----
+    if (t == 0) { s_lo = N; s_hi = 0; }
+    if (t < 384) {
+        const int col = t & 63, search = t >> 6;
+        const int cx = bx * 8 + (col & 7), cy = by * 8 + (col >> 3);
+        const int ax = search >> 1;
+        const float a_ax = (float)cx * c.right[ax] + (float)cy * c.up[ax];
+        s_search[search][col] = range_bisect(c, a_ax, ax, (search & 1) != 0);
+    }
+    __syncthreads();
+    if (t < 64) {
+        const int cx = bx * 8 + (t & 7), cy = by * 8 + (t >> 3);
+        int z_in = max(max(s_search[0][t], s_search[2][t]), s_search[4][t]);
+        int z_end = min(min(s_search[1][t], s_search[3][t]), s_search[5][t]);
+        if (z_end < z_in) z_end = z_in;
+        if (cx >= N || cy >= N) z_in = z_end = 0;
+        s_zin[t] = z_in;
+        s_zend[t] = z_end;
+        s_acc[t] = 0.0f;
+        if (z_in < z_end) {
+            atomicMin(&s_lo, z_in);
+            atomicMax(&s_hi, z_end);
+        }
+    }
+    __syncthreads();
+    const int hi = s_hi;
+    const int lo = hi > 0 ? (s_lo & ~7) : N;      // bundle never enters the cloud: every chunk is "before"
+
+    const int col = t & 63, lz = t >> 6;
+    const int x = bx * 8 + (t & 7), y = by * 8 + ((t >> 3) & 7);
+    const bool inb = x < N && y < N;
+    const int z_in = s_zin[col], z_end = s_zend[col];
+    const float fx = (float)x, fy = (float)y;
+    const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
+    // Approximate brick coordinate of this thread's voxel as a function of z (one FMA per axis).  It tracks the sampler's
+    // lower texel to within a quarter texel (bound checked on the host), and the wide table covers every texel a
+    // footprint within one texel of it can touch: a zero there proves the trilinear value is +-0 without the exact
+    // position / division / footprint chain.  Most of the cloud's bounding box is empty.
+    const bool pre = c.brick_absmax_wide != nullptr;
+    const float pa[3] = {__fmaf_rn(fy, c.pre_u[0], __fmaf_rn(fx, c.pre_r[0], c.pre_c[0])),
+                         __fmaf_rn(fy, c.pre_u[1], __fmaf_rn(fx, c.pre_r[1], c.pre_c[1])),
+                         __fmaf_rn(fy, c.pre_u[2], __fmaf_rn(fx, c.pre_r[2], c.pre_c[2]))};
+
+    // One pointer per thread, advanced by a whole chunk per iteration: in both global layouts the offset of slice
+    // z0 + lz (z0 a multiple of 8) is off_z(z0) + off_z(lz), and off_z(z0) is z0/8 steps of off_z(8).
+    ChunkCursor<OL> cur(c.out, x, y, lz);
+    int z0 = 0;
+    // ---- before any column of the bundle enters the cloud AABB: exp(-0) = 1 ----
+    for (; z0 + 8 <= lo; z0 += 8) {
+        if (inb) cur.store(c.out, z0, 1.0f);
+        cur.advance();
+    }
+    // ---- while some column is inside its interval: gather, serial sums, exp ----
+    for (; z0 < hi; z0 += 8) {
+        const int z = z0 + lz;
+        float add = 0.0f;                         // + 0 outside the interval leaves the sum unchanged (it is never -0)
+        if (z >= z_in && z < z_end) {
+            bool empty = false;
+            if (pre) {
+                const float fz = (float)z;
+                // floor by a round-down add of 2^23; inside the AABB the coordinate is >= -1/16 - 1/32, so only -1 needs a clamp
+                const int bi = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[0], pa[0]), 8388608.0f)) - 0x4B000000, 0);
+                const int bj = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[1], pa[1]), 8388608.0f)) - 0x4B000000, 0);
+                const int bk = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[2], pa[2]), 8388608.0f)) - 0x4B000000, 0);
+                const unsigned b = ((unsigned)min(bk, c.cloud.nbz - 1) * c.cloud.nby + (unsigned)min(bj, c.cloud.nby - 1)) * c.cloud.nbx +
+                                   (unsigned)min(bi, c.cloud.nbx - 1);
+                empty = __ldg(c.brick_absmax_wide + b) == 0.0f;
+            }
+            if (!empty) add = div_rn_by(column_sample<CL, true>(c, a, z) * c.density_scaling, c.base_scaling, c.rbase);
+        }
+        s_add[lz][col] = add;
+        __syncthreads();
+        if (t < 64) {
+            float s = s_acc[t];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                s = s + s_add[u][t];              // accumulatedValue after slice z0 + u, the shader's order (:89)
+                s_add[u][t] = s;
+            }
+            s_acc[t] = s;
+        }
+        __syncthreads();
+        const float acc = s_add[lz][col];
+        // ((-dist)*0)/(z+1) = +-0 and expf(+-0) = 1 exactly, the value the shader stores while a column has met no
+        // density: a warp (4x8 columns of one slice) none of whose columns has any skips the divide + exp altogether
+        float tr = 1.0f;
+        if (__any_sync(0xffffffffu, acc != 0.0f) && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
+        if (inb && z < N) cur.store(c.out, z0, tr);
+        cur.advance();
+    }
+    // ---- every column has left the AABB: the sums are final ----
+    {
+        const float acc = s_acc[col];
+        const bool any = __any_sync(0xffffffffu, acc != 0.0f);
+        for (; z0 < N; z0 += 8) {
+            const int z = z0 + lz;
+            float tr = 1.0f;
+            if (any && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
+            if (inb && z < N) cur.store(c.out, z0, tr);
+            cur.advance();
+        }
+    }
+}
+
 template <int CL, int OL>
 void launch_sv(const SVConst& c, int mode, int* launches, cudaStream_t s)
 {
+    if (mode == SV_MODE_FUSED) {
+        sv_fused_kernel<CL, OL><<<dim3((c.n + 7) / 8, (c.n + 7) / 8, 1), 512, 0, s>>>(c);
+        *launches = 1;
+        return;
+    }
     const dim3 block(32, SV_ROWS, 1);
     const dim3 grid((c.n + 31) / 32, (c.n + SV_ROWS - 1) / SV_ROWS, 1);
     if (mode == SV_MODE_TWO_PASS) {
@@ -449,6 +614,14 @@ int crv_sv_init_tables(crv_ctx* ctx)
     for (int z = 0; z < SV_MAX_FAST_N; ++z) tab[z] = 1.0f / (float)(z + 1);      // host IEEE division
     CRV_CUDA(cudaMemcpyToSymbol(c_rcp_z, tab, sizeof(tab)));
     ctx->sv_tables_ready = true;
+    return CRV_OK;
+}
+
+int crv_launch_sv_dist(crv_ctx* ctx, float* dist_z, int n, float voxel_size, cudaStream_t s)
+{
+    sv_dist_kernel<<<1, 32, 0, s>>>(dist_z, n, voxel_size);
+    ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
     return CRV_OK;
 }
 

@@ -20,6 +20,10 @@ struct SVConst {
     float* dist_z;              // dist_z[z] = accumulatedDistance after slice z (n entries, device; written by pass 0)
     int search_iters;           // ceil(log2(n + 1)): trip count of the per-column z-interval bisection
     ushort2* zrange;            // two-pass build: [z_in, z_end) of every column, n*n entries (device)
+    // fused build: approximate brick coordinate of voxel (x,y,z), affine in all three: v = pre_c + x*pre_r + y*pre_u + z*pre_l
+    // (~ ((s*size - 0.5) / 8) per axis), against the wide-dilated brick table; null when the error bound does not hold
+    const float* brick_absmax_wide;
+    float pre_c[3], pre_r[3], pre_u[3], pre_l[3];
 };
 
 constexpr int SV_MAX_FAST_N = 4096;   // entries of the constant reciprocal table (4096^3 floats = 275 GB: beyond HBM anyway)
@@ -31,5 +35,7 @@ int crv_sv_init_tables(crv_ctx* ctx);
 bool crv_sv_fast_path_ok(const SVConst& c);
 
 // crv_sv_mode of crv_c_api.h (AUTO is resolved by the caller)
-enum { SV_MODE_GENERIC = 1, SV_MODE_SINGLE_PASS = 2, SV_MODE_TWO_PASS = 3 };
+enum { SV_MODE_GENERIC = 1, SV_MODE_SINGLE_PASS = 2, SV_MODE_TWO_PASS = 3, SV_MODE_FUSED = 4 };
+// dist_z[z] = accumulatedDistance after slice z (the shader's repeated fp32 addition), for the fused build
+int crv_launch_sv_dist(crv_ctx* ctx, float* dist_z, int n, float voxel_size, cudaStream_t s);
 int crv_launch_sv_sweep(crv_ctx* ctx, const SVConst& c, int cloud_layout, int out_layout, int mode, cudaStream_t s);
