@@ -447,7 +447,7 @@ __global__ void sv_dist_kernel(float* __restrict__ dist_z, int n, float voxel_si
 }
 
 template <int CL, int OL>
-__global__ void __launch_bounds__(512) sv_fused_kernel(const __grid_constant__ SVConst c)
+__global__ void __launch_bounds__(512, 4) sv_fused_kernel(const __grid_constant__ SVConst c)
 {
     __shared__ int s_lo, s_hi;
     __shared__ int s_search[6][64];
