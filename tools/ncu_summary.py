@@ -160,9 +160,33 @@ def functions(path):
         print(f"{k:44s} {100 * a[0] / ti:8.2f}% {a[1] / max(a[0], 1):6.1f} {100 * a[2] / ts:12.2f}%")
 
 
+def traffic(path):
+    """ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv of one launch -> the JSON bench.py reads (profiles/traffic.json)"""
+    import json
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    ni, vi, ui, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Kernel Name")
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, kernel, dur = 0.0, "?", None
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        kernel = r[ki]
+        if r[ni].startswith("dram__bytes"):
+            tot += float(r[vi].replace(",", "")) * mult[r[ui]]
+        elif r[ni].startswith("gpu__time_duration"):
+            dur = r[vi] + " " + r[ui]
+    print(json.dumps({"pt_wavefront_kernel_bytes_per_launch": tot, "kernel": kernel, "launch_duration_under_ncu": dur,
+                      "source": path, "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one 128-frame "
+                                             "launch of the default bench.py step"}))
+
+
 if __name__ == "__main__":
     mode, path = sys.argv[1], sys.argv[2]
-    if mode == "launches":
+    if mode == "traffic":
+        traffic(path)
+    elif mode == "launches":
         launches(path)
     elif mode == "full":
         full(path)
