@@ -142,6 +142,12 @@ SIGNATURES = {
     "crv_pt_rng_tap": (C.c_int, [_vp, _i32, _u32, _u32, _u32, _vp, _vp]),
     "crv_pt_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "crv_pt_set_scheduler": (C.c_int, [_vp, C.c_int]),
+    "crv_image_blit_srgb8": (C.c_int, [_vp, _vp, _vp]),
+    "crv_image_save_png": (C.c_int, [_vp, C.c_char_p, _vp]),
+    "crv_image_save_pfm": (C.c_int, [_vp, C.c_char_p, _vp]),
+    "crv_image_save_checkpoint": (C.c_int, [_vp, C.c_uint32, C.c_int32, C.c_char_p, _vp]),
+    "crv_image_load_checkpoint": (C.c_int, [_vp, _P(C.c_uint32), _P(C.c_int32), C.c_char_p, _vp]),
+    "crv_write_png_rgba8": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _vp]),
     "crv_push_constants_init": (None, [_P(PushConstantsPOD)]),
     "crv_camera_init": (None, [_P(CameraPropertiesPOD)]),
     "crv_camera_set_resolution": (None, [_P(CameraPropertiesPOD), C.c_int, C.c_int]),

@@ -5,6 +5,8 @@
 // resources per image index, vkCmdDispatch becomes a kernel launch on the caller's stream.
 // All host arithmetic that feeds the kernels is fp32 in the shader's evaluation order (compiled with
 // -ffp-contract=off), because the kernels take these values as if the shader had computed them.
+#include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
@@ -436,6 +438,7 @@ int crv_image_destroy(crv_image* img)
     if (!img) return CRV_OK;
     cudaSetDevice(img->ctx->device);
     if (img->owned && img->rgba) cudaFree(img->rgba);
+    if (img->bgra8) cudaFree(img->bgra8);
     delete img;
     return CRV_OK;
 }
@@ -462,6 +465,95 @@ int crv_image_upload(crv_image* img, const float* host_rgba, void* stream)
     CRV_REQUIRE(img && host_rgba, "crv_image_upload: null argument");
     CRV_ENTER(img->ctx);
     CRV_CUDA(cudaMemcpyAsync(img->rgba, host_rgba, (size_t)img->width * img->height * 16, cudaMemcpyHostToDevice, as_stream(stream)));
+    return CRV_OK;
+}
+
+// ---- present step and image files ------------------------------------------------------------
+int crv_image_blit_srgb8(crv_image* img, uint8_t* host_bgra8, void* stream)
+{
+    CRV_REQUIRE(img && host_bgra8, "crv_image_blit_srgb8: null argument");
+    CRV_ENTER(img->ctx);
+    const size_t npix = (size_t)img->width * img->height;
+    if (!img->bgra8) CRV_CUDA(cudaMalloc(&img->bgra8, npix * 4));
+    cudaStream_t s = as_stream(stream);
+    CRV_TRY(crv_launch_blit_srgb8(img->ctx, img->rgba, img->bgra8, npix, s));
+    CRV_CUDA(cudaMemcpyAsync(host_bgra8, img->bgra8, npix * 4, cudaMemcpyDeviceToHost, s));
+    CRV_CUDA(cudaStreamSynchronize(s));
+    return CRV_OK;
+}
+
+int crv_image_save_png(crv_image* img, const char* path, void* stream)
+{
+    CRV_REQUIRE(img && path, "crv_image_save_png: null argument");
+    std::vector<uint8_t> px((size_t)img->width * img->height * 4);
+    CRV_TRY(crv_image_blit_srgb8(img, px.data(), stream));
+    for (size_t i = 0; i < px.size(); i += 4) std::swap(px[i], px[i + 2]);        // B8G8R8A8 -> PNG's R, G, B, A
+    return crv_write_png_rgba8(path, img->width, img->height, px.data());
+}
+
+int crv_image_save_pfm(crv_image* img, const char* path, void* stream)
+{
+    CRV_REQUIRE(img && path, "crv_image_save_pfm: null argument");
+    std::vector<float> px((size_t)img->width * img->height * 4);
+    CRV_TRY(crv_image_download(img, px.data(), stream));
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { crv_set_error("crv_image_save_pfm: cannot write '%s'", path); return CRV_ERR_IO; }
+    std::fprintf(f, "PF\n%u %u\n-1.0\n", img->width, img->height);              // RGB float, little endian, bottom-up rows
+    bool ok = true;
+    for (uint32_t y = img->height; y-- > 0 && ok;)
+        for (uint32_t x = 0; x < img->width && ok; ++x) ok = std::fwrite(&px[((size_t)y * img->width + x) * 4], sizeof(float), 3, f) == 3;
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { crv_set_error("crv_image_save_pfm: short write to '%s'", path); return CRV_ERR_IO; }
+    return CRV_OK;
+}
+
+// Accumulation checkpoint: the progressive state of the path is the result image plus the frame counter the next
+// dispatch will push (PathTracer.comp:420-424); the seed of the last frame is kept so a resumed run can continue the
+// reference's rand() sequence.  Layout: magic "CRVACC1\0", u32 width, u32 height, u32 frameCount, i32 seed, then
+// width*height*4 little-endian floats.
+struct CheckpointHeader {
+    char magic[8];
+    uint32_t width, height, frame_count;
+    int32_t seed;
+};
+
+int crv_image_save_checkpoint(crv_image* img, uint32_t frame_count, int32_t seed, const char* path, void* stream)
+{
+    CRV_REQUIRE(img && path, "crv_image_save_checkpoint: null argument");
+    std::vector<float> px((size_t)img->width * img->height * 4);
+    CRV_TRY(crv_image_download(img, px.data(), stream));
+    CheckpointHeader h{};
+    std::memcpy(h.magic, "CRVACC1", 8);
+    h.width = img->width; h.height = img->height; h.frame_count = frame_count; h.seed = seed;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { crv_set_error("crv_image_save_checkpoint: cannot write '%s'", path); return CRV_ERR_IO; }
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(px.data(), sizeof(float), px.size(), f) == px.size();
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { crv_set_error("crv_image_save_checkpoint: short write to '%s'", path); return CRV_ERR_IO; }
+    return CRV_OK;
+}
+
+int crv_image_load_checkpoint(crv_image* img, uint32_t* frame_count, int32_t* seed, const char* path, void* stream)
+{
+    CRV_REQUIRE(img && path, "crv_image_load_checkpoint: null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { crv_set_error("crv_image_load_checkpoint: cannot open '%s'", path); return CRV_ERR_IO; }
+    CheckpointHeader h{};
+    std::vector<float> px((size_t)img->width * img->height * 4);
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1;
+    if (ok && (std::memcmp(h.magic, "CRVACC1", 8) != 0 || h.width != img->width || h.height != img->height)) {
+        std::fclose(f);
+        crv_set_error("crv_image_load_checkpoint: '%s' is not a %ux%u accumulation checkpoint", path, img->width, img->height);
+        return CRV_ERR_INVALID;
+    }
+    ok = ok && std::fread(px.data(), sizeof(float), px.size(), f) == px.size();
+    std::fclose(f);
+    if (!ok) { crv_set_error("crv_image_load_checkpoint: '%s' is truncated", path); return CRV_ERR_IO; }
+    CRV_TRY(crv_image_upload(img, px.data(), stream));
+    CRV_ENTER(img->ctx);
+    CRV_CUDA(cudaStreamSynchronize(as_stream(stream)));          // px goes out of scope
+    if (frame_count) *frame_count = h.frame_count;
+    if (seed) *seed = h.seed;
     return CRV_OK;
 }
 

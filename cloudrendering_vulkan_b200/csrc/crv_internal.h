@@ -244,6 +244,7 @@ struct crv_image {
     uint32_t width = 0, height = 0;
     float* rgba = nullptr;                 // width*height*4 floats
     bool owned = true;
+    unsigned char* bgra8 = nullptr;        // width*height*4 bytes: staging of the present step (allocated on first use)
 };
 
 // kernels / helpers implemented across the .cu files --------------------------------------------------
@@ -251,4 +252,5 @@ int crv_launch_retile(crv_ctx* ctx, const float* linear_src, crv_volume* dst, cu
 int crv_launch_untile(crv_ctx* ctx, const crv_volume* src, float* linear_dst, cudaStream_t s);     // volume.cu
 int crv_launch_brick_max(crv_ctx* ctx, crv_volume* vol, cudaStream_t s);                           // volume.cu
 int crv_launch_majorant(crv_ctx* ctx, crv_volume* vol, cudaStream_t s);                            // volume.cu
+int crv_launch_blit_srgb8(crv_ctx* ctx, const float* rgba, unsigned char* bgra8, size_t npix, cudaStream_t s);  // volume.cu
 int crv_launch_fbm(crv_ctx* ctx, float* linear_dst, uint32_t n, uint32_t seed, cudaStream_t s);    // fbm.cu

@@ -25,7 +25,7 @@
 namespace {
 
 struct Options {
-    std::string xyz, pfm;
+    std::string xyz, pfm, png, resume, checkpoint;
     unsigned fbm = 128;
     int width = 512, height = 512, device = 0;
     unsigned spp = 16, nsv = 500;
@@ -57,6 +57,9 @@ bool parse(int argc, char** argv, Options& o)
         else if (a == "--per-frame") o.per_frame = true;
         else if (a == "--device") o.device = std::atoi(next("--device"));
         else if (a == "--pfm") o.pfm = next("--pfm");
+        else if (a == "--png") o.png = next("--png");
+        else if (a == "--resume") o.resume = next("--resume");
+        else if (a == "--checkpoint") o.checkpoint = next("--checkpoint");
         else return false;
     }
     return o.width > 0 && o.height > 0 && o.spp > 0 && o.nsv > 0;
@@ -124,7 +127,8 @@ int main(int argc, char** argv)
     Options o;
     if (!parse(argc, argv, o)) {
         std::fprintf(stderr, "usage: crv_headless [--xyz file | --fbm N] [--width W --height H] [--spp S] [--nsv N] [--g G | --isotropic]\n"
-                             "                    [--absorption A] [--density-scaling D] [--light x,y,z] [--fov F] [--per-frame] [--device i] [--pfm out]\n");
+                             "                    [--absorption A] [--density-scaling D] [--light x,y,z] [--fov F] [--per-frame] [--device i] [--pfm out]\n"
+                             "                    [--png out.png] [--resume acc.ckpt] [--checkpoint acc.ckpt]\n");
         return 2;
     }
     try {
@@ -181,8 +185,17 @@ int main(int argc, char** argv)
         const float sv_ms = app.shadowVolumeTechnique->LastBuildMs();
 
         // ---- RenderLoop (main.cpp:714-736): srand(0); per frame seed = rand() ----
-        std::vector<int32_t> seeds(o.spp);
-        crv::MsvcRandSequence(0, o.spp, seeds.data());
+        // --resume: continue a checkpointed accumulation -- the image, the frameCount the next dispatch pushes, and the
+        // rand() sequence from where it stopped (frame f of a run uses element f of srand(0)'s sequence)
+        uint32_t first_frame = 0;
+        if (!o.resume.empty()) {
+            int32_t last_seed = 0;
+            app.resultImage->LoadCheckpoint(o.resume.c_str(), &first_frame, &last_seed);
+            app.pushConstants.frameCount = first_frame;
+        }
+        std::vector<int32_t> all_seeds(first_frame + o.spp);
+        crv::MsvcRandSequence(0, first_frame + o.spp, all_seeds.data());
+        std::vector<int32_t> seeds(all_seeds.begin() + first_frame, all_seeds.end());
         app.device->WaitIdle();
         const auto t0 = std::chrono::steady_clock::now();
         if (o.per_frame) {
@@ -192,7 +205,7 @@ int main(int argc, char** argv)
                 app.pushConstants.frameCount++;
             }
         } else {
-            app.pathTracingTechnique->RenderBatch(seeds.data(), o.spp, 0, CRV_ACCUM_RUNNING_MEAN, nullptr, 0);
+            app.pathTracingTechnique->RenderBatch(seeds.data(), o.spp, first_frame, CRV_ACCUM_RUNNING_MEAN, nullptr, 0);
             app.pushConstants.frameCount += o.spp;
         }
         app.device->WaitIdle();
@@ -201,15 +214,9 @@ int main(int argc, char** argv)
         std::vector<float> rgba((size_t)o.width * o.height * 4);
         app.resultImage->Download(rgba.data());
         const crv_pt_stats st = app.pathTracingTechnique->GetStats();
-        if (!o.pfm.empty()) {
-            // PFM: RGB float, bottom-up rows, little endian
-            FILE* f = std::fopen(o.pfm.c_str(), "wb");
-            if (!f) { std::fprintf(stderr, "crv_headless: cannot write %s\n", o.pfm.c_str()); return 1; }
-            std::fprintf(f, "PF\n%d %d\n-1.0\n", o.width, o.height);
-            for (int y = o.height - 1; y >= 0; --y)
-                for (int x = 0; x < o.width; ++x) std::fwrite(&rgba[((size_t)y * o.width + x) * 4], sizeof(float), 3, f);
-            std::fclose(f);
-        }
+        if (!o.pfm.empty()) app.resultImage->SavePfm(o.pfm.c_str());                 // linear RGB float
+        if (!o.png.empty()) app.resultImage->SavePng(o.png.c_str());                 // what the sRGB swapchain image would show
+        if (!o.checkpoint.empty()) app.resultImage->SaveCheckpoint(o.checkpoint.c_str(), app.pushConstants.frameCount, seeds.back());
         std::printf("{\"width\": %d, \"height\": %d, \"spp\": %u, \"mode\": \"%s\", \"render_ms\": %.3f, \"mpath_samples_per_s\": %.1f, "
                     "\"sv_build_ms\": %.4f, \"paths\": %llu, \"tracking_steps\": %llu, \"collisions\": %llu, \"kernel_launches\": %llu, "
                     "\"image_fnv1a\": \"%016llx\"}\n",

@@ -2,6 +2,8 @@
 // setters of UniformBuffers.h (through include/crv/uniform_buffers.h), SetCloudProperties (main.cpp:144-163),
 // the MSVC rand() frame-seed sequence (main.cpp:722,949) and the Grid3D ".xyz" file format (Grid3D.h,
 // GridData.h).  Pure host code: compiled by g++ with -ffp-contract=off, no CUDA in this file.
+#include <cstdio>
+#include <vector>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -100,6 +102,74 @@ int crv_grid_save(const char* path, const uint32_t counts[3], const double voxel
 int crv_grid_save_zfastest(const char* path, const uint32_t counts[3], const double voxel_size[3], const float* data_xfastest)
 {
     return grid_save(path, counts, voxel_size, data_xfastest, true);
+}
+
+
+// ---- PNG: 8-bit RGBA, filter 0 on every row, zlib stream of stored deflate blocks (no compression library needed) ----
+static uint32_t png_crc(uint32_t crc, const unsigned char* p, size_t n)
+{
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        ready = true;
+    }
+    crc = ~crc;
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return ~crc;
+}
+
+static bool png_chunk(FILE* f, const char type[4], const unsigned char* data, uint32_t n)
+{
+    const unsigned char len[4] = {(unsigned char)(n >> 24), (unsigned char)(n >> 16), (unsigned char)(n >> 8), (unsigned char)n};
+    uint32_t crc = png_crc(0, reinterpret_cast<const unsigned char*>(type), 4);
+    if (n) crc = png_crc(crc, data, n);
+    const unsigned char c4[4] = {(unsigned char)(crc >> 24), (unsigned char)(crc >> 16), (unsigned char)(crc >> 8), (unsigned char)crc};
+    return std::fwrite(len, 1, 4, f) == 4 && std::fwrite(type, 1, 4, f) == 4 && (n == 0 || std::fwrite(data, 1, n, f) == n) &&
+           std::fwrite(c4, 1, 4, f) == 4;
+}
+
+int crv_write_png_rgba8(const char* path, uint32_t width, uint32_t height, const unsigned char* rgba)
+{
+    if (!path || !rgba || width == 0 || height == 0) { crv_set_error("crv_write_png_rgba8: bad argument"); return CRV_ERR_INVALID; }
+    // raw scanlines: filter byte 0 + width*4 bytes
+    const size_t row = (size_t)width * 4 + 1, raw_n = row * height;
+    std::vector<unsigned char> z;
+    z.reserve(raw_n + raw_n / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);                         // zlib header, no preset dictionary
+    uint32_t a = 1, b = 0;                                        // adler32 of the raw data
+    std::vector<unsigned char> raw(raw_n);
+    for (uint32_t y = 0; y < height; ++y) {
+        raw[y * row] = 0;
+        std::memcpy(&raw[y * row + 1], rgba + (size_t)y * width * 4, (size_t)width * 4);
+    }
+    for (size_t i = 0; i < raw_n; ++i) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+    for (size_t off = 0; off < raw_n; off += 65535) {
+        const size_t n = raw_n - off < 65535 ? raw_n - off : 65535;
+        z.push_back(off + n == raw_n ? 1 : 0);                    // BFINAL, BTYPE = 00 (stored)
+        z.push_back((unsigned char)(n & 0xff)); z.push_back((unsigned char)(n >> 8));
+        z.push_back((unsigned char)(~n & 0xff)); z.push_back((unsigned char)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+    }
+    const uint32_t adler = (b << 16) | a;
+    z.push_back((unsigned char)(adler >> 24)); z.push_back((unsigned char)(adler >> 16));
+    z.push_back((unsigned char)(adler >> 8)); z.push_back((unsigned char)adler);
+
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { crv_set_error("crv_write_png_rgba8: cannot write '%s'", path); return CRV_ERR_IO; }
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    const unsigned char ihdr[13] = {(unsigned char)(width >> 24), (unsigned char)(width >> 16), (unsigned char)(width >> 8), (unsigned char)width,
+                                    (unsigned char)(height >> 24), (unsigned char)(height >> 16), (unsigned char)(height >> 8), (unsigned char)height,
+                                    8, 6, 0, 0, 0};               // 8 bit, colour type 6 (RGBA), deflate, adaptive filtering, no interlace
+    bool ok = std::fwrite(sig, 1, 8, f) == 8 && png_chunk(f, "IHDR", ihdr, 13) && png_chunk(f, "IDAT", z.data(), (uint32_t)z.size()) &&
+              png_chunk(f, "IEND", nullptr, 0);
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { crv_set_error("crv_write_png_rgba8: short write to '%s'", path); return CRV_ERR_IO; }
+    return CRV_OK;
 }
 
 }  // extern "C"

@@ -195,3 +195,35 @@ int crv_launch_majorant(crv_ctx* ctx, crv_volume* vol, cudaStream_t s)
     vol->majorant_valid = true;
     return CRV_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Present step.  After the dispatch the reference blits the RGBA32F result image 1:1 into the swapchain image,
+// VK_FORMAT_B8G8R8A8_SRGB (RenderTechniquePT.cpp:143-167, VulkanSwapchain.cpp:68-79): per channel clamp to [0,1],
+// linear -> sRGB transfer function on R, G, B (alpha stays linear), round(x * 255) to UNORM8, stored B, G, R, A.
+// Same size and texel centres, so VK_FILTER_LINEAR reduces to a copy.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ float srgb_oetf(float l)
+{
+    const float c = fminf(fmaxf(l, 0.0f), 1.0f);                 // NaN -> 0
+    return c <= 0.0031308f ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+}
+__device__ __forceinline__ unsigned unorm8(float v) { return (unsigned)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f); }
+
+__global__ void blit_srgb8_kernel(const float4* __restrict__ src, uchar4* __restrict__ dst, size_t n)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = src[i];
+    dst[i] = make_uchar4((unsigned char)unorm8(srgb_oetf(p.z)), (unsigned char)unorm8(srgb_oetf(p.y)),
+                         (unsigned char)unorm8(srgb_oetf(p.x)), (unsigned char)unorm8(p.w));
+}
+}  // namespace
+
+int crv_launch_blit_srgb8(crv_ctx* ctx, const float* rgba, unsigned char* bgra8, size_t npix, cudaStream_t s)
+{
+    blit_srgb8_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(rgba), reinterpret_cast<uchar4*>(bgra8), npix);
+    ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    return CRV_OK;
+}

@@ -137,6 +137,28 @@ class Image:
     def scale(self, factor: float, stream=0):
         check(lib.crv_image_scale(self.handle, C.c_float(factor), _stream(stream)))
 
+    # ---- present step and files (RenderTechniquePT.cpp:143-167: blit to the B8G8R8A8_SRGB swapchain image) ----
+    def blit_srgb8(self, stream=0) -> np.ndarray:
+        """HxWx4 bytes in swapchain order B,G,R,A: clamp, linear->sRGB on colour, UNORM8"""
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        check(lib.crv_image_blit_srgb8(self.handle, out.ctypes.data_as(C.c_void_p), _stream(stream)))
+        return out
+
+    def save_png(self, path: str, stream=0):
+        check(lib.crv_image_save_png(self.handle, path.encode(), _stream(stream)))
+
+    def save_pfm(self, path: str, stream=0):
+        check(lib.crv_image_save_pfm(self.handle, path.encode(), _stream(stream)))
+
+    def save_checkpoint(self, path: str, frame_count: int, seed: int = 0, stream=0):
+        check(lib.crv_image_save_checkpoint(self.handle, int(frame_count), int(seed), path.encode(), _stream(stream)))
+
+    def load_checkpoint(self, path: str, stream=0):
+        """-> (frameCount the next dispatch pushes, seed of the last rendered frame)"""
+        fc, seed = C.c_uint32(), C.c_int32()
+        check(lib.crv_image_load_checkpoint(self.handle, C.byref(fc), C.byref(seed), path.encode(), _stream(stream)))
+        return fc.value, seed.value
+
     @property
     def device_ptr(self) -> int:
         p = C.c_void_p()

@@ -111,6 +111,18 @@ public:
     void Clear(CommandStream stream = nullptr) { Check(crv_image_clear(m_img, stream)); }
     void Download(float* host_rgba, CommandStream stream = nullptr) { Check(crv_image_download(m_img, host_rgba, stream)); }
     void Scale(float s, CommandStream stream = nullptr) { Check(crv_image_scale(m_img, s, stream)); }
+    // present step (RenderTechniquePT.cpp:143-167): the result image as the B8G8R8A8_SRGB swapchain image would hold it
+    void BlitSrgb8(uint8_t* host_bgra8, CommandStream stream = nullptr) { Check(crv_image_blit_srgb8(m_img, host_bgra8, stream)); }
+    void SavePng(const char* path, CommandStream stream = nullptr) { Check(crv_image_save_png(m_img, path, stream)); }
+    void SavePfm(const char* path, CommandStream stream = nullptr) { Check(crv_image_save_pfm(m_img, path, stream)); }
+    void SaveCheckpoint(const char* path, uint32_t frameCount, int32_t seed, CommandStream stream = nullptr)
+    {
+        Check(crv_image_save_checkpoint(m_img, frameCount, seed, path, stream));
+    }
+    void LoadCheckpoint(const char* path, uint32_t* frameCount, int32_t* seed, CommandStream stream = nullptr)
+    {
+        Check(crv_image_load_checkpoint(m_img, frameCount, seed, path, stream));
+    }
 
 private:
     crv_image* m_img = nullptr;

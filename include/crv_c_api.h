@@ -204,6 +204,19 @@ int  crv_image_clear(crv_image* img, void* stream);
 int  crv_image_download(crv_image* img, float* host_rgba, void* stream);
 int  crv_image_upload(crv_image* img, const float* host_rgba, void* stream);
 int  crv_image_device_ptr(crv_image* img, float** out);
+/* Present step: what the reference does right after the dispatch -- vkCmdBlitImage of the RGBA32F result
+ * image into the VK_FORMAT_B8G8R8A8_SRGB swapchain image (RenderTechniquePT.cpp:143-167,
+ * VulkanSwapchain.cpp:68-79): clamp, linear->sRGB on R,G,B, round to UNORM8, bytes B,G,R,A.  The
+ * conversion runs on the device; host_bgra8 receives width*height*4 bytes.  Synchronous. */
+int  crv_image_blit_srgb8(crv_image* img, uint8_t* host_bgra8, void* stream);
+/* the presented image as an 8-bit RGBA PNG / the linear result image as an RGB PFM (bottom-up rows) */
+int  crv_image_save_png(crv_image* img, const char* path, void* stream);
+int  crv_image_save_pfm(crv_image* img, const char* path, void* stream);
+/* accumulation checkpoint / resume: result image + the frameCount the next dispatch pushes + last seed */
+int  crv_image_save_checkpoint(crv_image* img, uint32_t frame_count, int32_t seed, const char* path, void* stream);
+int  crv_image_load_checkpoint(crv_image* img, uint32_t* frame_count, int32_t* seed, const char* path, void* stream);
+/* host-only helper behind crv_image_save_png: 8-bit RGBA PNG with stored (uncompressed) deflate blocks */
+int  crv_write_png_rgba8(const char* path, uint32_t width, uint32_t height, const unsigned char* rgba);
 /* out = in * scale (the divide-by-spp epilogue after the multi-GPU sum reduce) */
 int  crv_image_scale(crv_image* img, float scale, void* stream);
 

@@ -532,6 +532,23 @@ float orc_sample_phase(const void* params28, const float in[3], const float s[3]
 {
     return samplePhase(load_params(params28), vec3{in[0], in[1], in[2]}, vec3{s[0], s[1], s[2]});
 }
+void orc_blit_srgb8(const float* rgba, size_t npix, unsigned char* bgra8)
+{
+    auto oetf = [](float l) {
+        const float c = !(l > 0.0f) ? 0.0f : (l > 1.0f ? 1.0f : l);       // clamp; NaN -> 0
+        return c <= 0.0031308f ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+    };
+    auto unorm8 = [](float v) {
+        const float c = !(v > 0.0f) ? 0.0f : (v > 1.0f ? 1.0f : v);
+        return (unsigned char)lrintf(c * 255.0f);                        // round to nearest even, like cvt.rni
+    };
+    for (size_t i = 0; i < npix; ++i) {
+        bgra8[4 * i + 0] = unorm8(oetf(rgba[4 * i + 2]));
+        bgra8[4 * i + 1] = unorm8(oetf(rgba[4 * i + 1]));
+        bgra8[4 * i + 2] = unorm8(oetf(rgba[4 * i + 0]));
+        bgra8[4 * i + 3] = unorm8(rgba[4 * i + 3]);
+    }
+}
 void orc_background(const float dir[3], float rgba[4])
 {
     const vec4 c = sampleBackground(vec3{dir[0], dir[1], dir[2]});

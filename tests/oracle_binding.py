@@ -43,6 +43,7 @@ lib.orc_invert_cdf.argtypes = [_vp, _f]
 lib.orc_sample_phase.restype = _f
 lib.orc_sample_phase.argtypes = [_vp, _fp, _fp]
 lib.orc_background.argtypes = [_fp, _fp]
+lib.orc_blit_srgb8.argtypes = [_vp, C.c_size_t, _vp]
 lib.orc_texture3d.restype = _f
 lib.orc_texture3d.argtypes = [_vp, _u32, _u32, _u32, _fp]
 lib.orc_sample_cloud.restype = _f
@@ -123,6 +124,14 @@ def background(direction):
     out = (C.c_float * 4)()
     lib.orc_background(_f3(direction), out)
     return np.array(out[:], np.float32)
+
+
+def blit_srgb8(rgba):
+    """the reference's present step (vkCmdBlitImage to B8G8R8A8_SRGB): HxWx4 float -> HxWx4 bytes B,G,R,A"""
+    a = np.ascontiguousarray(rgba, np.float32)
+    out = np.empty(a.shape, np.uint8)
+    lib.orc_blit_srgb8(_ptr(a), a.size // 4, _ptr(out))
+    return out
 
 
 def texture3d(vol, nx, ny, nz, uvw):

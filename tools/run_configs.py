@@ -23,6 +23,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cloudrendering_vulkan_b200 as crv  # noqa: E402
 
 
+MATH_MODE = crv.PT_MATH_DRIVER
+
+
 def timed(fn):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -39,7 +42,7 @@ def run_plain(ctx, name, spp=None, parity=False):
     if spp:
         wl = dataclasses.replace(wl, spp=spp)
     stream = torch.cuda.current_stream().cuda_stream
-    r = crv.make_renderer(ctx, wl, cloud_layout="brick")
+    r = crv.make_renderer(ctx, wl, cloud_layout="brick", math_mode=MATH_MODE)
     r.set_cloud_synthetic(wl.n_cloud, wl.fbm_seed, stream)
     seeds = crv.msvc_rand_sequence(wl.spp)
     pt = r.pathTracingTechnique
@@ -111,7 +114,7 @@ def run_plain(ctx, name, spp=None, parity=False):
 def run_c5(ctx, frames):
     wl = crv.CONFIGS["c5"]
     stream = torch.cuda.current_stream().cuda_stream
-    r = crv.make_renderer(ctx, wl, cloud_layout="brick")
+    r = crv.make_renderer(ctx, wl, cloud_layout="brick", math_mode=MATH_MODE)
     r.set_cloud_synthetic(wl.n_cloud, wl.fbm_seed, stream)
     seeds = crv.msvc_rand_sequence(wl.spp)
     pt = r.pathTracingTechnique
@@ -143,7 +146,10 @@ def main():
     ap.add_argument("--configs", default="c1_iso,c1_hg,c4,c3,c5")
     ap.add_argument("--c3-spp", type=int, default=64)
     ap.add_argument("--c5-frames", type=int, default=8)
+    ap.add_argument("--math", default="driver", choices=["strict", "driver"])
     args = ap.parse_args()
+    global MATH_MODE
+    MATH_MODE = crv.PT_MATH_DRIVER if args.math == "driver" else crv.PT_MATH_STRICT
     torch.cuda.set_device(0)
     ctx = crv.Context(0)
     for name in args.configs.split(","):
@@ -153,6 +159,7 @@ def main():
             out = run_plain(ctx, "c3", spp=args.c3_spp)
         else:
             out = run_plain(ctx, name, parity=name.startswith("c1"))
+        out["math"] = args.math
         print(json.dumps(out), flush=True)
     ctx.close()
 
