@@ -114,6 +114,8 @@ struct crv_pt {
     float2* samples = nullptr;
     size_t samples_bytes = 0;
     unsigned int* job_counter = nullptr;
+    float* rcp_fc1 = nullptr;          // reciprocals of the running mean's divisors for the frames of the current render call
+    size_t rcp_elems = 0;
     unsigned long long* stats = nullptr;
     uint32_t* dbg_steps = nullptr;
     uint32_t* dbg_coll = nullptr;
@@ -793,6 +795,7 @@ int crv_pt_destroy(crv_pt* pt)
     if (pt->qtable) cudaFree(pt->qtable);
     if (pt->qtable_wide) cudaFree(pt->qtable_wide);
     if (pt->qcoarse) cudaFree(pt->qcoarse);
+    if (pt->rcp_fc1) cudaFree(pt->rcp_fc1);
     if (pt->hitlist) cudaFree(pt->hitlist);
     if (pt->start) cudaFree(pt->start);
     if (pt->nhit) cudaFree(pt->nhit);
@@ -1144,6 +1147,17 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
     c.start = pt->start;
     c.nhit = pt->nhit;
     c.first_frame_count = first_fc;
+    if (pt->rcp_elems < n) {
+        if (pt->rcp_fc1) CRV_CUDA(cudaFree(pt->rcp_fc1));
+        pt->rcp_fc1 = nullptr;
+        pt->rcp_elems = 0;
+        const size_t cap = n < 256 ? 256 : n;
+        CRV_CUDA(cudaMalloc(&pt->rcp_fc1, sizeof(float) * cap));
+        pt->rcp_elems = cap;
+    }
+    CRV_TRY(crv_launch_rcp_frames(pt->ctx, pt->rcp_fc1, first_fc, n, s));
+    pt->launches++;
+    c.rcp_fc1 = pt->rcp_fc1;
     CRV_CUDA(cudaMemsetAsync(pt->nhit, 0, sizeof(uint32_t), s));
     CRV_TRY(crv_launch_classify(pt->ctx, c, n, pt->hitlist, pt->start, pt->nhit, s));
     pt->launches++;
@@ -1182,6 +1196,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         fc.nframes = nf;
         fc.first_frame_count = first_fc + f0;
         fc.accum_mode = mode;
+        fc.rcp_fc1 = pt->rcp_fc1 + f0;
         CRV_TRY(crv_launch_fold(pt->ctx, fc, s));
         pt->launches += 2;
     }

@@ -75,6 +75,9 @@ struct PTConst {
     uint32_t nframes;                  // frames in this launch
     int32_t seeds[PT_MAX_FRAMES_PER_LAUNCH];   // pushConstants.seed of every frame of this launch (by value: no staging copy)
     uint32_t first_frame_count;        // pushConstants.frameCount of frame 0 of this launch
+    const float* rcp_fc1;              // rcp_fc1[f] = RN(1 / float(first_frame_count + f + 1)) for the frames of this render CALL
+                                       // (rcp_kernel, IEEE division): the running mean's divisor is frame-uniform, so its
+                                       // division is the exact FMA division of exact_div.cuh
     int accum_mode;                    // crv_accum_mode
     float4* image;                     // W*H rgba32f result image (binding 0); written by pt_classify_kernel / fold_kernel
     float2* samples;                   // nframes * nhit records (S, dir.y), index = job
@@ -94,11 +97,13 @@ struct FoldConst {
     const uint32_t* nhit;
     uint32_t npix, nframes, first_frame_count, width;
     int accum_mode;
+    const float* rcp_fc1;              // RN(1 / float(first_frame_count + f + 1)), f = 0 .. nframes-1 of THIS launch
 };
 
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
 int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, uint32_t* hitlist, float* start, uint32_t* nhit, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
+int crv_launch_rcp_frames(crv_ctx* ctx, float* rcp, uint32_t first_frame_count, uint32_t n, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
 int crv_launch_qcoarse(crv_ctx* ctx, const float* absmax_wide, uint8_t* qc, int nbx, int nby, int nbz, int shift, float max_ext, cudaStream_t s);
 int crv_pt_pool_smem_budget();     // bytes of shared memory the pool scheduler leaves for the coarse table
