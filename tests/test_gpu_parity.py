@@ -498,3 +498,81 @@ def test_cuda_path_against_live_reference_shaders(crv, orc, ctx):
     print(f"live reference shaders: {int((~same).sum())}/{same.size} threshold-divergent, max rel err {err[same].max():.2e}")
     assert same.mean() >= 0.99 and err[same].max() <= 1e-4 and rc.sum() > 1000
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# edge cases: empty / degenerate / ragged inputs, both schedulers
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sched", ["pool", "lanes"])
+def test_empty_cloud_is_pure_background(crv, orc, ctx, sched):
+    """an all-zero grid: majorant 0 -> maxExtinction = max(0, 0.01) (main.cpp:144-163); every path crosses the box without
+    a collision and every pixel is exactly the oracle's background-only sample; the shadow volume is all ones"""
+    n, w, h, nsv = 16, 40, 24, 24
+    cloud = np.zeros(n ** 3, np.float32)
+    wl = crv.Workload("t", n, w, h, 1, nsv, 50.0, 0.0, 0.85, (1.0, -1.0, 0.0))
+    r = crv.make_renderer(ctx, wl, cloud_layout="brick")
+    r.pathTracingTechnique.SetScheduler(sched)
+    r.set_cloud_host(cloud, (n, n, n), (1.0 / n,) * 3)
+    assert r.cloudProperties.maxExtinction == np.float32(0.01)
+    sv = r.shadowVolumeImage.download()
+    assert (sv == 1.0).all()
+    r.pathTracingTechnique.SetDebugCounters(True)
+    r.pushConstants.seed = 38
+    r.pathTracingTechnique.RecordDrawCommands(0, 0)
+    gpu = r.resultImage.download()
+    gs, gc = r.pathTracingTechnique.DownloadDebugCounters()
+    pc = crv.PushConstants()
+    pc.seed, pc.frameCount = 38, 0
+    cpu = np.zeros((h, w, 4), np.float32)
+    _, cs, cc = orc.path_trace_frame(cloud, sv, r.cameraProperties, r.cloudProperties, r.parameters, r.shadowVolumeProperties, pc, 0.0, cpu)
+    assert gc.sum() == 0 and cc.sum() == 0
+    assert np.array_equal(gs, cs), "tracking-iteration counts through empty space must be identical"
+    assert np.array_equal(_bits(gpu), _bits(cpu)), "no transcendental reaches the pixel value without a collision"
+    r.close()
+
+
+@pytest.mark.parametrize("shape,res", [((1, 1, 1), (2, 2)), ((3, 5, 2), (34, 2)), ((9, 8, 17), (30, 38))])
+def test_degenerate_sizes(crv, orc, ctx, shape, res):
+    """one-voxel and ragged grids, 2x2 / two-row / non-multiple-of-32 images (fewer jobs than one warp, off-grid dispatch stride; CameraProperties keeps half sizes, so resolutions are even: UniformBuffers.h:46-50)"""
+    rng = np.random.default_rng(21)
+    cloud = (rng.random(shape[0] * shape[1] * shape[2], dtype=np.float32) * 0.8 + 0.2).astype(np.float32)
+    w, h = res
+    wl = crv.Workload("t", 0, w, h, 1, 19, 300.0, 0.0, None, (0.3, -0.8, 0.5))
+    imgs = []
+    for sched in ["pool", "lanes"]:
+        r = crv.make_renderer(ctx, wl, cloud_layout="brick")
+        r.pathTracingTechnique.SetScheduler(sched)
+        r.set_cloud_host(cloud, shape, (0.5 / shape[0], 0.5 / shape[1], 0.5 / shape[2]))
+        _sv_check(r.shadowVolumeImage.download(), orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties))
+        sv_cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+        r.reset_accumulation()
+        r.pathTracingTechnique.SetDebugCounters(True)
+        r.pushConstants.seed = 7719
+        r.pathTracingTechnique.RecordDrawCommands(0, 0)
+        gpu = r.resultImage.download()
+        gs, gc = r.pathTracingTechnique.DownloadDebugCounters()
+        pc = crv.PushConstants()
+        pc.seed, pc.frameCount = 7719, 0
+        cpu = np.zeros((h, w, 4), np.float32)
+        _, cs, cc = orc.path_trace_frame(cloud, sv_cpu, r.cameraProperties, r.cloudProperties, r.parameters,
+                                         r.shadowVolumeProperties, pc, 0.0, cpu)
+        same = (gs == cs) & (gc == cc)
+        err = np.abs(gpu - cpu) / np.maximum(np.abs(cpu), 1e-3)
+        assert same.mean() >= 0.9 and (not same.any() or err[same].max() <= 1e-4)
+        r.render(3)                                   # and a batch on top of the frame, for the hit-list / fold path
+        imgs.append(r.resultImage.download().copy())
+        r.close()
+    assert np.array_equal(_bits(imgs[0]), _bits(imgs[1]))
+
+
+def test_more_frames_than_one_launch_carries(crv, orc, ctx):
+    """300 frames: more than the 256 seeds one launch carries by value -> several launches, still the sequential result"""
+    r, _ = make_scene(crv, orc, ctx, n=16, w=40, h=24, nsv=24, layout="brick", g=0.85, absorption=0.1)
+    seeds = crv.msvc_rand_sequence(300)
+    r.render(300, seeds=seeds)
+    a = r.resultImage.download().copy()
+    r.reset_accumulation()
+    for f in range(0, 300, 75):
+        r.render(75, seeds=seeds[f:f + 75])
+    assert np.array_equal(_bits(a), _bits(r.resultImage.download()))
+    r.close()
