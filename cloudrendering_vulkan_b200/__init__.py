@@ -8,14 +8,14 @@ loads the shared library and fails loudly if it has not been built: there is no 
 from . import capi
 from .capi import PT_MATH_DRIVER, PT_MATH_STRICT, ACCUM_RUNNING_MEAN, ACCUM_SUM, LAYOUT_BRICK, LAYOUT_LINEAR, LAYOUT_TEX3D, CrvError
 from .scene import CONFIGS, HeadlessRenderer, Workload, make_renderer
-from .structs import (CameraProperties, CloudProperties, Grid3D, Parameters, PathTracerExtensions, PushConstants,
+from .structs import (CameraProperties, CloudProperties, Grid3D, Parameters, PathTracerExtensions, PhotonMapProperties, PushConstants,
                       ShadowVolumeProperties, msvc_rand_sequence, orthonormal_basis)
-from .technique import Context, Image, RenderTechnique, RenderTechniquePT, RenderTechniqueSV, Volume, rng_tap
+from .technique import Context, Image, RenderTechnique, RenderTechniquePPM, RenderTechniquePT, RenderTechniqueSV, Volume, rng_tap
 
 __all__ = [
     "capi", "CrvError", "ACCUM_RUNNING_MEAN", "ACCUM_SUM", "PT_MATH_STRICT", "PT_MATH_DRIVER", "LAYOUT_LINEAR", "LAYOUT_BRICK", "LAYOUT_TEX3D",
     "CONFIGS", "HeadlessRenderer", "Workload", "make_renderer",
-    "CameraProperties", "CloudProperties", "Grid3D", "Parameters", "PathTracerExtensions", "PushConstants",
+    "CameraProperties", "CloudProperties", "Grid3D", "Parameters", "PathTracerExtensions", "PhotonMapProperties", "PushConstants",
     "ShadowVolumeProperties", "msvc_rand_sequence", "orthonormal_basis",
-    "Context", "Image", "RenderTechnique", "RenderTechniquePT", "RenderTechniqueSV", "Volume", "rng_tap",
+    "Context", "Image", "RenderTechnique", "RenderTechniquePPM", "RenderTechniquePT", "RenderTechniqueSV", "Volume", "rng_tap",
 ]

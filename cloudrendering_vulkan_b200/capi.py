@@ -58,6 +58,18 @@ class ShadowVolumePropertiesPOD(C.Structure):
                 ("voxelSize", C.c_float)]
 
 
+class PhotonPOD(C.Structure):
+    """UniformBuffers.h:203-210 / PPM_PT.comp:14-21"""
+    _fields_ = [("position", C.c_float * 4), ("power", C.c_float * 4), ("phi", C.c_float), ("theta", C.c_float),
+                ("_padding", C.c_float * 2)]
+
+
+class PhotonMapPropertiesPOD(C.Structure):
+    """UniformBuffers.h:212-249"""
+    _fields_ = [("lightDirection", C.c_float * 4), ("bounds", (C.c_float * 4) * 2), ("voxelCount", C.c_int32 * 3),
+                ("voxelSize", C.c_float), ("photonSize", C.c_uint32), ("stepSize", C.c_float), ("absorption", C.c_float)]
+
+
 class PTExtensionsPOD(C.Structure):
     _fields_ = [("absorption", C.c_float), ("math_mode", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
@@ -72,6 +84,7 @@ assert C.sizeof(CameraPropertiesPOD) == 68
 assert C.sizeof(CloudPropertiesPOD) == 60
 assert C.sizeof(ParametersPOD) == 28
 assert C.sizeof(ShadowVolumePropertiesPOD) == 152
+assert C.sizeof(PhotonPOD) == 48 and C.sizeof(PhotonMapPropertiesPOD) == 76
 
 _vp = C.c_void_p
 _u32 = C.c_uint32
@@ -142,6 +155,20 @@ SIGNATURES = {
     "crv_pt_rng_tap": (C.c_int, [_vp, _i32, _u32, _u32, _u32, _vp, _vp]),
     "crv_pt_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "crv_pt_set_scheduler": (C.c_int, [_vp, C.c_int]),
+    "crv_ppm_create": (C.c_int, [_vp, _P(PhotonMapPropertiesPOD), _P(PushConstantsPOD), _P(_vp)]),
+    "crv_ppm_destroy": (C.c_int, [_vp]),
+    "crv_ppm_allocate_resources": (C.c_int, [_vp]),
+    "crv_ppm_free_resources": (C.c_int, [_vp]),
+    "crv_ppm_queue_update_cloud_data": (C.c_int, [_vp, _P(CloudPropertiesPOD)]),
+    "crv_ppm_queue_update_cloud_data_sampler": (C.c_int, [_vp, _vp]),
+    "crv_ppm_queue_update_parameters": (C.c_int, [_vp, _P(ParametersPOD)]),
+    "crv_ppm_update_descriptor_sets": (C.c_int, [_vp]),
+    "crv_ppm_record_photon_tracing": (C.c_int, [_vp, _vp, C.c_uint32]),
+    "crv_ppm_download": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "crv_ppm_last_trace_stats": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint64), _P(C.c_float)]),
+    "crv_photon_map_init": (None, [_P(PhotonMapPropertiesPOD)]),
+    "crv_photon_map_set_bounds": (None, [_P(PhotonMapPropertiesPOD), _vp]),
+    "crv_photon_map_total_size": (C.c_uint32, [_P(PhotonMapPropertiesPOD)]),
     "crv_image_blit_srgb8": (C.c_int, [_vp, _vp, _vp]),
     "crv_image_save_png": (C.c_int, [_vp, C.c_char_p, _vp]),
     "crv_image_save_pfm": (C.c_int, [_vp, C.c_char_p, _vp]),

@@ -788,6 +788,232 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
     return CRV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// RenderTechniquePPM, photon-tracing pass
+// ---------------------------------------------------------------------------------------------------
+struct crv_ppm {
+    crv_ctx* ctx = nullptr;
+    const crv_photon_map_properties* ctor_props = nullptr;   // borrowed, like m_photonMapProperties (RenderTechniquePPM.cpp:12)
+    const crv_push_constants* pc = nullptr;
+    // committed / queued bindings
+    crv_photon_map_properties props{};
+    crv_cloud_properties cloud{};
+    crv_parameters params{};
+    crv_volume* cloud_vol = nullptr;
+    bool has_cloud = false, has_params = false;
+    const crv_cloud_properties* q_cloud = nullptr;
+    const crv_parameters* q_params = nullptr;
+    crv_volume* q_cloud_vol = nullptr;
+    // resources
+    crv_photon* photons = nullptr;
+    uint32_t* collisions = nullptr;
+    unsigned long long cells = 0;
+    float* qtable = nullptr;
+    size_t qtable_elems = 0;
+    unsigned long long* stats = nullptr;      // 3 u64
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+int crv_ppm_create(crv_ctx* ctx, const crv_photon_map_properties* props, const crv_push_constants* pc, crv_ppm** out)
+{
+    CRV_REQUIRE(ctx && props && pc && out, "crv_ppm_create: null argument");
+    CRV_ENTER(ctx);
+    *out = nullptr;
+    crv_ppm* p = new (std::nothrow) crv_ppm();
+    if (!p) { crv_set_error("out of host memory"); return CRV_ERR_OOM; }
+    p->ctx = ctx;
+    p->ctor_props = props;
+    p->pc = pc;
+    p->props = *props;
+    if (cudaMalloc(&p->stats, 3 * sizeof(unsigned long long)) != cudaSuccess || cudaEventCreate(&p->ev0) != cudaSuccess ||
+        cudaEventCreate(&p->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        crv_ppm_destroy(p);
+        crv_set_error("crv_ppm_create: device allocation failed");
+        return CRV_ERR_CUDA;
+    }
+    *out = p;
+    return CRV_OK;
+}
+
+int crv_ppm_free_resources(crv_ppm* ppm)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_free_resources: null technique");
+    CRV_ENTER(ppm->ctx);
+    if (ppm->photons) CRV_CUDA(cudaFree(ppm->photons));
+    if (ppm->collisions) CRV_CUDA(cudaFree(ppm->collisions));
+    ppm->photons = nullptr;
+    ppm->collisions = nullptr;
+    ppm->cells = 0;
+    return CRV_OK;
+}
+
+int crv_ppm_destroy(crv_ppm* ppm)
+{
+    if (!ppm) return CRV_OK;
+    cudaSetDevice(ppm->ctx->device);
+    if (ppm->photons) cudaFree(ppm->photons);
+    if (ppm->collisions) cudaFree(ppm->collisions);
+    if (ppm->qtable) cudaFree(ppm->qtable);
+    if (ppm->stats) cudaFree(ppm->stats);
+    if (ppm->ev0) cudaEventDestroy(ppm->ev0);
+    if (ppm->ev1) cudaEventDestroy(ppm->ev1);
+    delete ppm;
+    return CRV_OK;
+}
+
+int crv_ppm_allocate_resources(crv_ppm* ppm)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_allocate_resources: null technique");
+    CRV_TRY(crv_ppm_free_resources(ppm));
+    CRV_ENTER(ppm->ctx);
+    const crv_photon_map_properties& pr = *ppm->ctor_props;
+    CRV_REQUIRE(pr.voxelCount[0] > 0 && pr.voxelCount[1] > 0 && pr.voxelCount[2] > 0, "RenderTechniquePPM: empty photon map");
+    const unsigned long long cells = (unsigned long long)pr.voxelCount[0] * pr.voxelCount[1] * pr.voxelCount[2];
+    CRV_REQUIRE(cells <= 0x7fffffffull, "RenderTechniquePPM: photon map has more than 2^31 cells");
+    CRV_CUDA(cudaMalloc(&ppm->photons, cells * PPM_ELEMENTS_PER_CELL * sizeof(crv_photon)));
+    CRV_CUDA(cudaMalloc(&ppm->collisions, cells * 4 * sizeof(uint32_t)));
+    CRV_CUDA(cudaMemset(ppm->photons, 0, cells * PPM_ELEMENTS_PER_CELL * sizeof(crv_photon)));
+    CRV_CUDA(cudaMemset(ppm->collisions, 0, cells * 4 * sizeof(uint32_t)));
+    ppm->cells = cells;
+    return CRV_OK;
+}
+
+int crv_ppm_queue_update_cloud_data(crv_ppm* ppm, const crv_cloud_properties* cloud)
+{
+    CRV_REQUIRE(ppm && cloud, "crv_ppm_queue_update_cloud_data: null argument");
+    ppm->q_cloud = cloud;
+    return CRV_OK;
+}
+int crv_ppm_queue_update_cloud_data_sampler(crv_ppm* ppm, crv_volume* cloud_image)
+{
+    CRV_REQUIRE(ppm && cloud_image, "crv_ppm_queue_update_cloud_data_sampler: null argument");
+    ppm->q_cloud_vol = cloud_image;
+    return CRV_OK;
+}
+int crv_ppm_queue_update_parameters(crv_ppm* ppm, const crv_parameters* params)
+{
+    CRV_REQUIRE(ppm && params, "crv_ppm_queue_update_parameters: null argument");
+    ppm->q_params = params;
+    return CRV_OK;
+}
+int crv_ppm_update_descriptor_sets(crv_ppm* ppm)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_update_descriptor_sets: null technique");
+    if (ppm->q_cloud) { ppm->cloud = *ppm->q_cloud; ppm->has_cloud = true; ppm->q_cloud = nullptr; }
+    if (ppm->q_cloud_vol) { ppm->cloud_vol = ppm->q_cloud_vol; ppm->q_cloud_vol = nullptr; }
+    if (ppm->q_params) { ppm->params = *ppm->q_params; ppm->has_params = true; ppm->q_params = nullptr; }
+    ppm->props = *ppm->ctor_props;              // g_photonMapPropertiesBuffer->SetData() (main.cpp:300)
+    return CRV_OK;
+}
+
+int crv_ppm_record_photon_tracing(crv_ppm* ppm, void* stream, uint32_t groups_x)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_record_photon_tracing: null technique");
+    CRV_ENTER(ppm->ctx);
+    CRV_REQUIRE(ppm->has_cloud && ppm->cloud_vol, "RenderTechniquePPM: cloud data / sampler not bound (bindings 2,3)");
+    CRV_REQUIRE(ppm->has_params, "RenderTechniquePPM: Parameters not bound (binding 4)");
+    CRV_REQUIRE(ppm->photons && ppm->collisions, "RenderTechniquePPM: AllocateResources has not been called");
+    const crv_photon_map_properties& pr = ppm->props;
+    CRV_REQUIRE((unsigned long long)pr.voxelCount[0] * pr.voxelCount[1] * pr.voxelCount[2] == ppm->cells,
+                "RenderTechniquePPM: PhotonMapProperties.voxelCount changed since AllocateResources");
+    CRV_REQUIRE(ppm->cloud.maxExtinction > 0.0f, "RenderTechniquePPM: maxExtinction must be positive");
+    if (groups_x == 0) groups_x = 200;          // vkCmdDispatch(commandBuffer, 200, 1, 1) (RenderTechniquePPM.cpp:253)
+    CRV_REQUIRE(groups_x <= (1u << 24), "RenderTechniquePPM: more than 2^30 photons per dispatch");
+    cudaStream_t s = as_stream(stream);
+
+    PPMConst k;
+    std::memset(&k, 0, sizeof(k));
+    PTConst& c = k.base;
+    const crv_cloud_properties& cp = ppm->cloud;
+    for (int i = 0; i < 3; ++i) {
+        c.cb0[i] = cp.bounds[0][i];
+        c.cb1[i] = cp.bounds[1][i];
+        c.cext[i] = cp.bounds[1][i] - cp.bounds[0][i];
+        k.pm_light[i] = pr.lightDirection[i];
+        k.pm_b0[i] = pr.bounds[0][i];
+        k.pm_count[i] = pr.voxelCount[i];
+    }
+    c.max_ext = cp.maxExtinction;
+    c.sigma = (cp.maxExtinction * cp.densityScaling) / cp.baseScaling;
+    c.density_scaling = cp.densityScaling;
+    c.light_intensity = 1.0f * ppm->params.lightIntensity;
+    c.two_g = 2.0f * ppm->params.phaseG;
+    c.one_minus_g = 1.0f - ppm->params.phaseG;
+    c.one_plus_g2 = ppm->params.phaseOnePlusG2;
+    c.one_minus_g2 = ppm->params.phaseOneMinusG2;
+    c.one_over_2g = ppm->params.phaseOneOver2G;
+    c.isotropic = ppm->params.isotropic != 0;
+    {
+        auto ordinary = [](float v) { return std::isfinite(v) && std::fabs(v) >= 1e-18f && std::fabs(v) <= 1e18f; };
+        bool ok = ordinary(c.sigma) && ordinary(c.max_ext);
+        for (int i = 0; i < 3; ++i) ok = ok && ordinary(c.cext[i]);
+        CRV_REQUIRE(ok || !(c.density_scaling > 0.0f), "RenderTechniquePPM: extinction scale and cloud extent must be finite and within 1e-18..1e18");
+        c.r_sigma = 1.0f / c.sigma;
+        c.r_max_ext = 1.0f / c.max_ext;
+        for (int i = 0; i < 3; ++i) c.rcext[i] = 1.0f / c.cext[i];
+    }
+    crv_volume* cv = ppm->cloud_vol;
+    c.cloud = cv->view();
+    CRV_REQUIRE((uint32_t)c.cloud.nx == cp.voxelCount[0] && (uint32_t)c.cloud.ny == cp.voxelCount[1] && (uint32_t)c.cloud.nz == cp.voxelCount[2],
+                "RenderTechniquePPM: cloud image size differs from CloudProperties.voxelCount");
+    const size_t nbricks = (size_t)cv->nbx * cv->nby * cv->nbz;
+    if (!cv->brick_max_valid) CRV_TRY(crv_launch_brick_max(ppm->ctx, cv, s));
+    if (ppm->qtable_elems != nbricks) {
+        if (ppm->qtable) CRV_CUDA(cudaFree(ppm->qtable));
+        ppm->qtable = nullptr;
+        ppm->qtable_elems = 0;
+        CRV_CUDA(cudaMalloc(&ppm->qtable, nbricks * sizeof(float)));
+        ppm->qtable_elems = nbricks;
+    }
+    CRV_TRY(crv_launch_qtable(ppm->ctx, cv->brick_absmax, ppm->qtable, (long long)nbricks, c.max_ext, s));   // 1 MB: rebuilt every dispatch
+    c.qtable = ppm->qtable;
+    k.pm_voxel_size = pr.voxelSize;
+    k.pm_absorption = pr.absorption;
+    k.seed = ppm->pc->seed;                    // vkCmdPushConstants snapshot (RenderTechniquePPM.cpp:243)
+    k.n_photons = groups_x * 64u;
+    k.photons = ppm->photons;
+    k.collisions = ppm->collisions;
+    k.stats = ppm->stats;
+    k.cells = ppm->cells;
+
+    CRV_CUDA(cudaEventRecord(ppm->ev0, s));
+    CRV_CUDA(cudaMemsetAsync(ppm->stats, 0, 3 * sizeof(unsigned long long), s));
+    CRV_TRY(crv_launch_ppm_clear(ppm->ctx, ppm->photons, ppm->collisions, ppm->cells, s));
+    CRV_TRY(crv_launch_ppm_trace(ppm->ctx, k, cv->layout, s));
+    CRV_CUDA(cudaEventRecord(ppm->ev1, s));
+    ppm->timed = true;
+    return CRV_OK;
+}
+
+int crv_ppm_download(crv_ppm* ppm, crv_photon* host_photons, uint32_t* host_collisions, void* stream)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_download: null technique");
+    CRV_ENTER(ppm->ctx);
+    CRV_REQUIRE(ppm->photons && ppm->collisions, "crv_ppm_download: no resources allocated");
+    cudaStream_t s = as_stream(stream);
+    if (host_photons) CRV_CUDA(cudaMemcpyAsync(host_photons, ppm->photons, ppm->cells * PPM_ELEMENTS_PER_CELL * sizeof(crv_photon), cudaMemcpyDeviceToHost, s));
+    if (host_collisions) CRV_CUDA(cudaMemcpyAsync(host_collisions, ppm->collisions, ppm->cells * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CRV_CUDA(cudaStreamSynchronize(s));
+    return CRV_OK;
+}
+
+int crv_ppm_last_trace_stats(crv_ppm* ppm, uint64_t* steps, uint64_t* deposits, uint64_t* dropped, float* ms)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_last_trace_stats: null technique");
+    CRV_ENTER(ppm->ctx);
+    CRV_REQUIRE(ppm->timed, "crv_ppm_last_trace_stats: no dispatch recorded yet");
+    CRV_CUDA(cudaEventSynchronize(ppm->ev1));
+    unsigned long long v[3];
+    CRV_CUDA(cudaMemcpy(v, ppm->stats, sizeof(v), cudaMemcpyDeviceToHost));
+    if (steps) *steps = v[0];
+    if (deposits) *deposits = v[1];
+    if (dropped) *dropped = v[2];
+    if (ms) CRV_CUDA(cudaEventElapsedTime(ms, ppm->ev0, ppm->ev1));
+    return CRV_OK;
+}
+
 int crv_pt_destroy(crv_pt* pt)
 {
     if (!pt) return CRV_OK;

@@ -2,6 +2,7 @@
 // setters of UniformBuffers.h (through include/crv/uniform_buffers.h), SetCloudProperties (main.cpp:144-163),
 // the MSVC rand() frame-seed sequence (main.cpp:722,949) and the Grid3D ".xyz" file format (Grid3D.h,
 // GridData.h).  Pure host code: compiled by g++ with -ffp-contract=off, no CUDA in this file.
+#include <cmath>
 #include <cstdio>
 #include <vector>
 #include <cstring>
@@ -50,6 +51,35 @@ void crv_orthonormal_basis(const float n[3], float right[3], float up[3])
     up[0] = u.x; up[1] = u.y; up[2] = u.z;
 }
 void crv_msvc_rand_sequence(uint32_t seed0, unsigned n, int32_t* out) { crv::MsvcRandSequence(seed0, n, out); }
+
+// ---- PhotonMapProperties (UniformBuffers.h:212-249) ----------------------------------------------------
+void crv_photon_map_init(crv_photon_map_properties* p)
+{
+    std::memset(p, 0, sizeof(*p));
+    const float inv = 1.0f / std::sqrt(1.0f * 1.0f + 1.0f * 1.0f);        // glm::normalize(vec4(1,-1,0,0)): v * inversesqrt(dot(v,v))
+    p->lightDirection[0] = 1.0f * inv; p->lightDirection[1] = -1.0f * inv;
+    for (int i = 0; i < 4; ++i) p->bounds[1][i] = 100.0f;
+    p->voxelCount[0] = p->voxelCount[1] = p->voxelCount[2] = 100;
+    p->voxelSize = (p->bounds[1][0] - p->bounds[0][0]) / (float)p->voxelCount[0];
+    p->photonSize = (uint32_t)sizeof(crv_photon);
+    p->stepSize = 10.0f;
+    p->absorption = 0.0f;
+}
+void crv_photon_map_set_bounds(crv_photon_map_properties* p, const float bounds[2][4])
+{
+    float size[4];
+    for (int i = 0; i < 4; ++i) { p->bounds[0][i] = bounds[0][i]; size[i] = bounds[1][i] - bounds[0][i]; }
+    int hi = 0;
+    float best = 1.175494351e-38f;                                         // FLT_MIN, like the reference's scan
+    for (int i = 0; i < 3; ++i)
+        if (best < std::fabs(size[i])) { hi = i; best = std::fabs(size[i]); }
+    for (int i = 0; i < 4; ++i) p->bounds[1][i] = p->bounds[0][i] + size[hi];
+    p->voxelSize = (p->bounds[1][0] - p->bounds[0][0]) / (float)p->voxelCount[0];
+}
+uint32_t crv_photon_map_total_size(const crv_photon_map_properties* p)
+{
+    return (uint32_t)(p->voxelCount[0] * p->voxelCount[1] * p->voxelCount[2]);
+}
 
 // ---- Grid3D .xyz -----------------------------------------------------------------------------------
 int crv_grid_load(const char* path, uint32_t counts[3], double voxel_size[3], float* data, size_t capacity)

@@ -111,3 +111,23 @@ int crv_launch_qtable_padded(crv_ctx* ctx, const float* absmax_wide, float* qpad
 int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);
 int crv_launch_log_selftest(crv_ctx* ctx, unsigned long long* d_mismatches, cudaStream_t s);
 int crv_launch_scale(crv_ctx* ctx, float* data, size_t n, float scale, cudaStream_t s);
+
+// ---- PPM photon tracer (PPM_PT.comp; RenderTechniquePPM's tracing pass) -------------------------------------------
+constexpr uint32_t PPM_ELEMENTS_PER_CELL = 32;      // PPM_PT.comp:26
+struct PPMConst {
+    PTConst base;                  // cloud bounds / extinction / phase parameters / cloud view / narrow q-table, as the path tracer builds them
+    // PhotonMapProperties (PPM_PT.comp:57-67)
+    float pm_light[3];
+    float pm_b0[3];
+    int pm_count[3];
+    float pm_voxel_size;
+    float pm_absorption;
+    int32_t seed;                  // pushConstants.seed
+    uint32_t n_photons;            // 64 * groups_x invocations (= emittedPhotons, :459)
+    crv_photon* photons;           // cells * 32 records
+    uint32_t* collisions;          // cells uvec4, .x = photons deposited in the cell
+    unsigned long long* stats;     // [0] tracking iterations, [1] deposits, [2] deposits dropped (cell already holds 32)
+    unsigned long long cells;
+};
+int crv_launch_ppm_clear(crv_ctx* ctx, crv_photon* photons, uint32_t* collisions, unsigned long long cells, cudaStream_t s);
+int crv_launch_ppm_trace(crv_ctx* ctx, const PPMConst& c, int cloud_layout, cudaStream_t s);

@@ -105,6 +105,25 @@ class ShadowVolumeProperties(capi.ShadowVolumePropertiesPOD):
         return tuple(self.lightDirection)
 
 
+class PhotonMapProperties(capi.PhotonMapPropertiesPOD):
+    """UniformBuffers.h:212-249: a cube of voxelCount^3 cells over the cloud's largest extent."""
+
+    def __init__(self):
+        super().__init__()
+        lib.crv_photon_map_init(C.byref(self))
+
+    def SetBounds(self, bounds):
+        """bounds: the CloudProperties.bounds array (2 x vec4), as main.cpp:162 passes it"""
+        b = ((C.c_float * 4) * 2)()
+        for i in range(2):
+            for j in range(4):
+                b[i][j] = float(bounds[i][j])
+        lib.crv_photon_map_set_bounds(C.byref(self), C.cast(b, C.c_void_p))
+
+    def GetTotalSize(self) -> int:
+        return int(lib.crv_photon_map_total_size(C.byref(self)))
+
+
 class PathTracerExtensions(capi.PTExtensionsPOD):
     """Not in the reference: absorption (1 - albedo); 0 keeps the reference's RNG stream untouched.
     math_mode: capi.PT_MATH_STRICT (default) or capi.PT_MATH_DRIVER (crv_c_api.h: crv_pt_math_mode)."""

@@ -22,7 +22,7 @@ import numpy as np
 
 from . import capi
 from .capi import check, lib
-from .structs import (CameraProperties, CloudProperties, Parameters, PathTracerExtensions, PushConstants,
+from .structs import (CameraProperties, CloudProperties, Parameters, PathTracerExtensions, PhotonMapProperties, PushConstants,
                       ShadowVolumeProperties)
 
 
@@ -389,6 +389,63 @@ class RenderTechniquePT(RenderTechnique):
     def close(self):
         if self.handle:
             lib.crv_pt_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class RenderTechniquePPM:
+    """RenderTechniquePPM (RenderTechniquePPM.h/.cpp), photon-tracing pass only: the dispatch of
+    shaders/PPM_PT.comp that fills the photon map; the estimate pass (PPM_PE.comp) is not built."""
+
+    def __init__(self, device: Context, photonMapProperties, pushConstants: PushConstants):
+        self.ctx = device
+        self.photonMapProperties = photonMapProperties       # borrowed, like the reference's pointer member
+        self.pushConstants = pushConstants
+        self.handle = C.c_void_p()
+        check(lib.crv_ppm_create(device.handle, C.byref(photonMapProperties), C.byref(pushConstants), C.byref(self.handle)))
+        self._keep = []
+
+    def AllocateResources(self):
+        check(lib.crv_ppm_allocate_resources(self.handle))
+
+    def FreeResources(self):
+        check(lib.crv_ppm_free_resources(self.handle))
+
+    def QueueUpdateCloudData(self, cloudProperties, imageIdx=0):
+        self._keep.append(cloudProperties)
+        check(lib.crv_ppm_queue_update_cloud_data(self.handle, C.byref(cloudProperties)))
+
+    def QueueUpdateCloudDataSampler(self, cloudImage: Volume, imageIdx=0):
+        self._keep.append(cloudImage)
+        check(lib.crv_ppm_queue_update_cloud_data_sampler(self.handle, cloudImage.handle))
+
+    def QueueUpdateParameters(self, parameters, imageIdx=0):
+        self._keep.append(parameters)
+        check(lib.crv_ppm_queue_update_parameters(self.handle, C.byref(parameters)))
+
+    def UpdateDescriptorSets(self):
+        check(lib.crv_ppm_update_descriptor_sets(self.handle))
+        self._keep = self._keep[-3:]
+
+    def RecordPhotonTracing(self, stream=0, groups_x: int = 0):
+        """the tracing half of RecordDrawCommands (RenderTechniquePPM.cpp:229-254); groups_x = 0 -> the reference's 200"""
+        check(lib.crv_ppm_record_photon_tracing(self.handle, _stream(stream), int(groups_x)))
+
+    def Download(self, stream=0):
+        """-> (photons as a (cells, 32, 12) float32 array, collisions as (cells, 4) uint32)"""
+        cells = self.photonMapProperties.GetTotalSize()
+        ph = np.empty((cells, 32, 12), dtype=np.float32)
+        co = np.empty((cells, 4), dtype=np.uint32)
+        check(lib.crv_ppm_download(self.handle, ph.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p), _stream(stream)))
+        return ph, co
+
+    def LastTraceStats(self):
+        a, b, c, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
+        check(lib.crv_ppm_last_trace_stats(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(ms)))
+        return {"tracking_steps": a.value, "deposits": b.value, "dropped": c.value, "ms": ms.value}
+
+    def close(self):
+        if self.handle:
+            lib.crv_ppm_destroy(self.handle)
             self.handle = C.c_void_p()
 
 

@@ -316,4 +316,41 @@ private:
     uint32_t m_setCount = 1;
 };
 
+// RenderTechniquePPM.h / .cpp, photon-tracing pass only: the dispatch of shaders/PPM_PT.comp that fills the
+// photon map.  The estimate pass (PPM_PE.comp) and its camera / result-image / shadow-volume bindings are not built, so this
+// class does not derive from RenderTechnique: it has no image to draw into.
+class RenderTechniquePPM {
+public:
+    RenderTechniquePPM(Device* device, const PhotonMapProperties* photonMapProperties, PushConstants* pushConstants)
+    {
+        Check(crv_ppm_create(device->Get(), photonMapProperties, pushConstants, &m_ppm));
+    }
+    ~RenderTechniquePPM() { crv_ppm_destroy(m_ppm); }
+    RenderTechniquePPM(const RenderTechniquePPM&) = delete;
+    RenderTechniquePPM& operator=(const RenderTechniquePPM&) = delete;
+
+    void AllocateResources() { Check(crv_ppm_allocate_resources(m_ppm)); }          // RenderTechniquePPM.cpp:127-160
+    void FreeResources() { Check(crv_ppm_free_resources(m_ppm)); }                  // :113-125
+    void QueueUpdateCloudData(DescriptorBufferInfo& info, unsigned int /*imageIdx*/)
+    {
+        Check(crv_ppm_queue_update_cloud_data(m_ppm, static_cast<const crv_cloud_properties*>(info.buffer)));
+    }
+    void QueueUpdateCloudDataSampler(DescriptorImageInfo& info, unsigned int /*imageIdx*/)
+    {
+        Check(crv_ppm_queue_update_cloud_data_sampler(m_ppm, info.image ? info.image->Get() : nullptr));
+    }
+    void QueueUpdateParameters(DescriptorBufferInfo& info, unsigned int /*imageIdx*/)
+    {
+        Check(crv_ppm_queue_update_parameters(m_ppm, static_cast<const crv_parameters*>(info.buffer)));
+    }
+    void UpdateDescriptorSets() { Check(crv_ppm_update_descriptor_sets(m_ppm)); }
+    // the tracing half of RecordDrawCommands (:229-254); groupsX = 0 is the reference's vkCmdDispatch(200, 1, 1)
+    void RecordPhotonTracing(CommandStream commandBuffer, uint32_t groupsX = 0) { Check(crv_ppm_record_photon_tracing(m_ppm, commandBuffer, groupsX)); }
+    void Download(crv_photon* photons, uint32_t* collisions, CommandStream stream = nullptr) { Check(crv_ppm_download(m_ppm, photons, collisions, stream)); }
+    crv_ppm* Get() const { return m_ppm; }
+
+private:
+    crv_ppm* m_ppm = nullptr;
+};
+
 }  // namespace crv

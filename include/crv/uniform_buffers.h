@@ -340,6 +340,19 @@ static_assert(offsetof(crv_shadow_volume_properties, voxelAxisCount) == 144 &&
                   offsetof(crv_shadow_volume_properties, voxelSize) == 148,
               "ShadowVolumeProperties offsets");
 
+// UniformBuffers.h:203-210
+struct Photon : crv_photon {};
+static_assert(sizeof(Photon) == 48, "Photon must match the std430 record of PPM_PT.comp:14-21");
+
+// UniformBuffers.h:212-249.  The setters are implemented once, behind the C ABI (host_helpers.cpp), and pinned against
+// the reference's own struct by tests/test_ppm.py.
+struct PhotonMapProperties : crv_photon_map_properties {
+    PhotonMapProperties() { crv_photon_map_init(this); }
+    void SetBounds(const float bounds[2][4]) { crv_photon_map_set_bounds(this, bounds); }
+    uint32_t GetTotalSize() const { return crv_photon_map_total_size(this); }
+};
+static_assert(sizeof(PhotonMapProperties) == 76, "PhotonMapProperties must match the std140 block of PPM_PT.comp:57-67");
+
 // Extension block (not in the reference): see crv_c_api.h
 struct PathTracerExtensions : crv_pt_extensions {
     PathTracerExtensions()

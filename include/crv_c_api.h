@@ -95,6 +95,27 @@ typedef struct crv_shadow_volume_properties {
     float    voxelSize;
 } crv_shadow_volume_properties;
 
+/* Photon of the PPM technique (UniformBuffers.h:203-210, PPM_PT.comp:14-21): 48 bytes in the std430 storage buffer. */
+typedef struct crv_photon {
+    float position[4];
+    float power[4];
+    float phi;
+    float theta;
+    float _padding[2];
+} crv_photon;
+
+/* PhotonMapProperties (UniformBuffers.h:212-249; std140 block of PPM_PT.comp:57-67): 76 bytes.  The grid of cells covers a
+ * cube: bounds[1] = bounds[0] + the cloud's largest extent (SetBounds), voxelSize = that extent / voxelCount.x. */
+typedef struct crv_photon_map_properties {
+    float    lightDirection[4];   /* normalize((1,-1,0,0)) by default; main.cpp:225 keeps it equal to the sun direction */
+    float    bounds[2][4];
+    int32_t  voxelCount[3];       /* 100^3 */
+    float    voxelSize;
+    uint32_t photonSize;          /* sizeof(Photon) = 48 */
+    float    stepSize;            /* 10; used by the estimate pass only */
+    float    absorption;          /* 0 */
+} crv_photon_map_properties;
+
 /* Extension block (NOT in the reference).  The reference path tracer has no absorption and no
  * bounce cap (PathTracer.comp:396-416).  absorption > 0 adds one RNG draw per real collision,
  * after the direct-light add and before scatterRay, and ends the path when xi <= absorption
@@ -160,6 +181,7 @@ typedef struct crv_volume crv_volume;   /* R32_SFLOAT 3D image + sampler (cloud 
 typedef struct crv_image  crv_image;    /* R32G32B32A32_SFLOAT 2D storage image (result)       */
 typedef struct crv_sv     crv_sv;       /* RenderTechniqueSV                                   */
 typedef struct crv_pt     crv_pt;       /* RenderTechniquePT                                   */
+typedef struct crv_ppm    crv_ppm;      /* RenderTechniquePPM, photon-tracing pass             */
 
 /* per-render statistics, filled by crv_pt_get_stats (all counts are exact u64 sums) */
 typedef struct crv_pt_stats {
@@ -290,6 +312,33 @@ int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_
  *   0 = pool  (default) every warp owns 128 paths in shared memory and runs one kind of work at a time on 32 of them
  *   1 = lanes every lane owns one path plus one in reserve (kept for A/B measurements) */
 int  crv_pt_set_scheduler(crv_pt* pt, int scheduler);
+
+/* ---- RenderTechniquePPM, photon-tracing pass (RenderTechniquePPM.h / .cpp; shaders/PPM_PT.comp) -----------------
+ * Only the first of the technique's two dispatches is built: emit 64 * groups_x photons from the sun
+ * and the sky, delta-track them through the cloud with the path tracer's code, deposit one photon per scattering event
+ * after the first into a uniform grid of cells (32 slots each, an atomic counter per cell).  The estimate pass
+ * (PPM_PE.comp) is not built.  Bindings: 0 photon map, 1 PhotonMapProperties, 2 cloud sampler, 3 CloudProperties,
+ * 4 Parameters, 5 collision map (RenderTechniquePPM.cpp:22-38). */
+int  crv_ppm_create(crv_ctx* ctx, const crv_photon_map_properties* props, const crv_push_constants* pc, crv_ppm** out);
+int  crv_ppm_destroy(crv_ppm* ppm);
+/* AllocateResources / FreeResources (RenderTechniquePPM.cpp:113-160): photon map = cells*32 photons, collision map =
+ * cells uvec4, sized from the PhotonMapProperties given at creation; both start zeroed */
+int  crv_ppm_allocate_resources(crv_ppm* ppm);
+int  crv_ppm_free_resources(crv_ppm* ppm);
+int  crv_ppm_queue_update_cloud_data(crv_ppm* ppm, const crv_cloud_properties* cloud);             /* binding 3 */
+int  crv_ppm_queue_update_cloud_data_sampler(crv_ppm* ppm, crv_volume* cloud_image);                /* binding 2 */
+int  crv_ppm_queue_update_parameters(crv_ppm* ppm, const crv_parameters* params);                   /* binding 4 */
+int  crv_ppm_update_descriptor_sets(crv_ppm* ppm);      /* also snapshots the PhotonMapProperties (binding 1, SetData) */
+/* The tracing half of RecordDrawCommands (RenderTechniquePPM.cpp:229-254): clear both buffers, push the constants
+ * (seed is read now), dispatch groups_x x 1 x 1 groups of 64 photons; groups_x = 0 means the reference's 200. */
+int  crv_ppm_record_photon_tracing(crv_ppm* ppm, void* stream, uint32_t groups_x);
+/* photons: cells*32 records, collisions: cells*4 u32 (x = deposits in the cell; may exceed 32); either may be NULL */
+int  crv_ppm_download(crv_ppm* ppm, crv_photon* host_photons, uint32_t* host_collisions, void* stream);
+/* tracking iterations / deposits / deposits dropped because their cell was full, of the last dispatch; device ms */
+int  crv_ppm_last_trace_stats(crv_ppm* ppm, uint64_t* steps, uint64_t* deposits, uint64_t* dropped, float* ms);
+void crv_photon_map_init(crv_photon_map_properties* p);                                             /* :212-222 */
+void crv_photon_map_set_bounds(crv_photon_map_properties* p, const float bounds[2][4]);             /* :225-243 */
+uint32_t crv_photon_map_total_size(const crv_photon_map_properties* p);                             /* :245-248 */
 
 /* ---- host-side helpers with the reference's setter semantics (UniformBuffers.h) ------------ */
 void crv_push_constants_init(crv_push_constants* p);                                   /* :6-13   */

@@ -334,6 +334,167 @@ bool findScatterPoint(const float* vol, const Cloud& cp, Rng& rng, Ray& ray, Cou
     return true;
 }
 
+// ==========================================================================================================
+// PPM photon tracer: shaders/PPM_PT.comp.  Helper bodies shared with PathTracer.comp are reused
+// (rand_xorshift / generateRandomNumber / intersectCloud / invertCDF / sampleCloud are byte-identical there); what
+// differs is restated here with its PPM_PT.comp lines: scatterRay ends in normalize() (:296), the delta-tracking exit
+// test is `t > dist` (:414), and the path deposits photons instead of gathering sun light.
+// ==========================================================================================================
+struct PhotonMapProps {   // PPM_PT.comp:57-67 (std140 offsets 0 / 16,32 / 48 / 60 / 64 / 68 / 72)
+    vec4 lightDirection; vec4 bounds[2]; int32_t voxelCount[3]; float voxelSize; uint32_t photonSize; float stepSize, absorption;
+};
+PhotonMapProps load_photon_map_props(const void* p)
+{
+    PhotonMapProps q;
+    q.lightDirection = rd4(p, 0); q.bounds[0] = rd4(p, 16); q.bounds[1] = rd4(p, 32);
+    for (int i = 0; i < 3; ++i) q.voxelCount[i] = rd<int32_t>(p, 48 + 4 * i);
+    q.voxelSize = rd<float>(p, 60); q.photonSize = rd<uint32_t>(p, 64); q.stepSize = rd<float>(p, 68); q.absorption = rd<float>(p, 72);
+    return q;
+}
+struct Photon { float position[4], power[4], phi, theta, padding[2]; };     // PPM_PT.comp:14-21, 48 bytes (std430)
+const uint32_t ELEMENTS_PER_CELL = 32;                                       // :26
+
+inline vec3 normalize3(vec3 v) { const float l = std::sqrt(dot(v, v)); return {v.x / l, v.y / l, v.z / l}; }
+inline float clampf(float x, float lo, float hi) { const float a = x < lo ? lo : x; return hi < a ? hi : a; }   // min(max(x, lo), hi)
+
+float SphericalTheta(vec3 v) { return std::acos(clampf(v.z, -1.0f, 1.0f)); }                 // :180-182
+float SphericalPhi(vec3 v)                                                                   // :184-187
+{
+    const float p = std::atan2(v.y, v.x) * 2.0f;
+    return (p < 0.0f) ? (p + 2.0f * PI) : p;
+}
+vec3 dirFromPolar(float theta, float phi)                                                    // :189-195
+{
+    return {std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)};
+}
+
+// :262-297: PathTracer.comp's scatterRay followed by normalize(sampleDirection)
+void scatterRayPPM(const Params& p, Rng& rng, vec3 incoming, vec3& out)
+{
+    scatterRay(p, rng, incoming, out);
+    out = normalize3(out);
+}
+
+struct PhotonSink {
+    Photon* photons;
+    uint32_t* collisions;     // uvec4 per cell, .x is the counter
+    vec4 currentColor;
+};
+
+// :303-321
+void depositPhoton(const PhotonMapProps& pm, PhotonSink& sink, vec3 pos, vec3 dir)
+{
+    const vec3 normPos = {(pos.x - pm.bounds[0].x) / pm.voxelSize, (pos.y - pm.bounds[0].y) / pm.voxelSize, (pos.z - pm.bounds[0].z) / pm.voxelSize};
+    const int32_t ix = (int32_t)normPos.x, iy = (int32_t)normPos.y, iz = (int32_t)normPos.z;      // ivec3(float): truncation
+    const int32_t idx = ix + (iy + iz * pm.voxelCount[1]) * pm.voxelCount[0];
+    Photon ph;
+    ph.position[0] = pos.x; ph.position[1] = pos.y; ph.position[2] = pos.z; ph.position[3] = 0.0f;
+    ph.power[0] = sink.currentColor.x; ph.power[1] = sink.currentColor.y; ph.power[2] = sink.currentColor.z; ph.power[3] = sink.currentColor.w;
+    ph.theta = SphericalTheta(dir);
+    ph.phi = SphericalPhi(dir);
+    ph.padding[0] = ph.padding[1] = 0.0f;
+    uint32_t offset;
+#pragma omp atomic capture
+    { offset = sink.collisions[4 * (size_t)idx]; sink.collisions[4 * (size_t)idx] += 1u; }
+    if (offset < ELEMENTS_PER_CELL) sink.photons[(size_t)idx * ELEMENTS_PER_CELL + offset] = ph;
+}
+
+// :324-361 (the commented-out face selection is dead; pdf = 1 / projected area, a point drawn in the box moved to tmin)
+void generateSunRay(const Cloud& cp, const PhotonMapProps& pm, Rng& rng, Ray& ray, float& pdf)
+{
+    const vec4 bd = cp.bounds[1] - cp.bounds[0];
+    const vec3 L = {pm.lightDirection.x, pm.lightDirection.y, pm.lightDirection.z};
+    const vec3 areas = {(bd.z * bd.y) * std::fabs(L.x), (bd.x * bd.z) * std::fabs(L.y), (bd.y * bd.x) * std::fabs(L.z)};   // zxy * yzx * abs(L)
+    const float totalArea = (areas.x * 1.0f + areas.y * 1.0f) + areas.z * 1.0f;                 // dot(areas, vec3(1))
+    pdf = 1.0f / totalArea;
+    ray.dir = L;
+    const float r0 = rng.generateRandomNumber(), r1 = rng.generateRandomNumber(), r2 = rng.generateRandomNumber();   // left to right
+    ray.pos = vec3{cp.bounds[0].x, cp.bounds[0].y, cp.bounds[0].z} + vec3{bd.x * r0, bd.y * r1, bd.z * r2};
+    float tmax = 0, tmin = 0;
+    intersectCloud(cp, ray, tmax, tmin);
+    ray.pos = ray.pos + ray.dir * tmin;
+}
+
+// :363-387
+void generateAmbientRay(const Cloud& cp, Rng& rng, Ray& ray, float& pdf)
+{
+    const float theta = (2.0f * PI) * rng.generateRandomNumber();                               // 2 * PI * rnd: int*float first
+    const float phi = std::acos(1.0f - 2.0f * rng.generateRandomNumber());
+    ray.dir = normalize3(dirFromPolar(theta, phi));
+    const vec4 bd4 = cp.bounds[1] - cp.bounds[0];
+    const vec3 bd = {bd4.x, bd4.y, bd4.z};
+    const vec3 areas = {(bd.z * bd.y) * std::fabs(ray.dir.x), (bd.x * bd.z) * std::fabs(ray.dir.y), (bd.y * bd.x) * std::fabs(ray.dir.z)};
+    const float totalArea = (areas.x * 1.0f + areas.y * 1.0f) + areas.z * 1.0f;
+    const float r0 = rng.generateRandomNumber(), r1 = rng.generateRandomNumber(), r2 = rng.generateRandomNumber();
+    const vec3 q = vec3{cp.bounds[0].x, cp.bounds[0].y, cp.bounds[0].z} + vec3{bd.x * r0, bd.y * r1, bd.z * r2};
+    ray.pos = {q.x + 0.1f, q.y + 0.1f, q.z + 0.1f};
+    pdf = INV_4Pi / totalArea;
+    float tmax = 0, tmin = 0;
+    intersectCloud(cp, ray, tmax, tmin);
+    ray.pos = ray.pos + ray.dir * tmin;
+}
+
+// :395-446; returns true to keep scattering.  `steps` counts delta-tracking iterations (log calls), like the path tracer's.
+bool interactWithMedium(const float* vol, const Cloud& cp, const PhotonMapProps& pm, Rng& rng, PhotonSink& sink, Ray& ray,
+                        bool& firstScatter, uint64_t& steps)
+{
+    float tmax = 0, tmin = 0;
+    if (!intersectCloud(cp, ray, tmax, tmin)) return false;
+    const vec3 exitPoint = ray.pos + ray.dir * tmax;
+    const float dist = length(ray.pos - exitPoint);
+    float t = 0;
+    vec3 currentPoint{0, 0, 0};
+    const float sigma = (cp.maxExtinction * cp.densityScaling) / cp.baseScaling;
+    do {
+        const float zeta = rng.generateRandomNumber();
+        ++steps;
+        t += (-std::log(zeta)) / sigma;
+        if (t > dist) return false;                        // :414 -- strictly greater, unlike PathTracer.comp:339
+        if (!(t == t)) return false;                       // a NaN would spin forever in the shader
+        currentPoint = ray.pos + t * ray.dir;
+        const float extinction = sampleCloud(vol, cp, currentPoint);
+        const float xi = rng.generateRandomNumber();
+        if (xi < extinction / cp.maxExtinction) break;
+    } while (true);
+    ray.pos = currentPoint;
+    if (firstScatter) firstScatter = false;                // :434-441: the first scattering event deposits nothing
+    else depositPhoton(pm, sink, currentPoint, ray.dir);
+    const float xi = rng.generateRandomNumber();
+    return xi > pm.absorption;                             // :445-446
+}
+
+// :451-488, one invocation
+void tracePhoton(const float* vol, const Cloud& cp, const Params& par, const PhotonMapProps& pm, int32_t seed, uint32_t gid_x,
+                 uint32_t emittedPhotons, Photon* photons, uint32_t* collisions, uint64_t& steps)
+{
+    if (cp.densityScaling <= 0.0f) return;
+    Rng rng;
+    rng.initializeRandom((uint32_t)seed * gid_x);          // gid.y = 0 in the (groups,1,1) dispatch
+    PhotonSink sink{photons, collisions, {0, 0, 0, 0}};
+    bool firstScatter = true;
+    Ray ray{{0, 0, 0}, {0, 0, 0}};
+    float pdf = 0;
+    const float prob = 0.5f;
+    if (rng.generateRandomNumber() < prob) {
+        generateSunRay(cp, pm, rng, ray, pdf);
+        const float s = (1.0f * par.lightIntensity) / (pdf * (float)emittedPhotons);    // SUNLIGHT_COLOR * I / (pdf * N)
+        sink.currentColor = {s / prob, s / prob, s / prob, s / prob};
+    } else {
+        generateAmbientRay(cp, rng, ray, pdf);
+        const vec4 bg = sampleBackground(-ray.dir);
+        const float d = pdf * (float)emittedPhotons;
+        const vec4 c = {(bg.x / d) * 0.5f, (bg.y / d) * 0.5f, (bg.z / d) * 0.5f, (bg.w / d) * 0.5f};
+        const float q = 1.0f - prob;
+        sink.currentColor = {c.x / q, c.y / q, c.z / q, c.w / q};
+    }
+    sink.currentColor = sink.currentColor * 0.5f;
+    vec3 newDir{0, 0, 0};
+    while (interactWithMedium(vol, cp, pm, rng, sink, ray, firstScatter, steps)) {
+        scatterRayPPM(par, rng, ray.dir, newDir);
+        ray.dir = newDir;
+    }
+}
+
 // :366-425 without the final accumulate; returns `result`
 vec4 tracePixel(const float* vol, const float* sv, const Camera& cam, const Cloud& cp, const Params& par,
                 const Shadow& sp, int32_t seed, float absorption, uint32_t gx, uint32_t gy, uint32_t ngx, Counters& cnt)
@@ -531,6 +692,21 @@ float orc_invert_cdf(const void* params28, float xi) { return invertCDF(load_par
 float orc_sample_phase(const void* params28, const float in[3], const float s[3])
 {
     return samplePhase(load_params(params28), vec3{in[0], in[1], in[2]}, vec3{s[0], s[1], s[2]});
+}
+uint64_t orc_ppm_trace(const float* cloud, const void* cloud60, const void* params28, const void* pmprops76, int32_t seed,
+                       uint32_t groups_x, void* photons, uint32_t* collisions, uint64_t cells, int num_threads)
+{
+    const Cloud cp = load_cloud(cloud60);
+    const Params par = load_params(params28);
+    const PhotonMapProps pm = load_photon_map_props(pmprops76);
+    std::memset(photons, 0, cells * ELEMENTS_PER_CELL * sizeof(Photon));       // RenderTechniquePPM.cpp:236-237
+    std::memset(collisions, 0, cells * 4 * sizeof(uint32_t));
+    const int total = (int)(groups_x * 64u);
+    uint64_t steps = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps) num_threads(num_threads > 0 ? num_threads : omp_get_max_threads())
+    for (int i = 0; i < total; ++i)
+        tracePhoton(cloud, cp, par, pm, seed, (uint32_t)i, (uint32_t)total, static_cast<Photon*>(photons), collisions, steps);
+    return steps;
 }
 void orc_blit_srgb8(const float* rgba, size_t npix, unsigned char* bgra8)
 {

@@ -51,6 +51,8 @@ template <class T> struct tvec3 {
     T& operator[](int i) { return (&x)[i]; }
     const T& operator[](int i) const { return (&x)[i]; }
     tvec2<T> xy() const { return tvec2<T>(x, y); }
+    tvec3 zxy() const { return tvec3(z, x, y); }
+    tvec3 yzx() const { return tvec3(y, z, x); }
 
     friend tvec3 operator+(const tvec3& a, const tvec3& b) { return tvec3(a.x + b.x, a.y + b.y, a.z + b.z); }
     friend tvec3 operator-(const tvec3& a, const tvec3& b) { return tvec3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -79,6 +81,8 @@ template <class T> struct tvec4 {
     T& operator[](int i) { return (&x)[i]; }
     const T& operator[](int i) const { return (&x)[i]; }
     tvec3<T> xyz() const { return tvec3<T>(x, y, z); }
+    tvec3<T> zxy() const { return tvec3<T>(z, x, y); }
+    tvec3<T> yzx() const { return tvec3<T>(y, z, x); }
     tvec2<T> xy() const { return tvec2<T>(x, y); }
 
     friend tvec4 operator+(const tvec4& a, const tvec4& b) { return tvec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -156,6 +160,15 @@ inline float dot(const vec4& a, const vec4& b) { return a.x * b.x + a.y * b.y + 
 inline float length(const vec3& a) { return std::sqrt(dot(a, a)); }
 inline float distance(const vec3& a, const vec3& b) { return length(a - b); }
 inline vec3 normalize(const vec3& a) { return a / std::sqrt(dot(a, a)); }
+inline vec3 abs(const vec3& a) { return vec3(std::fabs(a.x), std::fabs(a.y), std::fabs(a.z)); }
+// storage-buffer atomics (PPM_PT.comp:316): the CPU dispatch runs invocations on several threads
+inline uint atomicAdd(uint& mem, uint v)
+{
+    uint old;
+#pragma omp atomic capture
+    { old = mem; mem += v; }
+    return old;
+}
 inline vec4 exp(const vec4& a) { return vec4(std::exp(a.x), std::exp(a.y), std::exp(a.z), std::exp(a.w)); }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -12,10 +12,13 @@ touches what is GLSL *syntax* rather than C++:
   #version / local_size layout      -> dropped / `static const uvec3 gl_WorkGroupSize(x, y, z);`
   layout(...) uniform Block {..} n; -> `struct Block_block {..}; static Block_block n;`   (bool -> bool32: 4 bytes in std140)
   layout(...) uniform sampler3D n;  -> `static sampler3D n;`   (likewise image2D / image3D, `writeonly` dropped)
+  layout(...) buffer B { T n[]; };  -> `static T* n;`   (storage buffers of PPM_PT.comp: one unsized array each)
   in / out / inout parameters       -> by value / by reference
   lowp / mediump / highp            -> dropped (evaluated as fp32, as crv_oracle.h states)
   1.5  2.0  3.14159265359  1e-3     -> suffixed with `f` (an unsuffixed GLSL literal is a 32-bit float, a C++ one a double)
   v.xyz / v.xy                      -> v.xyz() / v.xy()   (read swizzles; the shaders write no swizzles)
+  vec3(f(), g(), h())               -> vec3{f(), g(), h()} when more than one argument draws a random number: GLSL evaluates
+                                       constructor arguments left to right, C++ only does so inside braces
   mutable globals (uint rng_state)  -> `static thread_local` (private per invocation in GLSL)
   void main()                       -> void shader_main()
 
@@ -37,6 +40,25 @@ def suffix_float_literals(src: str) -> str:
     # decimal floating literals without a suffix: 1.0  1.  .5  3.402823466e+38  1e5
     pat = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
     return pat.sub(lambda m: m.group(1) + "f", src)
+
+
+def order_constructor_arguments(src: str, log) -> str:
+    """vecN( ... ) whose argument list calls generateRandomNumber() more than once -> vecN{ ... } (sequenced left to right)"""
+    out, i = [], 0
+    for m in re.finditer(r"\b(vec[234])\s*\(", src):
+        if m.start() < i:
+            continue
+        depth, j = 1, m.end()
+        while depth and j < len(src):
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        args = src[m.end():j - 1]
+        if args.count("generateRandomNumber()") > 1 and not re.search(r"\bvec[234]\s*\(", args):
+            log(f"ordered constructor: {m.group(1)}{{{args.strip()[:60]}...}}")
+            out.append(src[i:m.start()] + m.group(1) + "{" + args + "}")
+            i = j
+    out.append(src[i:])
+    return "".join(out)
 
 
 def rewrite(src: str, log) -> str:
@@ -67,6 +89,13 @@ def rewrite(src: str, log) -> str:
         return f"static {typ} {name};"
 
     src = re.sub(r"layout\s*\(([^)]*)\)\s*uniform\s+(?:writeonly\s+|readonly\s+)?(sampler3D|image2D|image3D)\s+(\w+)\s*;", opaque, src)
+    # storage buffers: one unsized array per block, no instance name
+    def ssbo(mm):
+        quals, name, typ, arr = mm.group(1), mm.group(2), mm.group(3), mm.group(4)
+        log(f"buffer {name}: {typ} {arr}[] layout({quals.strip()})")
+        return f"static {typ}* {arr};"
+
+    src = re.sub(r"layout\s*\(([^)]*)\)\s*(?:restrict\s+|readonly\s+|writeonly\s+|coherent\s+)*buffer\s+(\w+)\s*\{\s*(\w+)\s+(\w+)\s*\[\s*\]\s*;\s*\}\s*;", ssbo, src)
     if re.search(r"\blayout\s*\(", src):
         raise SystemExit("unhandled layout qualifier left in the source")
 
@@ -77,8 +106,9 @@ def rewrite(src: str, log) -> str:
     src = re.sub(r"\b(?:lowp|mediump|highp)\s+", "", src)
     # literals, swizzles, entry point
     src = suffix_float_literals(src)
-    src = re.sub(r"\.(xyz|xy)\b(?!\s*\()", r".\1()", src)
+    src = re.sub(r"\.(xyz|xy|zxy|yzx)\b(?!\s*\()", r".\1()", src)
     src = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", src)
+    src = order_constructor_arguments(src, log)
 
     # mutable globals -> thread_local (brace depth 0 only)
     out, depth = [], 0

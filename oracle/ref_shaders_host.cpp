@@ -23,6 +23,9 @@ namespace pt {
 namespace sv {
 #include "_ref/ShadowVolume.comp.inc"
 }
+namespace ppm {
+#include "_ref/PPM_PT.comp.inc"
+}
 }  // namespace glsl
 
 namespace {
@@ -120,5 +123,37 @@ void refsh_shadow_volume(const float* cloud, int nx, int ny, int nz, const void*
 }
 
 int refsh_max_threads(void) { return omp_get_max_threads(); }
+
+
+// One photon-tracing dispatch of PPM_PT.comp (RenderTechniquePPM.cpp:233-253: both buffers zero-filled, then
+// vkCmdDispatch(groups_x, 1, 1) of 64x1x1 invocations; the reference uses groups_x = 200).  photons = cells*32 records of
+// 48 bytes, collisions = cells uvec4; bindings 0-5 as RenderTechniquePPM.cpp:22-38 declares them.
+uint32_t refsh_ppm_block_size(void) { return (uint32_t)sizeof(glsl::ppm::PhotonMapProperties_block); }
+uint32_t refsh_ppm_photon_size(void) { return (uint32_t)sizeof(glsl::ppm::Photon); }
+
+void refsh_ppm_trace(const float* cloud, int nx, int ny, int nz, const void* cloud60, const void* params28, const void* pmprops76,
+                     const void* push24, uint32_t groups_x, void* photons, uint32_t* collisions, uint64_t cells, int num_threads)
+{
+    namespace P = glsl::ppm;
+    bind_block(P::cloudProperties, cloud60, 60, sizeof(P::CloudProperties_block));
+    bind_block(P::parameters, params28, 28, sizeof(P::Parameters_block));
+    bind_block(P::photonMapProperties, pmprops76, 76, sizeof(P::PhotonMapProperties_block));
+    std::memset(&P::pushConstants, 0, sizeof(P::pushConstants));
+    std::memcpy(&P::pushConstants, push24, 24 < sizeof(P::pushConstants) ? 24 : sizeof(P::pushConstants));
+    P::cloudSampler.texels = cloud;
+    P::cloudSampler.nx = nx; P::cloudSampler.ny = ny; P::cloudSampler.nz = nz;
+    P::cloudSampler.slot = 0;
+    P::photons = static_cast<P::Photon*>(photons);
+    P::collisions = reinterpret_cast<glsl::uvec4*>(collisions);
+    std::memset(photons, 0, cells * 32 * sizeof(P::Photon));            // vkCmdFillBuffer(..., 0)
+    std::memset(collisions, 0, cells * sizeof(glsl::uvec4));
+    const int total = (int)(groups_x * 64u);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(resolve_threads(num_threads))
+    for (int i = 0; i < total; ++i) {
+        glsl::invocation().global_id = glsl::uvec3((uint32_t)i, 0u, 0u);
+        glsl::invocation().num_groups = glsl::uvec3(groups_x, 1u, 1u);
+        P::shader_main();
+    }
+}
 
 }  // extern "C"

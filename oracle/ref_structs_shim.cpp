@@ -141,4 +141,20 @@ int ref_grid_save(const char* path, unsigned nx, unsigned ny, unsigned nz, doubl
     return 0;
 }
 
+// PhotonMapProperties / Photon (UniformBuffers.h:203-249) for the PPM photon tracer:
+// which = 0: sizeof(PhotonMapProperties), 1: sizeof(Photon)
+int ref_ppm_sizeof(int which) { return which == 0 ? (int)sizeof(PhotonMapProperties) : (int)sizeof(Photon); }
+// default-constructed block, then (optionally) SetBounds(cloud bounds) -- out receives sizeof(PhotonMapProperties) bytes
+void ref_photon_map_properties(const float cloud_bounds[8], int set_bounds, void* out, unsigned* total_size)
+{
+    PhotonMapProperties p;
+    if (set_bounds) {
+        glm::vec4 b[2] = {glm::vec4(cloud_bounds[0], cloud_bounds[1], cloud_bounds[2], cloud_bounds[3]),
+                          glm::vec4(cloud_bounds[4], cloud_bounds[5], cloud_bounds[6], cloud_bounds[7])};
+        p.SetBounds(b);
+    }
+    std::memcpy(out, &p, sizeof(p));
+    if (total_size) *total_size = p.GetTotalSize();
+}
+
 }  // extern "C"

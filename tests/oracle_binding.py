@@ -44,6 +44,8 @@ lib.orc_sample_phase.restype = _f
 lib.orc_sample_phase.argtypes = [_vp, _fp, _fp]
 lib.orc_background.argtypes = [_fp, _fp]
 lib.orc_blit_srgb8.argtypes = [_vp, C.c_size_t, _vp]
+lib.orc_ppm_trace.restype = C.c_uint64
+lib.orc_ppm_trace.argtypes = [_vp, _vp, _vp, _vp, _i32, _u32, _vp, _vp, C.c_uint64, C.c_int]
 lib.orc_texture3d.restype = _f
 lib.orc_texture3d.argtypes = [_vp, _u32, _u32, _u32, _fp]
 lib.orc_sample_cloud.restype = _f
@@ -124,6 +126,31 @@ def background(direction):
     out = (C.c_float * 4)()
     lib.orc_background(_f3(direction), out)
     return np.array(out[:], np.float32)
+
+
+def ppm_trace(cloud, cloud_props, params, pm_props, seed, groups_x=200, threads=0):
+    """one photon-tracing dispatch of PPM_PT.comp (restatement) -> (photons (cells,32,12) f32, collisions (cells,4) u32, steps)"""
+    cells = int(np.prod(np.frombuffer(bytes(pm_props), np.int32, 3, 48)))
+    ph = np.empty((cells, 32, 12), np.float32)
+    co = np.empty((cells, 4), np.uint32)
+    steps = lib.orc_ppm_trace(_ptr(np.ascontiguousarray(cloud, np.float32)), _raw(cloud_props), _raw(params), _raw(pm_props), int(seed),
+                              int(groups_x), _ptr(ph), _ptr(co), cells, threads)
+    return ph, co, int(steps)
+
+
+def refsh_ppm_trace(cloud, cloud_props, params, pm_props, seed, groups_x=200, threads=0):
+    """the same dispatch through the reference's own PPM_PT.comp compiled by g++ (oracle/_ref)"""
+    rl = ref_shaders_lib()
+    cells = int(np.prod(np.frombuffer(bytes(pm_props), np.int32, 3, 48)))
+    nx, ny, nz = _cloud_dims(cloud_props)
+    ph = np.empty((cells, 32, 12), np.float32)
+    co = np.empty((cells, 4), np.uint32)
+    rl.refsh_ppm_trace.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _u32, _vp, _vp, C.c_uint64, C.c_int]
+    rl.refsh_ppm_block_size.restype = _u32
+    rl.refsh_ppm_photon_size.restype = _u32
+    rl.refsh_ppm_trace(_ptr(np.ascontiguousarray(cloud, np.float32)), nx, ny, nz, _raw(cloud_props), _raw(params), _raw(pm_props),
+                       push_constants_bytes(seed, 0), int(groups_x), _ptr(ph), _ptr(co), cells, threads)
+    return ph, co
 
 
 def blit_srgb8(rgba):

@@ -141,6 +141,44 @@ def run_c5(ctx, frames):
     return out
 
 
+def run_ppm(ctx, groups_list=(200, 2000, 20000)):
+    """the photon-tracing dispatch of RenderTechniquePPM on the c2 scene (512^3 cloud, default 100^3 photon map,
+    densityScaling 200 -- the reference default): the reference's 200 groups of 64 photons, and larger dispatches."""
+    n = 512
+    vol = crv.Volume(ctx, n, n, n, layout="brick")
+    vol.fbm_generate(1234)
+    cp = crv.CloudProperties()
+    cp.SetFromGrid((n, n, n), (1.0 / n,) * 3, vol.majorant())
+    par = crv.Parameters()
+    par.SetPhaseG(0.85)
+    pm = crv.PhotonMapProperties()
+    pm.SetBounds(cp.bounds)
+    pc = crv.PushConstants()
+    pc.seed = 38
+    ppm = crv.RenderTechniquePPM(ctx, pm, pc)
+    ppm.AllocateResources()
+    ppm.QueueUpdateCloudData(cp)
+    ppm.QueueUpdateCloudDataSampler(vol)
+    ppm.QueueUpdateParameters(par)
+    ppm.UpdateDescriptorSets()
+    rows = []
+    for g in groups_list:
+        ms = []
+        for i in range(4):
+            ppm.RecordPhotonTracing(0, g)
+            st = ppm.LastTraceStats()
+            if i:
+                ms.append(st["ms"])
+        rows.append({"groups_x": g, "photons": 64 * g, "ms_median": float(np.median(ms)), "mphotons_per_s": 64 * g / float(np.median(ms)) / 1e3,
+                     "tracking_steps": st["tracking_steps"], "deposits": st["deposits"], "dropped_cell_full": st["dropped"]})
+    ppm.close()
+    vol.close()
+    return {"config": "ppm_photon_tracing", "n_cloud": n, "photon_map_cells": pm.GetTotalSize(), "density_scaling": cp.densityScaling,
+            "g": 0.85, "dispatches": rows,
+            "note": "includes the per-dispatch clear of the previously touched cells (the reference zero-fills 1.5 GB + 16 MB) and the "
+                    "q-table refresh; one thread per photon like PPM_PT.comp, latency of the longest photon path dominates small dispatches"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c1_iso,c1_hg,c4,c3,c5")
@@ -153,7 +191,9 @@ def main():
     torch.cuda.set_device(0)
     ctx = crv.Context(0)
     for name in args.configs.split(","):
-        if name == "c5":
+        if name == "ppm":
+            out = run_ppm(ctx)
+        elif name == "c5":
             out = run_c5(ctx, args.c5_frames)
         elif name == "c3":
             out = run_plain(ctx, "c3", spp=args.c3_spp)
