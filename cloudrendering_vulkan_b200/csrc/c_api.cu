@@ -305,8 +305,17 @@ int crv_volume_upload(crv_volume* v, const float* data, int is_device, void* str
     cudaStream_t s = as_stream(stream);
     const size_t n = (size_t)v->nx * v->ny * v->nz;
     const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    // scratch of the fused table pass (volume.cu): 3 window-maxima arrays of nbx * ny * nz floats, stream-ordered
+    const size_t scratch_bytes = 3 * (size_t)v->nbx * v->ny * v->nz * sizeof(float);
+    bool tables_done = false;
     if (v->layout == CRV_LAYOUT_LINEAR) {
         CRV_CUDA(cudaMemcpyAsync(v->data, data, n * sizeof(float), kind, s));
+        float* scratch = nullptr;
+        CRV_CUDA(cudaMallocAsync(&scratch, scratch_bytes, s));
+        const int rc = crv_launch_retile_tables(v->ctx, v->data, v, false, scratch, s);
+        CRV_CUDA(cudaFreeAsync(scratch, s));
+        if (rc != CRV_OK) return rc;
+        tables_done = true;
     } else if (v->layout == CRV_LAYOUT_TEX3D) {
         cudaMemcpy3DParms p{};
         p.srcPtr = make_cudaPitchedPtr(const_cast<float*>(data), v->nx * sizeof(float), v->nx, v->ny);
@@ -315,18 +324,23 @@ int crv_volume_upload(crv_volume* v, const float* data, int is_device, void* str
         p.kind = kind;
         CRV_CUDA(cudaMemcpy3DAsync(&p, s));
     } else {
+        float* scratch = nullptr;
+        CRV_CUDA(cudaMallocAsync(&scratch, scratch_bytes, s));
+        int rc;
         if (is_device) {
-            CRV_TRY(crv_launch_retile(v->ctx, data, v, s));
+            rc = crv_launch_retile_tables(v->ctx, data, v, true, scratch, s);
         } else {
             float* tmp = nullptr;
             CRV_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
             CRV_CUDA(cudaMemcpyAsync(tmp, data, n * sizeof(float), cudaMemcpyHostToDevice, s));
-            const int rc = crv_launch_retile(v->ctx, tmp, v, s);
+            rc = crv_launch_retile_tables(v->ctx, tmp, v, true, scratch, s);
             CRV_CUDA(cudaFreeAsync(tmp, s));
-            if (rc != CRV_OK) return rc;
         }
+        CRV_CUDA(cudaFreeAsync(scratch, s));
+        if (rc != CRV_OK) return rc;
+        tables_done = true;
     }
-    v->brick_max_valid = false;
+    v->brick_max_valid = tables_done;
     v->majorant_valid = false;
     vol_touch(v);
     return CRV_OK;

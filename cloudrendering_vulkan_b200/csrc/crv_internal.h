@@ -249,6 +249,7 @@ struct crv_image {
 
 // kernels / helpers implemented across the .cu files --------------------------------------------------
 int crv_launch_retile(crv_ctx* ctx, const float* linear_src, crv_volume* dst, cudaStream_t s);     // volume.cu
+int crv_launch_retile_tables(crv_ctx* ctx, const float* linear_src, crv_volume* dst, bool store, float* scratch, cudaStream_t s);  // volume.cu
 int crv_launch_untile(crv_ctx* ctx, const crv_volume* src, float* linear_dst, cudaStream_t s);     // volume.cu
 int crv_launch_brick_max(crv_ctx* ctx, crv_volume* vol, cudaStream_t s);                           // volume.cu
 int crv_launch_majorant(crv_ctx* ctx, crv_volume* vol, cudaStream_t s);                            // volume.cu

@@ -102,6 +102,85 @@ __global__ void brick_absmax_wide_kernel(VolView v, float* __restrict__ out_abs)
     if (lane == 0) out_abs[brick] = ma;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// The same three tables from the LINEAR x-fastest source at upload time, as a separable max filter fused with the layout
+// conversion: the dilated voxel sets are products of intervals ([8b, 8b+8] and [8b-1, 8b+9] per axis, clamped), so
+//   pass X (retile_tables_kernel, the pass that reads every voxel anyway): per (brick column bx, y, z) the three window
+//           maxima along x -> three arrays of nbx * ny * nz
+//   pass YZ (tables_yz_kernel): per brick the maxima of those over its y and z windows.
+// max is exact and order-independent: the tables hold the same floats as brick_max_kernel / brick_absmax_wide_kernel
+// (1.4 ms of strided gathers at 512^3) produce.
+// ------------------------------------------------------------------------------------------------------
+template <int LAYOUT, bool STORE>
+__global__ void __launch_bounds__(256) retile_tables_kernel(const float* __restrict__ src, VolView dst, float* __restrict__ ax_abs,
+                                                            float* __restrict__ ax_max, float* __restrict__ ax_wide)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x;            // blockDim = (64, 4): two warps per row, 8-lane groups = brick rows
+    const int j = blockIdx.y * 4 + threadIdx.y;
+    const int k = blockIdx.z;
+    const bool row = j < dst.ny;
+    const size_t base = (size_t)dst.nx * ((size_t)(row ? j : 0) + (size_t)dst.ny * k);
+    const bool in = row && i < dst.nx;
+    const float val = in ? src[base + i] : 0.0f;
+    if (STORE && in) VolAcc<LAYOUT>::store(dst, i, j, k, val);
+    // out-of-range lanes contribute the identity of both statistics (the clamped sets only repeat edge voxels)
+    float a = fabsf(val), m = fmaxf(val, 0.0f);
+    const unsigned lane = threadIdx.x & 31u;
+    const float a_self = a, m_self = m;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    // neighbours of the 8-voxel group: x = g-1, g+8, g+9 (g = first voxel of the group); from the adjacent groups of
+    // the warp where they exist, otherwise straight from memory
+    const unsigned g0 = lane & ~7u;
+    const int gx = i & ~7;
+    float n1a = __shfl_sync(0xffffffffu, a_self, (g0 + 8u) & 31u), n1m = __shfl_sync(0xffffffffu, m_self, (g0 + 8u) & 31u);
+    float n2a = __shfl_sync(0xffffffffu, a_self, (g0 + 9u) & 31u);
+    float p1a = __shfl_sync(0xffffffffu, a_self, (g0 + 31u) & 31u);
+    if (g0 == 24u) {
+        const float v1 = (row && gx + 8 < dst.nx) ? src[base + gx + 8] : 0.0f;
+        const float v2 = (row && gx + 9 < dst.nx) ? src[base + gx + 9] : 0.0f;
+        n1a = fabsf(v1); n1m = fmaxf(v1, 0.0f); n2a = fabsf(v2);
+    }
+    if (g0 == 0u) p1a = (row && gx >= 1 && gx - 1 < dst.nx) ? fabsf(src[base + gx - 1]) : 0.0f;
+    if ((lane & 7u) == 0u && row && gx < dst.nx) {
+        const size_t o = (size_t)(gx >> 3) + (size_t)dst.nbx * ((size_t)j + (size_t)dst.ny * k);
+        const float na = fmaxf(a, n1a);
+        ax_abs[o] = na;
+        ax_max[o] = fmaxf(m, n1m);
+        ax_wide[o] = fmaxf(fmaxf(na, n2a), p1a);
+    }
+}
+
+// one thread per brick, lanes along bx (coalesced rows of the pass-X arrays)
+__global__ void __launch_bounds__(128) tables_yz_kernel(const float* __restrict__ ax_abs, const float* __restrict__ ax_max,
+                                                        const float* __restrict__ ax_wide, int nbx, int nby, int nbz, int ny, int nz,
+                                                        float* __restrict__ out_abs, float* __restrict__ out_max, float* __restrict__ out_wide)
+{
+    const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y, bz = blockIdx.z;
+    if (bx >= nbx) return;
+    float na = 0.0f, nm = 0.0f, wa = 0.0f;
+    for (int dz = -1; dz <= 9; ++dz) {
+        const int k = min(max(bz * 8 + dz, 0), nz - 1);
+        for (int dy = -1; dy <= 9; ++dy) {
+            const int j = min(max(by * 8 + dy, 0), ny - 1);
+            const size_t o = (size_t)bx + (size_t)nbx * ((size_t)j + (size_t)ny * k);
+            wa = fmaxf(wa, ax_wide[o]);
+            if (dz >= 0 && dz <= 8 && dy >= 0 && dy <= 8) {
+                na = fmaxf(na, ax_abs[o]);
+                nm = fmaxf(nm, ax_max[o]);
+            }
+        }
+    }
+    const size_t b = (size_t)bx + (size_t)nbx * ((size_t)by + (size_t)nby * bz);
+    out_abs[b] = na;
+    out_max[b] = nm;
+    out_wide[b] = wa;
+}
+
 // majorant = max over the brick-max grid (each voxel belongs to at least one brick's set)
 __global__ void majorant_kernel(const float* __restrict__ brick_max, long long n, float* __restrict__ out)
 {
@@ -129,6 +208,32 @@ int crv_launch_retile(crv_ctx* ctx, const float* linear_src, crv_volume* dst, cu
         retile_kernel<CRV_LAYOUT_LINEAR><<<grid, block, 0, s>>>(linear_src, v);
     ctx->launches++;
     CRV_CUDA(cudaGetLastError());
+    return CRV_OK;
+}
+
+// Upload path: layout conversion (when `store`) + all three brick tables in two passes over a linear x-fastest source.
+// `scratch` holds the pass-X arrays: 3 * nbx * ny * nz floats.
+int crv_launch_retile_tables(crv_ctx* ctx, const float* linear_src, crv_volume* dst, bool store, float* scratch, cudaStream_t s)
+{
+    const long long nbricks = (long long)dst->nbx * dst->nby * dst->nbz;
+    if (!dst->brick_max) CRV_CUDA(cudaMalloc(&dst->brick_max, sizeof(float) * nbricks));
+    if (!dst->brick_absmax) CRV_CUDA(cudaMalloc(&dst->brick_absmax, sizeof(float) * nbricks));
+    if (!dst->brick_absmax_wide) CRV_CUDA(cudaMalloc(&dst->brick_absmax_wide, sizeof(float) * nbricks));
+    const size_t na = (size_t)dst->nbx * dst->ny * dst->nz;
+    float *ax_abs = scratch, *ax_max = scratch + na, *ax_wide = scratch + 2 * na;
+    const dim3 block(64, 4, 1);
+    const dim3 grid((dst->nx + 63) / 64, (dst->ny + 3) / 4, dst->nz);
+    const VolView v = dst->view();
+    if (!store) retile_tables_kernel<CRV_LAYOUT_LINEAR, false><<<grid, block, 0, s>>>(linear_src, v, ax_abs, ax_max, ax_wide);
+    else if (dst->layout == CRV_LAYOUT_BRICK) retile_tables_kernel<CRV_LAYOUT_BRICK, true><<<grid, block, 0, s>>>(linear_src, v, ax_abs, ax_max, ax_wide);
+    else if (dst->layout == CRV_LAYOUT_TEX3D) retile_tables_kernel<CRV_LAYOUT_TEX3D, true><<<grid, block, 0, s>>>(linear_src, v, ax_abs, ax_max, ax_wide);
+    else retile_tables_kernel<CRV_LAYOUT_LINEAR, true><<<grid, block, 0, s>>>(linear_src, v, ax_abs, ax_max, ax_wide);
+    const dim3 grid2((dst->nbx + 127) / 128, dst->nby, dst->nbz);
+    tables_yz_kernel<<<grid2, 128, 0, s>>>(ax_abs, ax_max, ax_wide, (int)dst->nbx, (int)dst->nby, (int)dst->nbz, (int)dst->ny, (int)dst->nz,
+                                            dst->brick_absmax, dst->brick_max, dst->brick_absmax_wide);
+    ctx->launches += 2;
+    CRV_CUDA(cudaGetLastError());
+    dst->brick_max_valid = true;
     return CRV_OK;
 }
 
