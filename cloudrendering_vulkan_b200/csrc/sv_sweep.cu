@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(512, 4) sv_fused_kernel(const __grid_constant_
     __shared__ int s_lo, s_hi;
     __shared__ int s_search[6][64];
     __shared__ int s_zin[64], s_zend[64];
-    __shared__ float s_add[8][64];      // the chunk's addends, then the running sums after each slice
+    __shared__ float s_add[16][64];     // two chunks' addends, then the running sums after each slice
     __shared__ float s_acc[64];         // running sum of every column after the previous chunk
     const int N = c.n;
     const int t = threadIdx.x;
@@ -510,42 +510,48 @@ __global__ void __launch_bounds__(512, 4) sv_fused_kernel(const __grid_constant_
         if (inb) cur.store(c.out, z0, 1.0f);
         cur.advance();
     }
-    // ---- while some column is inside its interval: gather, serial sums, exp ----
-    for (; z0 < hi; z0 += 8) {
-        const int z = z0 + lz;
-        float add = 0.0f;                         // + 0 outside the interval leaves the sum unchanged (it is never -0)
-        if (z >= z_in && z < z_end) {
-            bool empty = false;
-            if (pre) {
-                const float fz = (float)z;
-                // floor by a round-down add of 2^23; inside the AABB the coordinate is >= -1/16 - 1/32, so only -1 needs a clamp
-                const int bi = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[0], pa[0]), 8388608.0f)) - 0x4B000000, 0);
-                const int bj = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[1], pa[1]), 8388608.0f)) - 0x4B000000, 0);
-                const int bk = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[2], pa[2]), 8388608.0f)) - 0x4B000000, 0);
-                const unsigned b = ((unsigned)min(bk, c.cloud.nbz - 1) * c.cloud.nby + (unsigned)min(bj, c.cloud.nby - 1)) * c.cloud.nbx +
-                                   (unsigned)min(bi, c.cloud.nbx - 1);
-                empty = __ldg(c.brick_absmax_wide + b) == 0.0f;
-            }
-            if (!empty) add = div_rn_by(column_sample<CL, true>(c, a, z) * c.density_scaling, c.base_scaling, c.rbase);
+    // ---- while some column is inside its interval: gather, serial sums, exp -- two chunks (16 slices) per barrier pair ----
+    auto addend = [&](int z) -> float {
+        if (!(z >= z_in && z < z_end)) return 0.0f;       // + 0 outside the interval leaves the sum unchanged (it is never -0)
+        if (pre) {
+            const float fz = (float)z;
+            // floor by a round-down add of 2^23; inside the AABB the coordinate is >= -1/16 - 1/32, so only -1 needs a clamp
+            const int bi = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[0], pa[0]), 8388608.0f)) - 0x4B000000, 0);
+            const int bj = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[1], pa[1]), 8388608.0f)) - 0x4B000000, 0);
+            const int bk = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[2], pa[2]), 8388608.0f)) - 0x4B000000, 0);
+            const unsigned b = ((unsigned)min(bk, c.cloud.nbz - 1) * c.cloud.nby + (unsigned)min(bj, c.cloud.nby - 1)) * c.cloud.nbx +
+                               (unsigned)min(bi, c.cloud.nbx - 1);
+            if (__ldg(c.brick_absmax_wide + b) == 0.0f) return 0.0f;
         }
-        s_add[lz][col] = add;
+        return div_rn_by(column_sample<CL, true>(c, a, z) * c.density_scaling, c.base_scaling, c.rbase);
+    };
+    // ((-dist)*0)/(z+1) = +-0 and expf(+-0) = 1 exactly, the value the shader stores while a column has met no
+    // density: a warp (4x8 columns of one slice) none of whose columns has any skips the divide + exp altogether
+    auto transmittance = [&](int z, float acc) -> float {
+        float tr = 1.0f;
+        if (__any_sync(0xffffffffu, acc != 0.0f) && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
+        return tr;
+    };
+    for (; z0 < hi; z0 += 16) {
+        const int za = z0 + lz, zb = z0 + 8 + lz;
+        s_add[lz][col] = addend(za);
+        s_add[8 + lz][col] = addend(zb);
         __syncthreads();
         if (t < 64) {
             float s = s_acc[t];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 s = s + s_add[u][t];              // accumulatedValue after slice z0 + u, the shader's order (:89)
                 s_add[u][t] = s;
             }
             s_acc[t] = s;
         }
         __syncthreads();
-        const float acc = s_add[lz][col];
-        // ((-dist)*0)/(z+1) = +-0 and expf(+-0) = 1 exactly, the value the shader stores while a column has met no
-        // density: a warp (4x8 columns of one slice) none of whose columns has any skips the divide + exp altogether
-        float tr = 1.0f;
-        if (__any_sync(0xffffffffu, acc != 0.0f) && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
-        if (inb && z < N) cur.store(c.out, z0, tr);
+        const float tra = transmittance(za, s_add[lz][col]);
+        const float trb = transmittance(zb, s_add[8 + lz][col]);
+        if (inb && za < N) cur.store(c.out, z0, tra);
+        cur.advance();
+        if (inb && zb < N) cur.store(c.out, z0 + 8, trb);
         cur.advance();
     }
     // ---- every column has left the AABB: the sums are final ----
