@@ -802,6 +802,43 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
     return CRV_OK;
 }
 
+// Coarse threshold table (pt_wavefront.h: PTConst::qcoarse): cell size and padded byte count for a cloud volume, and the
+// approximate-cell-coordinate constants of the tracker's pre-test for the geometry in c (cb0 / cb1 / cext / cloud set).
+static void coarse_table_shape(const crv_volume* cv, int& shift, uint32_t& bytes)
+{
+    size_t cells = 0;
+    for (shift = 0;; ++shift) {
+        const size_t ncx = ((cv->nbx - 1) >> shift) + 1, ncy = ((cv->nby - 1) >> shift) + 1, ncz = ((cv->nbz - 1) >> shift) + 1;
+        cells = (ncx + 2) * (ncy + 2) * (ncz + 2);
+        if (cells + 1 <= (size_t)crv_pt_pool_smem_budget()) break;
+    }
+    bytes = (uint32_t)((cells + 1 + 15) / 16 * 16);
+}
+
+static void coarse_pretest_geometry(PTConst& c, int shift)
+{
+    c.use_wide = 1;
+    for (int i = 0; i < 3; ++i) {
+        const double n = i == 0 ? c.cloud.nx : i == 1 ? c.cloud.ny : c.cloud.nz;
+        const double sc = n / (double)c.cext[i], of = -(double)c.cb0[i] * sc - 0.5;
+        const double cell = 8.0 * (double)(1 << shift);
+        c.ascc[i] = (float)(sc / cell);
+        c.aofc[i] = (float)(of / cell + 1.0);
+        const double span = std::fabs((double)c.cb0[i]) + std::fabs((double)c.cb1[i]);
+        if (!(span * std::fabs(sc) * 8.0 * 1.1920929e-07 < 0.25) || !(n < 2097152.0)) c.use_wide = 0;
+    }
+    c.cnx = (((uint32_t)c.cloud.nbx - 1u) >> shift) + 3u;
+    const uint32_t cny = (((uint32_t)c.cloud.nby - 1u) >> shift) + 3u, cnz = (((uint32_t)c.cloud.nbz - 1u) >> shift) + 3u;
+    c.cnxy = c.cnx * cny;
+    c.cbias = 0x4B000000u * (1u + c.cnx + c.cnxy);
+    c.cmax = c.cnxy * cnz - 1u;
+    if (!c.use_wide) {          // scale 0 and a bias that selects the never-reject byte behind the table
+        for (int i = 0; i < 3; ++i) c.ascc[i] = c.aofc[i] = 0.0f;
+        c.cmax += 1u;
+        c.cbias -= c.cmax;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // RenderTechniquePPM, photon-tracing pass
 // ---------------------------------------------------------------------------------------------------
@@ -824,6 +861,9 @@ struct crv_ppm {
     unsigned long long cells = 0;
     float* qtable = nullptr;
     size_t qtable_elems = 0;
+    uint8_t* qcoarse = nullptr;               // shared-memory threshold table, like the path tracer's
+    uint32_t qcoarse_bytes = 0;
+    int qcoarse_shift = 0;
     unsigned long long* stats = nullptr;      // 3 u64
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -870,6 +910,7 @@ int crv_ppm_destroy(crv_ppm* ppm)
     if (ppm->photons) cudaFree(ppm->photons);
     if (ppm->collisions) cudaFree(ppm->collisions);
     if (ppm->qtable) cudaFree(ppm->qtable);
+    if (ppm->qcoarse) cudaFree(ppm->qcoarse);
     if (ppm->stats) cudaFree(ppm->stats);
     if (ppm->ev0) cudaEventDestroy(ppm->ev0);
     if (ppm->ev1) cudaEventDestroy(ppm->ev1);
@@ -979,8 +1020,17 @@ int crv_ppm_record_photon_tracing(crv_ppm* ppm, void* stream, uint32_t groups_x)
         ppm->qtable = nullptr;
         ppm->qtable_elems = 0;
         CRV_CUDA(cudaMalloc(&ppm->qtable, nbricks * sizeof(float)));
+        if (ppm->qcoarse) CRV_CUDA(cudaFree(ppm->qcoarse));
+        ppm->qcoarse = nullptr;
+        coarse_table_shape(cv, ppm->qcoarse_shift, ppm->qcoarse_bytes);
+        CRV_CUDA(cudaMalloc(&ppm->qcoarse, ppm->qcoarse_bytes));
         ppm->qtable_elems = nbricks;
     }
+    CRV_CUDA(cudaMemsetAsync(ppm->qcoarse, 128, ppm->qcoarse_bytes, s));
+    CRV_TRY(crv_launch_qcoarse(ppm->ctx, cv->brick_absmax_wide, ppm->qcoarse, (int)cv->nbx, (int)cv->nby, (int)cv->nbz, ppm->qcoarse_shift, c.max_ext, s));
+    c.qcoarse = ppm->qcoarse;
+    c.qcoarse_bytes = ppm->qcoarse_bytes;
+    coarse_pretest_geometry(c, ppm->qcoarse_shift);
     CRV_TRY(crv_launch_qtable(ppm->ctx, cv->brick_absmax, ppm->qtable, (long long)nbricks, c.max_ext, s));   // 1 MB: rebuilt every dispatch
     c.qtable = ppm->qtable;
     k.pm_voxel_size = pr.voxelSize;
