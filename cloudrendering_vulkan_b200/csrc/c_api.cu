@@ -1289,15 +1289,7 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             CRV_CUDA(cudaMalloc(&pt->qtable, nbricks * sizeof(float)));
             CRV_CUDA(cudaMalloc(&pt->qtable_wide, ((size_t)(cv->nbx + 2) * (cv->nby + 2) * (cv->nbz + 2) + 1) * sizeof(float)));   // + the +inf entry
             // coarse table: the smallest cell size whose padded table fits the pool scheduler's shared-memory budget
-            int shift = 0;
-            size_t cells = 0;
-            for (;; ++shift) {
-                const size_t ncx = ((cv->nbx - 1) >> shift) + 1, ncy = ((cv->nby - 1) >> shift) + 1, ncz = ((cv->nbz - 1) >> shift) + 1;
-                cells = (ncx + 2) * (ncy + 2) * (ncz + 2);
-                if (cells + 1 <= (size_t)crv_pt_pool_smem_budget()) break;
-            }
-            pt->qcoarse_shift = shift;
-            pt->qcoarse_bytes = (uint32_t)((cells + 1 + 15) / 16 * 16);
+            coarse_table_shape(cv, pt->qcoarse_shift, pt->qcoarse_bytes);
             CRV_CUDA(cudaMalloc(&pt->qcoarse, pt->qcoarse_bytes));
             pt->qtable_elems = nbricks;
         }
@@ -1330,41 +1322,25 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
         // approximate brick pre-test: v = q*asc8 + aof8 ~ ((((q - cb0)/cext)*size - 0.5) / 8) + 1, the padded brick
         // coordinate, evaluated with FMAs.  Its error is a few ulps of the largest term, |cb0/cext|*size (in texels);
         // the wide table tolerates 1 texel, we allow 1/4.
-        c.use_wide = 1;
         for (int i = 0; i < 3; ++i) {
             c.rcext[i] = 1.0f / c.cext[i];
             c.rsden[i] = 1.0f / c.sden[i];
             const double n = i == 0 ? c.cloud.nx : i == 1 ? c.cloud.ny : c.cloud.nz;
             const double sc = n / (double)c.cext[i], of = -(double)c.cb0[i] * sc - 0.5;
-            c.asc8[i] = (float)(sc / 8.0);
+            c.asc8[i] = (float)(sc / 8.0);             // lane-owned scheduler: the same coordinate at brick granularity
             c.aof8[i] = (float)(of / 8.0 + 1.0);
-            const double cell = 8.0 * (double)(1 << pt->qcoarse_shift);
-            c.ascc[i] = (float)(sc / cell);
-            c.aofc[i] = (float)(of / cell + 1.0);
-            const double span = std::fabs((double)c.cb0[i]) + std::fabs((double)c.cb1[i]);
-            if (!(span * std::fabs(sc) * 8.0 * 1.1920929e-07 < 0.25) || !(n < 2097152.0)) c.use_wide = 0;
         }
+        coarse_pretest_geometry(c, pt->qcoarse_shift);  // pool scheduler: cell coordinate, strides, bias; decides c.use_wide
         c.pnbx = (uint32_t)c.cloud.nbx + 2u;
         c.pnbxy = c.pnbx * ((uint32_t)c.cloud.nby + 2u);
         c.pbias = 0x4B000000u * (1u + c.pnbx + c.pnbxy);          // mod 2^32, like the device-side sum it cancels
         c.pmax = c.pnbxy * ((uint32_t)c.cloud.nbz + 2u) - 1u;
-        {
-            const int sh = pt->qcoarse_shift;
-            c.cnx = (((uint32_t)c.cloud.nbx - 1u) >> sh) + 3u;
-            const uint32_t cny = (((uint32_t)c.cloud.nby - 1u) >> sh) + 3u, cnz = (((uint32_t)c.cloud.nbz - 1u) >> sh) + 3u;
-            c.cnxy = c.cnx * cny;
-            c.cbias = 0x4B000000u * (1u + c.cnx + c.cnxy);
-            c.cmax = c.cnxy * cnz - 1u;
-        }
         if (!c.use_wide) {
             // every approximate coordinate collapses to 0 and the bias moves the index to the +inf entry behind the
             // table: the pre-test never rejects and every tentative collision goes through the exact sampler
             for (int i = 0; i < 3; ++i) c.asc8[i] = c.aof8[i] = 0.0f;
             c.pmax += 1u;
             c.pbias -= c.pmax;
-            for (int i = 0; i < 3; ++i) c.ascc[i] = c.aofc[i] = 0.0f;
-            c.cmax += 1u;
-            c.cbias -= c.cmax;
         }
     }
 
