@@ -336,13 +336,18 @@ def run_ours(args, wl):
     peak, peak_src = _peak()
     alg_bytes_rank = (32.0 * (st.tracking_steps + st.collisions) + 32.0 * st.paths) / args.steps
     achieved = alg_bytes_rank / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pt_wavefront_kernel_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("pt_wavefront_kernel_bytes_per_launch")
+        if "warp_inst_per_cycle_per_sm" in tj:      # the limiter that actually binds: issue slots (from the same ncu pass)
+            issue = {"warp_inst_per_cycle_per_sm": tj["warp_inst_per_cycle_per_sm"], "peak": 4.0,
+                     "frac": tj["warp_inst_per_cycle_per_sm"] / 4.0, "issue_active_pct": tj.get("issue_active_pct"),
+                     "active_lanes_per_warp_inst": tj.get("active_lanes_per_warp_inst"), "source": "profiles/traffic.json (ncu, not live)"}
     except Exception:
         pass
     roofline = {"kernel": "pt_wavefront_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "issue": issue, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_rank / max(1, k_n), "launches_per_step": k_n,
                 "kernel_ms_per_step": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "steps_per_path": tot_steps / tot_paths, "collisions_per_path": tot_coll / tot_paths,

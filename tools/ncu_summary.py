@@ -168,7 +168,7 @@ def traffic(path):
     hdr = rows[hi]
     ni, vi, ui, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Kernel Name")
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot, kernel, dur = 0.0, "?", None
+    tot, kernel, dur, extra = 0.0, "?", None, {}
     for r in rows[hi + 1:]:
         if len(r) <= vi:
             continue
@@ -177,7 +177,13 @@ def traffic(path):
             tot += float(r[vi].replace(",", "")) * mult[r[ui]]
         elif r[ni].startswith("gpu__time_duration"):
             dur = r[vi] + " " + r[ui]
-    print(json.dumps({"pt_wavefront_kernel_bytes_per_launch": tot, "kernel": kernel, "launch_duration_under_ncu": dur,
+        elif r[ni] == "sm__inst_executed.avg.per_cycle_elapsed":
+            extra["warp_inst_per_cycle_per_sm"] = float(r[vi].replace(",", ""))      # of 4 issue slots per cycle
+        elif r[ni] == "smsp__thread_inst_executed_per_inst_executed.ratio":
+            extra["active_lanes_per_warp_inst"] = float(r[vi].replace(",", ""))      # of 32
+        elif r[ni] == "smsp__issue_active.avg.pct_of_peak_sustained_active":
+            extra["issue_active_pct"] = float(r[vi].replace(",", ""))
+    print(json.dumps({"pt_wavefront_kernel_bytes_per_launch": tot, **extra, "kernel": kernel, "launch_duration_under_ncu": dur,
                       "source": path, "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one 128-frame "
                                              "launch of the default bench.py step"}))
 
