@@ -1432,7 +1432,9 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
     const size_t frame_bytes = (size_t)c.npix * sizeof(float2);
     uint64_t per_round = pt->sample_budget / frame_bytes;
     if (per_round < 1) per_round = 1;
-    const uint64_t max_jobs_frames = 0xffffffffull / c.npix;       // job ids are 32-bit
+    // job ids are 32-bit, and every warp may bump the job counter once more after the queue ran dry (<= 32 per warp, a few
+    // thousand warps): keep a margin so that the counter cannot wrap back into the valid range
+    const uint64_t max_jobs_frames = (0xffffffffull - (1ull << 22)) / c.npix;
     if (per_round > max_jobs_frames) per_round = max_jobs_frames;
     if (per_round > (uint64_t)PT_MAX_FRAMES_PER_LAUNCH) per_round = PT_MAX_FRAMES_PER_LAUNCH;   // seeds travel by value
     if (per_round > n) per_round = n;
