@@ -1435,6 +1435,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
     // job ids are 32-bit, and every warp may bump the job counter once more after the queue ran dry (<= 32 per warp, a few
     // thousand warps): keep a margin so that the counter cannot wrap back into the valid range
     const uint64_t max_jobs_frames = (0xffffffffull - (1ull << 22)) / c.npix;
+    CRV_REQUIRE(max_jobs_frames >= 1, "RenderTechniquePT: more than 2^32 - 2^22 pixels per frame is not supported");
     if (per_round > max_jobs_frames) per_round = max_jobs_frames;
     if (per_round > (uint64_t)PT_MAX_FRAMES_PER_LAUNCH) per_round = PT_MAX_FRAMES_PER_LAUNCH;   // seeds travel by value
     if (per_round > n) per_round = n;
