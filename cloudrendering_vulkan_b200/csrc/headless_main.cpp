@@ -31,7 +31,7 @@ struct Options {
     unsigned spp = 16, nsv = 500;
     float g = 0.85f, absorption = 0.0f, density_scaling = 50.0f, fov = 90.0f;
     float light[3] = {1.0f, -1.0f, 0.0f};
-    bool isotropic = false, per_frame = false;
+    bool isotropic = false, per_frame = false, warmup = false, math_driver = false;
 };
 
 bool parse(int argc, char** argv, Options& o)
@@ -58,6 +58,8 @@ bool parse(int argc, char** argv, Options& o)
         else if (a == "--device") o.device = std::atoi(next("--device"));
         else if (a == "--pfm") o.pfm = next("--pfm");
         else if (a == "--png") o.png = next("--png");
+        else if (a == "--warmup") o.warmup = true;
+        else if (a == "--math") { const std::string v = next("--math"); if (v != "strict" && v != "driver") return false; o.math_driver = v == "driver"; }
         else if (a == "--resume") o.resume = next("--resume");
         else if (a == "--checkpoint") o.checkpoint = next("--checkpoint");
         else return false;
@@ -128,7 +130,7 @@ int main(int argc, char** argv)
     if (!parse(argc, argv, o)) {
         std::fprintf(stderr, "usage: crv_headless [--xyz file | --fbm N] [--width W --height H] [--spp S] [--nsv N] [--g G | --isotropic]\n"
                              "                    [--absorption A] [--density-scaling D] [--light x,y,z] [--fov F] [--per-frame] [--device i] [--pfm out]\n"
-                             "                    [--png out.png] [--resume acc.ckpt] [--checkpoint acc.ckpt]\n");
+                             "                    [--png out.png] [--resume acc.ckpt] [--checkpoint acc.ckpt] [--warmup] [--math strict|driver]\n");
         return 2;
     }
     try {
@@ -161,6 +163,7 @@ int main(int argc, char** argv)
         app.pathTracingTechnique->UpdateDescriptorSets();
         crv::PathTracerExtensions ext;
         ext.absorption = o.absorption;
+        ext.math_mode = o.math_driver ? CRV_PT_MATH_DRIVER : CRV_PT_MATH_STRICT;
         app.pathTracingTechnique->SetExtensions(ext);
 
         // ---- LoadCloudFile (main.cpp:166-190) or the synthetic fBm scene, then SetCloudProperties (main.cpp:144-163) ----
@@ -196,18 +199,35 @@ int main(int argc, char** argv)
         std::vector<int32_t> all_seeds(first_frame + o.spp);
         crv::MsvcRandSequence(0, first_frame + o.spp, all_seeds.data());
         std::vector<int32_t> seeds(all_seeds.begin() + first_frame, all_seeds.end());
+        auto render = [&]() {
+            if (o.per_frame) {
+                for (unsigned f = 0; f < o.spp; ++f) {
+                    app.pushConstants.seed = seeds[f];
+                    app.pathTracingTechnique->RecordDrawCommands(nullptr, 0);
+                    app.pushConstants.frameCount++;
+                }
+            } else {
+                app.pathTracingTechnique->RenderBatch(seeds.data(), o.spp, first_frame, CRV_ACCUM_RUNNING_MEAN, nullptr, 0);
+                app.pushConstants.frameCount += o.spp;
+            }
+        };
+        if (o.warmup) {
+            // --warmup: the same render once untimed (first-use allocations, table builds), then the accumulation is put back
+            // where it was -- cleared, or the checkpoint reloaded -- so that the timed run produces the same image
+            render();
+            app.device->WaitIdle();
+            app.resultImage->Clear();
+            app.pushConstants.frameCount = 0;
+            if (!o.resume.empty()) {
+                int32_t last_seed = 0;
+                app.resultImage->LoadCheckpoint(o.resume.c_str(), &first_frame, &last_seed);
+                app.pushConstants.frameCount = first_frame;
+            }
+            app.pathTracingTechnique->ResetStats();
+        }
         app.device->WaitIdle();
         const auto t0 = std::chrono::steady_clock::now();
-        if (o.per_frame) {
-            for (unsigned f = 0; f < o.spp; ++f) {
-                app.pushConstants.seed = seeds[f];
-                app.pathTracingTechnique->RecordDrawCommands(nullptr, 0);
-                app.pushConstants.frameCount++;
-            }
-        } else {
-            app.pathTracingTechnique->RenderBatch(seeds.data(), o.spp, first_frame, CRV_ACCUM_RUNNING_MEAN, nullptr, 0);
-            app.pushConstants.frameCount += o.spp;
-        }
+        render();
         app.device->WaitIdle();
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
