@@ -100,6 +100,11 @@ struct crv_pt {
     float* start = nullptr;             // per hit pixel start state (7 floats, SoA)
     uint32_t* nhit = nullptr;
     size_t hitlist_elems = 0;
+    uint32_t* misslist = nullptr;      // pixels whose camera ray misses the box
+    float* missdy = nullptr;           // dir.y of those rays
+    // the classification depends on the camera and the cloud box only: kept across render calls while those bytes stand
+    bool geom_valid = false;
+    unsigned char geom_key[68 + 32 + 4] = {};
     // q-table cache
     float* qtable_wide = nullptr;
     float* qtable = nullptr;
@@ -795,7 +800,7 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
     pt->pc = pc;
     pt->sets.resize(1);
     CRV_CUDA(cudaMalloc(&pt->job_counter, sizeof(unsigned int)));
-    CRV_CUDA(cudaMalloc(&pt->nhit, sizeof(uint32_t)));
+    CRV_CUDA(cudaMalloc(&pt->nhit, 2 * sizeof(uint32_t)));      // [0] hits, [1] misses
     CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
     CRV_CUDA(cudaMemset(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT));
     *out = pt;
@@ -1089,6 +1094,8 @@ int crv_pt_destroy(crv_pt* pt)
     if (pt->hitlist) cudaFree(pt->hitlist);
     if (pt->start) cudaFree(pt->start);
     if (pt->nhit) cudaFree(pt->nhit);
+    if (pt->misslist) cudaFree(pt->misslist);
+    if (pt->missdy) cudaFree(pt->missdy);
     if (pt->samples) cudaFree(pt->samples);
     if (pt->job_counter) cudaFree(pt->job_counter);
     if (pt->stats) cudaFree(pt->stats);
@@ -1402,11 +1409,18 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
     if (pt->hitlist_elems != c.npix) {
         if (pt->hitlist) CRV_CUDA(cudaFree(pt->hitlist));
         if (pt->start) CRV_CUDA(cudaFree(pt->start));
+        if (pt->misslist) CRV_CUDA(cudaFree(pt->misslist));
+        if (pt->missdy) CRV_CUDA(cudaFree(pt->missdy));
         pt->hitlist = nullptr;
         pt->start = nullptr;
+        pt->misslist = nullptr;
+        pt->missdy = nullptr;
         pt->hitlist_elems = 0;
+        pt->geom_valid = false;
         CRV_CUDA(cudaMalloc(&pt->hitlist, sizeof(uint32_t) * c.npix));
         CRV_CUDA(cudaMalloc(&pt->start, sizeof(float) * 7 * (size_t)c.npix));
+        CRV_CUDA(cudaMalloc(&pt->misslist, sizeof(uint32_t) * c.npix));
+        CRV_CUDA(cudaMalloc(&pt->missdy, sizeof(float) * c.npix));
         pt->hitlist_elems = c.npix;
     }
     c.hitlist = pt->hitlist;
@@ -1421,12 +1435,26 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         CRV_CUDA(cudaMalloc(&pt->rcp_fc1, sizeof(float) * cap));
         pt->rcp_elems = cap;
     }
-    CRV_TRY(crv_launch_rcp_frames(pt->ctx, pt->rcp_fc1, first_fc, n, s));
-    pt->launches++;
-    c.rcp_fc1 = pt->rcp_fc1;
-    CRV_CUDA(cudaMemsetAsync(pt->nhit, 0, sizeof(uint32_t), s));
-    CRV_TRY(crv_launch_classify(pt->ctx, c, n, pt->hitlist, pt->start, pt->nhit, s));
-    pt->launches++;
+    if (n > 1) {                      // a single frame computes its one reciprocal in the fold kernel (same IEEE division)
+        CRV_TRY(crv_launch_rcp_frames(pt->ctx, pt->rcp_fc1, first_fc, n, s));
+        pt->launches++;
+    }
+    c.rcp_fc1 = n > 1 ? pt->rcp_fc1 : nullptr;
+    {
+        unsigned char key[sizeof(pt->geom_key)];
+        std::memcpy(key, &b.cam, 68);
+        std::memcpy(key + 68, b.cloud.bounds, 32);
+        const uint32_t off = b.cloud.densityScaling <= 0.0f ? 1u : 0u;
+        std::memcpy(key + 100, &off, 4);
+        if (!pt->geom_valid || std::memcmp(key, pt->geom_key, sizeof(key)) != 0) {
+            CRV_CUDA(cudaMemsetAsync(pt->nhit, 0, 2 * sizeof(uint32_t), s));
+            CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
+            CRV_TRY(crv_launch_classify(pt->ctx, c, pt->hitlist, pt->start, pt->nhit, pt->misslist, pt->missdy, s));
+            pt->launches++;
+            std::memcpy(pt->geom_key, key, sizeof(key));
+            pt->geom_valid = true;
+        }
+    }
 
     // rounds of `per_round` frames through the sample buffer (sized for the worst case: every pixel hits)
     const size_t frame_bytes = (size_t)c.npix * sizeof(float2);
@@ -1453,8 +1481,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         c.nframes = nf;
         std::memcpy(c.seeds, seeds + f0, sizeof(int32_t) * nf);
         c.first_frame_count = first_fc + f0;
-        CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
-        CRV_TRY(pt_timed_launch(pt, c, b, s));
+        CRV_TRY(pt_timed_launch(pt, c, b, s));        // the job counter is zero: reset by the previous fold (or by the classification)
         FoldConst fc{};
         fc.image = c.image;
         fc.samples = pt->samples;
@@ -1465,7 +1492,11 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         fc.nframes = nf;
         fc.first_frame_count = first_fc + f0;
         fc.accum_mode = mode;
-        fc.rcp_fc1 = pt->rcp_fc1 + f0;
+        fc.rcp_fc1 = c.rcp_fc1 ? pt->rcp_fc1 + f0 : nullptr;
+        fc.misslist = pt->misslist;
+        fc.missdy = pt->missdy;
+        fc.job_counter = pt->job_counter;
+        fc.stats = pt->stats;
         CRV_TRY(crv_launch_fold(pt->ctx, fc, s));
         pt->launches += 2;
     }

@@ -97,11 +97,16 @@ struct FoldConst {
     const uint32_t* nhit;
     uint32_t npix, nframes, first_frame_count, width;
     int accum_mode;
-    const float* rcp_fc1;              // RN(1 / float(first_frame_count + f + 1)), f = 0 .. nframes-1 of THIS launch
+    const float* rcp_fc1;              // RN(1 / float(first_frame_count + f + 1)), f = 0 .. nframes-1 of THIS launch; null: computed in place
+    const uint32_t* misslist;          // pixels whose camera ray misses the box (npix - *nhit entries): pixel index
+    const float* missdy;               // and dir.y of that ray
+    unsigned int* job_counter;         // reset for the next tracker launch
+    unsigned long long* stats;         // PT_STAT_PATHS += the miss pixels' paths (may be null)
 };
 
+
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
-int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t nframes_call, uint32_t* hitlist, float* start, uint32_t* nhit, cudaStream_t s);
+int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t* hitlist, float* start, uint32_t* counts, uint32_t* misslist, float* missdy, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_rcp_frames(crv_ctx* ctx, float* rcp, uint32_t first_frame_count, uint32_t n, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
