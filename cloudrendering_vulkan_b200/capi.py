@@ -155,7 +155,16 @@ SIGNATURES = {
     "crv_pt_rng_tap": (C.c_int, [_vp, _i32, _u32, _u32, _u32, _vp, _vp]),
     "crv_pt_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "crv_pt_set_scheduler": (C.c_int, [_vp, C.c_int]),
-    "crv_ppm_create": (C.c_int, [_vp, _P(PhotonMapPropertiesPOD), _P(PushConstantsPOD), _P(_vp)]),
+    "crv_ppm_create": (C.c_int, [_vp, _P(PhotonMapPropertiesPOD), _P(PushConstantsPOD), C.c_float, _P(_vp)]),
+    "crv_ppm_set_frame_references": (C.c_int, [_vp, _P(_vp), C.c_uint]),
+    "crv_ppm_queue_update_camera_properties": (C.c_int, [_vp, _P(CameraPropertiesPOD)]),
+    "crv_ppm_queue_update_shadow_volume": (C.c_int, [_vp, _P(ShadowVolumePropertiesPOD)]),
+    "crv_ppm_queue_update_shadow_volume_sampler": (C.c_int, [_vp, _vp]),
+    "crv_ppm_record_draw_commands": (C.c_int, [_vp, _vp, C.c_uint]),
+    "crv_ppm_update_radius": (C.c_int, [_vp, C.c_uint]),
+    "crv_ppm_record_photon_estimate": (C.c_int, [_vp, _vp, C.c_uint]),
+    "crv_ppm_upload": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "crv_ppm_last_estimate_stats": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_float)]),
     "crv_ppm_destroy": (C.c_int, [_vp]),
     "crv_ppm_allocate_resources": (C.c_int, [_vp]),
     "crv_ppm_free_resources": (C.c_int, [_vp]),

@@ -850,7 +850,20 @@ static void coarse_pretest_geometry(PTConst& c, int shift)
 struct crv_ppm {
     crv_ctx* ctx = nullptr;
     const crv_photon_map_properties* ctor_props = nullptr;   // borrowed, like m_photonMapProperties (RenderTechniquePPM.cpp:12)
-    const crv_push_constants* pc = nullptr;
+    crv_push_constants* pc = nullptr;                        // borrowed; UpdateRadius writes pmRadius into it (:302-312)
+    float initial_radius = 10.0f;                            // main.cpp:813
+    float alpha = 0.8f;                                      // RenderTechniquePPM.h:66
+    // estimate-pass bindings
+    crv_camera_properties cam{};
+    crv_shadow_volume_properties sv{};
+    crv_volume* sv_vol = nullptr;
+    bool has_cam = false, has_sv = false;
+    const crv_camera_properties* q_cam = nullptr;
+    const crv_shadow_volume_properties* q_sv = nullptr;
+    crv_volume* q_sv_vol = nullptr;
+    std::vector<crv_image*> images;
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;
+    bool timed_estimate = false;
     // committed / queued bindings
     crv_photon_map_properties props{};
     crv_cloud_properties cloud{};
@@ -874,7 +887,7 @@ struct crv_ppm {
     bool timed = false;
 };
 
-int crv_ppm_create(crv_ctx* ctx, const crv_photon_map_properties* props, const crv_push_constants* pc, crv_ppm** out)
+int crv_ppm_create(crv_ctx* ctx, const crv_photon_map_properties* props, crv_push_constants* pc, float initial_radius, crv_ppm** out)
 {
     CRV_REQUIRE(ctx && props && pc && out, "crv_ppm_create: null argument");
     CRV_ENTER(ctx);
@@ -885,8 +898,10 @@ int crv_ppm_create(crv_ctx* ctx, const crv_photon_map_properties* props, const c
     p->ctor_props = props;
     p->pc = pc;
     p->props = *props;
-    if (cudaMalloc(&p->stats, 3 * sizeof(unsigned long long)) != cudaSuccess || cudaEventCreate(&p->ev0) != cudaSuccess ||
-        cudaEventCreate(&p->ev1) != cudaSuccess) {
+    p->initial_radius = initial_radius;
+    pc->pmRadius = initial_radius;                  // RenderTechniquePPM.cpp:15
+    if (cudaMalloc(&p->stats, 4 * sizeof(unsigned long long)) != cudaSuccess || cudaEventCreate(&p->ev0) != cudaSuccess ||
+        cudaEventCreate(&p->ev1) != cudaSuccess || cudaEventCreate(&p->ev2) != cudaSuccess || cudaEventCreate(&p->ev3) != cudaSuccess) {
         cudaGetLastError();
         crv_ppm_destroy(p);
         crv_set_error("crv_ppm_create: device allocation failed");
@@ -919,6 +934,8 @@ int crv_ppm_destroy(crv_ppm* ppm)
     if (ppm->stats) cudaFree(ppm->stats);
     if (ppm->ev0) cudaEventDestroy(ppm->ev0);
     if (ppm->ev1) cudaEventDestroy(ppm->ev1);
+    if (ppm->ev2) cudaEventDestroy(ppm->ev2);
+    if (ppm->ev3) cudaEventDestroy(ppm->ev3);
     delete ppm;
     return CRV_OK;
 }
@@ -958,9 +975,36 @@ int crv_ppm_queue_update_parameters(crv_ppm* ppm, const crv_parameters* params)
     ppm->q_params = params;
     return CRV_OK;
 }
+int crv_ppm_set_frame_references(crv_ppm* ppm, crv_image* const* result_images, unsigned count)
+{
+    CRV_REQUIRE(ppm && (result_images || count == 0), "crv_ppm_set_frame_references: null argument");
+    ppm->images.assign(result_images, result_images + count);
+    return CRV_OK;
+}
+int crv_ppm_queue_update_camera_properties(crv_ppm* ppm, const crv_camera_properties* cam)
+{
+    CRV_REQUIRE(ppm && cam, "crv_ppm_queue_update_camera_properties: null argument");
+    ppm->q_cam = cam;
+    return CRV_OK;
+}
+int crv_ppm_queue_update_shadow_volume(crv_ppm* ppm, const crv_shadow_volume_properties* p)
+{
+    CRV_REQUIRE(ppm && p, "crv_ppm_queue_update_shadow_volume: null argument");
+    ppm->q_sv = p;
+    return CRV_OK;
+}
+int crv_ppm_queue_update_shadow_volume_sampler(crv_ppm* ppm, crv_volume* shadow_image)
+{
+    CRV_REQUIRE(ppm && shadow_image, "crv_ppm_queue_update_shadow_volume_sampler: null argument");
+    ppm->q_sv_vol = shadow_image;
+    return CRV_OK;
+}
 int crv_ppm_update_descriptor_sets(crv_ppm* ppm)
 {
     CRV_REQUIRE(ppm != nullptr, "crv_ppm_update_descriptor_sets: null technique");
+    if (ppm->q_cam) { ppm->cam = *ppm->q_cam; ppm->has_cam = true; ppm->q_cam = nullptr; }
+    if (ppm->q_sv) { ppm->sv = *ppm->q_sv; ppm->has_sv = true; ppm->q_sv = nullptr; }
+    if (ppm->q_sv_vol) { ppm->sv_vol = ppm->q_sv_vol; ppm->q_sv_vol = nullptr; }
     if (ppm->q_cloud) { ppm->cloud = *ppm->q_cloud; ppm->has_cloud = true; ppm->q_cloud = nullptr; }
     if (ppm->q_cloud_vol) { ppm->cloud_vol = ppm->q_cloud_vol; ppm->q_cloud_vol = nullptr; }
     if (ppm->q_params) { ppm->params = *ppm->q_params; ppm->has_params = true; ppm->q_params = nullptr; }
@@ -968,22 +1012,16 @@ int crv_ppm_update_descriptor_sets(crv_ppm* ppm)
     return CRV_OK;
 }
 
-int crv_ppm_record_photon_tracing(crv_ppm* ppm, void* stream, uint32_t groups_x)
+// kernel-parameter block shared by the two dispatches: cloud, phase and photon-map parameters, tables
+static int ppm_build_const(crv_ppm* ppm, cudaStream_t s, PPMConst& k)
 {
-    CRV_REQUIRE(ppm != nullptr, "crv_ppm_record_photon_tracing: null technique");
-    CRV_ENTER(ppm->ctx);
-    CRV_REQUIRE(ppm->has_cloud && ppm->cloud_vol, "RenderTechniquePPM: cloud data / sampler not bound (bindings 2,3)");
-    CRV_REQUIRE(ppm->has_params, "RenderTechniquePPM: Parameters not bound (binding 4)");
+    CRV_REQUIRE(ppm->has_cloud && ppm->cloud_vol, "RenderTechniquePPM: cloud data / sampler not bound");
+    CRV_REQUIRE(ppm->has_params, "RenderTechniquePPM: Parameters not bound");
     CRV_REQUIRE(ppm->photons && ppm->collisions, "RenderTechniquePPM: AllocateResources has not been called");
     const crv_photon_map_properties& pr = ppm->props;
     CRV_REQUIRE((unsigned long long)pr.voxelCount[0] * pr.voxelCount[1] * pr.voxelCount[2] == ppm->cells,
                 "RenderTechniquePPM: PhotonMapProperties.voxelCount changed since AllocateResources");
     CRV_REQUIRE(ppm->cloud.maxExtinction > 0.0f, "RenderTechniquePPM: maxExtinction must be positive");
-    if (groups_x == 0) groups_x = 200;          // vkCmdDispatch(commandBuffer, 200, 1, 1) (RenderTechniquePPM.cpp:253)
-    CRV_REQUIRE(groups_x <= (1u << 24), "RenderTechniquePPM: more than 2^30 photons per dispatch");
-    cudaStream_t s = as_stream(stream);
-
-    PPMConst k;
     std::memset(&k, 0, sizeof(k));
     PTConst& c = k.base;
     const crv_cloud_properties& cp = ppm->cloud;
@@ -1041,18 +1079,133 @@ int crv_ppm_record_photon_tracing(crv_ppm* ppm, void* stream, uint32_t groups_x)
     k.pm_voxel_size = pr.voxelSize;
     k.pm_absorption = pr.absorption;
     k.seed = ppm->pc->seed;                    // vkCmdPushConstants snapshot (RenderTechniquePPM.cpp:243)
-    k.n_photons = groups_x * 64u;
     k.photons = ppm->photons;
     k.collisions = ppm->collisions;
     k.stats = ppm->stats;
     k.cells = ppm->cells;
 
+    k.pm_step_size = pr.stepSize;
+    k.base_scaling = cp.baseScaling;
+    return CRV_OK;
+}
+
+int crv_ppm_record_photon_tracing(crv_ppm* ppm, void* stream, uint32_t groups_x)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_record_photon_tracing: null technique");
+    CRV_ENTER(ppm->ctx);
+    if (groups_x == 0) groups_x = 200;          // vkCmdDispatch(commandBuffer, 200, 1, 1) (RenderTechniquePPM.cpp:253)
+    CRV_REQUIRE(groups_x <= (1u << 24), "RenderTechniquePPM: more than 2^30 photons per dispatch");
+    cudaStream_t s = as_stream(stream);
+    PPMConst k;
+    CRV_TRY(ppm_build_const(ppm, s, k));
+    k.n_photons = groups_x * 64u;
     CRV_CUDA(cudaEventRecord(ppm->ev0, s));
-    CRV_CUDA(cudaMemsetAsync(ppm->stats, 0, 3 * sizeof(unsigned long long), s));
+    CRV_CUDA(cudaMemsetAsync(ppm->stats, 0, 4 * sizeof(unsigned long long), s));
     CRV_TRY(crv_launch_ppm_clear(ppm->ctx, ppm->photons, ppm->collisions, ppm->cells, s));
-    CRV_TRY(crv_launch_ppm_trace(ppm->ctx, k, cv->layout, s));
+    CRV_TRY(crv_launch_ppm_trace(ppm->ctx, k, ppm->cloud_vol->layout, s));
     CRV_CUDA(cudaEventRecord(ppm->ev1, s));
     ppm->timed = true;
+    return CRV_OK;
+}
+
+// The estimate half of RecordDrawCommands (RenderTechniquePPM.cpp:260-273): PPM_PE.comp over the current photon map into
+// result image `image_index`, with seed / frameCount / pmRadius read from the PushConstants now.
+int crv_ppm_record_photon_estimate(crv_ppm* ppm, void* stream, unsigned image_index)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_record_photon_estimate: null technique");
+    CRV_ENTER(ppm->ctx);
+    CRV_REQUIRE(image_index < ppm->images.size() && ppm->images[image_index], "RenderTechniquePPM: no result image (binding 0)");
+    CRV_REQUIRE(ppm->has_cam, "RenderTechniquePPM: CameraProperties not bound (binding 1)");
+    CRV_REQUIRE(ppm->has_sv && ppm->sv_vol, "RenderTechniquePPM: shadow volume / sampler not bound (bindings 8,9)");
+    cudaStream_t s = as_stream(stream);
+    PPMConst k;
+    CRV_TRY(ppm_build_const(ppm, s, k));
+    PTConst& c = k.base;
+    crv_image* img = ppm->images[image_index];
+    const int W = ppm->cam.halfWidth * 2, H = ppm->cam.halfHeight * 2;
+    CRV_REQUIRE(W > 0 && H > 0 && (int)img->width == W && (int)img->height == H, "RenderTechniquePPM: result image size differs from CameraProperties resolution");
+    const uint32_t nsv = ppm->sv.voxelAxisCount;
+    CRV_REQUIRE(ppm->sv_vol->nx == nsv && ppm->sv_vol->ny == nsv && ppm->sv_vol->nz == nsv, "RenderTechniquePPM: shadow image is not voxelAxisCount^3");
+    float d[4];
+    for (int i = 0; i < 3; ++i) {
+        c.cam_pos[i] = ppm->cam.position[i];
+        c.fwd_near[i] = ppm->cam.forward[i] * ppm->cam.nearPlane;
+        c.right_psx[i] = ppm->cam.right[i] * ppm->cam.pixelSizeX;
+        c.up_psy[i] = ppm->cam.up[i] * ppm->cam.pixelSizeY;
+        c.light[i] = ppm->sv.lightDirection[i];
+        c.m0[i] = ppm->sv.basisChange[0][i];
+        c.m1[i] = ppm->sv.basisChange[1][i];
+        c.m2[i] = ppm->sv.basisChange[2][i];
+        c.m3[i] = ppm->sv.basisChange[3][i];
+    }
+    for (int i = 0; i < 4; ++i) {
+        c.sb0[i] = ppm->sv.bounds[0][i];
+        d[i] = ppm->sv.bounds[1][i] - ppm->sv.bounds[0][i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        c.sden[i] = ((ppm->sv.basisChange[0][i] * d[0] + ppm->sv.basisChange[1][i] * d[1]) + ppm->sv.basisChange[2][i] * d[2]) + ppm->sv.basisChange[3][i] * d[3];
+        CRV_REQUIRE(std::isfinite(c.sden[i]) && std::fabs(c.sden[i]) >= 1e-18f && std::fabs(c.sden[i]) <= 1e18f,
+                    "RenderTechniquePPM: shadow-volume extent must be finite and within 1e-18..1e18");
+        c.rsden[i] = 1.0f / c.sden[i];
+    }
+    c.half_w = ppm->cam.halfWidth;
+    c.half_h = ppm->cam.halfHeight;
+    c.width = W;
+    c.height = H;
+    c.row_stride = 32u * (uint32_t)(W / 32 + 1);
+    c.inv4pi_omg2 = (1.0f / (4.0f * 3.14159265359f)) * ppm->params.phaseOneMinusG2;
+    c.sv = ppm->sv_vol->view();
+    k.pm_radius = ppm->pc->pmRadius;
+    k.frame_count = ppm->pc->frameCount;
+    k.image = reinterpret_cast<float4*>(img->rgba);
+    CRV_CUDA(cudaEventRecord(ppm->ev2, s));
+    CRV_TRY(crv_launch_ppm_estimate(ppm->ctx, k, ppm->cloud_vol->layout, ppm->sv_vol->layout, s));
+    CRV_CUDA(cudaEventRecord(ppm->ev3, s));
+    ppm->timed_estimate = true;
+    return CRV_OK;
+}
+
+// UpdateRadius (RenderTechniquePPM.cpp:302-312): the progressive radius, written into the caller's PushConstants
+int crv_ppm_update_radius(crv_ppm* ppm, unsigned frame_number)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_update_radius: null technique");
+    if (frame_number <= 1) ppm->pc->pmRadius = ppm->initial_radius;
+    else ppm->pc->pmRadius = ppm->pc->pmRadius * std::pow(((float)(frame_number - 1u) + ppm->alpha) / (float)frame_number, .33333f);
+    return CRV_OK;
+}
+
+// RenderTechniquePPM::RecordDrawCommands (:229-273) without the swapchain blit: radius update, tracing, estimate
+int crv_ppm_record_draw_commands(crv_ppm* ppm, void* stream, unsigned image_index)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_record_draw_commands: null technique");
+    CRV_TRY(crv_ppm_update_radius(ppm, ppm->pc->frameCount));
+    CRV_TRY(crv_ppm_record_photon_tracing(ppm, stream, 0));
+    return crv_ppm_record_photon_estimate(ppm, stream, image_index);
+}
+
+// test / tooling hook: replace the photon map by host data (cells*32 photons, cells*4 u32)
+int crv_ppm_upload(crv_ppm* ppm, const crv_photon* host_photons, const uint32_t* host_collisions, void* stream)
+{
+    CRV_REQUIRE(ppm && host_photons && host_collisions, "crv_ppm_upload: null argument");
+    CRV_ENTER(ppm->ctx);
+    CRV_REQUIRE(ppm->photons && ppm->collisions, "crv_ppm_upload: no resources allocated");
+    cudaStream_t s = as_stream(stream);
+    CRV_CUDA(cudaMemcpyAsync(ppm->photons, host_photons, ppm->cells * PPM_ELEMENTS_PER_CELL * sizeof(crv_photon), cudaMemcpyHostToDevice, s));
+    CRV_CUDA(cudaMemcpyAsync(ppm->collisions, host_collisions, ppm->cells * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CRV_CUDA(cudaStreamSynchronize(s));
+    return CRV_OK;
+}
+
+int crv_ppm_last_estimate_stats(crv_ppm* ppm, uint64_t* march_steps, float* ms)
+{
+    CRV_REQUIRE(ppm != nullptr, "crv_ppm_last_estimate_stats: null technique");
+    CRV_ENTER(ppm->ctx);
+    CRV_REQUIRE(ppm->timed_estimate, "crv_ppm_last_estimate_stats: no estimate dispatch recorded yet");
+    CRV_CUDA(cudaEventSynchronize(ppm->ev3));
+    unsigned long long v = 0;
+    CRV_CUDA(cudaMemcpy(&v, ppm->stats + 3, sizeof(v), cudaMemcpyDeviceToHost));
+    if (march_steps) *march_steps = v;
+    if (ms) CRV_CUDA(cudaEventElapsedTime(ms, ppm->ev2, ppm->ev3));
     return CRV_OK;
 }
 

@@ -131,8 +131,15 @@ struct PPMConst {
     uint32_t n_photons;            // 64 * groups_x invocations (= emittedPhotons, :459)
     crv_photon* photons;           // cells * 32 records
     uint32_t* collisions;          // cells uvec4, .x = photons deposited in the cell
-    unsigned long long* stats;     // [0] tracking iterations, [1] deposits, [2] deposits dropped (cell already holds 32)
+    unsigned long long* stats;     // [0] tracking iterations, [1] deposits, [2] deposits dropped (cell already holds 32), [3] estimate march steps
     unsigned long long cells;
+    // ---- estimate pass (PPM_PE.comp) ----
+    float pm_step_size;            // PhotonMapProperties.stepSize
+    float pm_radius;               // pushConstants.pmRadius
+    float base_scaling;            // CloudProperties.baseScaling
+    uint32_t frame_count;          // pushConstants.frameCount
+    float4* image;                 // result image (binding 0)
 };
+int crv_launch_ppm_estimate(crv_ctx* ctx, const PPMConst& c, int cloud_layout, int sv_layout, cudaStream_t s);
 int crv_launch_ppm_clear(crv_ctx* ctx, crv_photon* photons, uint32_t* collisions, unsigned long long cells, cudaStream_t s);
 int crv_launch_ppm_trace(crv_ctx* ctx, const PPMConst& c, int cloud_layout, cudaStream_t s);

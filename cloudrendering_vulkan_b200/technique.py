@@ -393,16 +393,55 @@ class RenderTechniquePT(RenderTechnique):
 
 
 class RenderTechniquePPM:
-    """RenderTechniquePPM (RenderTechniquePPM.h/.cpp), photon-tracing pass only: the dispatch of
-    shaders/PPM_PT.comp that fills the photon map; the estimate pass (PPM_PE.comp) is not built."""
+    """RenderTechniquePPM (RenderTechniquePPM.h/.cpp): progressive photon mapping -- per frame the radius update,
+    the photon-tracing dispatch (shaders/PPM_PT.comp) and the photon-estimate dispatch (shaders/PPM_PE.comp)."""
 
-    def __init__(self, device: Context, photonMapProperties, pushConstants: PushConstants):
+    def __init__(self, device: Context, photonMapProperties, pushConstants: PushConstants, initialRadius: float = 10.0):
         self.ctx = device
         self.photonMapProperties = photonMapProperties       # borrowed, like the reference's pointer member
-        self.pushConstants = pushConstants
+        self.pushConstants = pushConstants                   # UpdateRadius writes pmRadius into it
         self.handle = C.c_void_p()
-        check(lib.crv_ppm_create(device.handle, C.byref(photonMapProperties), C.byref(pushConstants), C.byref(self.handle)))
+        check(lib.crv_ppm_create(device.handle, C.byref(photonMapProperties), C.byref(pushConstants), C.c_float(initialRadius),
+                                 C.byref(self.handle)))
         self._keep = []
+        self._images = []
+
+    def SetFrameReferences(self, images):
+        self._images = list(images)
+        arr = (C.c_void_p * len(self._images))(*[im.handle for im in self._images])
+        check(lib.crv_ppm_set_frame_references(self.handle, arr, len(self._images)))
+
+    def QueueUpdateCameraProperties(self, cameraProperties, imageIdx=0):
+        self._keep.append(cameraProperties)
+        check(lib.crv_ppm_queue_update_camera_properties(self.handle, C.byref(cameraProperties)))
+
+    def QueueUpdateShadowVolume(self, shadowVolumeProperties, imageIdx=0):
+        self._keep.append(shadowVolumeProperties)
+        check(lib.crv_ppm_queue_update_shadow_volume(self.handle, C.byref(shadowVolumeProperties)))
+
+    def QueueUpdateShadowVolumeSampler(self, shadowImage: Volume, imageIdx=0):
+        self._keep.append(shadowImage)
+        check(lib.crv_ppm_queue_update_shadow_volume_sampler(self.handle, shadowImage.handle))
+
+    def RecordDrawCommands(self, stream=0, imageIndex: int = 0):
+        """RenderTechniquePPM.cpp:229-273: UpdateRadius(frameCount), tracing (200 groups), estimate"""
+        check(lib.crv_ppm_record_draw_commands(self.handle, _stream(stream), int(imageIndex)))
+
+    def UpdateRadius(self, frameNumber: int):
+        check(lib.crv_ppm_update_radius(self.handle, int(frameNumber)))
+
+    def RecordPhotonEstimate(self, stream=0, imageIndex: int = 0):
+        check(lib.crv_ppm_record_photon_estimate(self.handle, _stream(stream), int(imageIndex)))
+
+    def Upload(self, photons: np.ndarray, collisions: np.ndarray, stream=0):
+        ph = np.ascontiguousarray(photons, np.float32)
+        co = np.ascontiguousarray(collisions, np.uint32)
+        check(lib.crv_ppm_upload(self.handle, ph.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p), _stream(stream)))
+
+    def LastEstimateStats(self):
+        a, ms = C.c_uint64(), C.c_float()
+        check(lib.crv_ppm_last_estimate_stats(self.handle, C.byref(a), C.byref(ms)))
+        return {"march_steps": a.value, "ms": ms.value}
 
     def AllocateResources(self):
         check(lib.crv_ppm_allocate_resources(self.handle))
@@ -424,7 +463,7 @@ class RenderTechniquePPM:
 
     def UpdateDescriptorSets(self):
         check(lib.crv_ppm_update_descriptor_sets(self.handle))
-        self._keep = self._keep[-3:]
+        self._keep = self._keep[-8:]
 
     def RecordPhotonTracing(self, stream=0, groups_x: int = 0):
         """the tracing half of RecordDrawCommands (RenderTechniquePPM.cpp:229-254); groups_x = 0 -> the reference's 200"""

@@ -316,36 +316,60 @@ private:
     uint32_t m_setCount = 1;
 };
 
-// RenderTechniquePPM.h / .cpp, photon-tracing pass only: the dispatch of shaders/PPM_PT.comp that fills the
-// photon map.  The estimate pass (PPM_PE.comp) and its camera / result-image / shadow-volume bindings are not built, so this
-// class does not derive from RenderTechnique: it has no image to draw into.
-class RenderTechniquePPM {
+// RenderTechniquePPM.h:8-70 / .cpp: progressive photon mapping -- per frame the radius update, the
+// photon-tracing dispatch (shaders/PPM_PT.comp) and the photon-estimate dispatch (shaders/PPM_PE.comp)
+class RenderTechniquePPM : public RenderTechnique {
 public:
-    RenderTechniquePPM(Device* device, const PhotonMapProperties* photonMapProperties, PushConstants* pushConstants)
+    RenderTechniquePPM(Device* device, const CameraProperties* /*cameraProperties: read from its descriptor*/, PhotonMapProperties* photonMapProperties,
+                       PushConstants* pushConstants, float initialRadius)
+        : RenderTechnique(device, pushConstants)
     {
-        Check(crv_ppm_create(device->Get(), photonMapProperties, pushConstants, &m_ppm));
+        Check(crv_ppm_create(device->Get(), photonMapProperties, pushConstants, initialRadius, &m_ppm));
     }
-    ~RenderTechniquePPM() { crv_ppm_destroy(m_ppm); }
-    RenderTechniquePPM(const RenderTechniquePPM&) = delete;
-    RenderTechniquePPM& operator=(const RenderTechniquePPM&) = delete;
+    ~RenderTechniquePPM() override { crv_ppm_destroy(m_ppm); }
 
     void AllocateResources() { Check(crv_ppm_allocate_resources(m_ppm)); }          // RenderTechniquePPM.cpp:127-160
     void FreeResources() { Check(crv_ppm_free_resources(m_ppm)); }                  // :113-125
-    void QueueUpdateCloudData(DescriptorBufferInfo& info, unsigned int /*imageIdx*/)
+    void SetFrameReferences(std::vector<FrameImage>& frameImages) override
+    {
+        std::vector<crv_image*> imgs;
+        for (auto& f : frameImages) imgs.push_back(f.image2D ? f.image2D->Get() : nullptr);
+        Check(crv_ppm_set_frame_references(m_ppm, imgs.data(), (unsigned)imgs.size()));
+    }
+    void ClearFrameReferences() override { Check(crv_ppm_set_frame_references(m_ppm, nullptr, 0)); }
+    uint32_t GetRequiredSetCount() const override { return 2; }                     // tracing and estimate sets (:191-194)
+    void QueueUpdateCloudData(DescriptorBufferInfo& info, unsigned int) override
     {
         Check(crv_ppm_queue_update_cloud_data(m_ppm, static_cast<const crv_cloud_properties*>(info.buffer)));
     }
-    void QueueUpdateCloudDataSampler(DescriptorImageInfo& info, unsigned int /*imageIdx*/)
+    void QueueUpdateCloudDataSampler(DescriptorImageInfo& info, unsigned int) override
     {
         Check(crv_ppm_queue_update_cloud_data_sampler(m_ppm, info.image ? info.image->Get() : nullptr));
     }
-    void QueueUpdateParameters(DescriptorBufferInfo& info, unsigned int /*imageIdx*/)
+    void QueueUpdateCameraProperties(DescriptorBufferInfo& info, unsigned int) override
+    {
+        Check(crv_ppm_queue_update_camera_properties(m_ppm, static_cast<const crv_camera_properties*>(info.buffer)));
+    }
+    void QueueUpdateParameters(DescriptorBufferInfo& info, unsigned int) override
     {
         Check(crv_ppm_queue_update_parameters(m_ppm, static_cast<const crv_parameters*>(info.buffer)));
     }
-    void UpdateDescriptorSets() { Check(crv_ppm_update_descriptor_sets(m_ppm)); }
-    // the tracing half of RecordDrawCommands (:229-254); groupsX = 0 is the reference's vkCmdDispatch(200, 1, 1)
+    void QueueUpdateShadowVolume(DescriptorBufferInfo& info, unsigned int) override
+    {
+        Check(crv_ppm_queue_update_shadow_volume(m_ppm, static_cast<const crv_shadow_volume_properties*>(info.buffer)));
+    }
+    void QueueUpdateShadowVolumeSampler(DescriptorImageInfo& info, unsigned int) override
+    {
+        Check(crv_ppm_queue_update_shadow_volume_sampler(m_ppm, info.image ? info.image->Get() : nullptr));
+    }
+    void UpdateDescriptorSets() override { Check(crv_ppm_update_descriptor_sets(m_ppm)); }
+    // one progressive frame: UpdateRadius(frameCount), photon tracing, photon estimate (:229-273)
+    void RecordDrawCommands(CommandStream commandBuffer, unsigned int imageIndex) override
+    {
+        Check(crv_ppm_record_draw_commands(m_ppm, commandBuffer, imageIndex));
+    }
     void RecordPhotonTracing(CommandStream commandBuffer, uint32_t groupsX = 0) { Check(crv_ppm_record_photon_tracing(m_ppm, commandBuffer, groupsX)); }
+    void RecordPhotonEstimate(CommandStream commandBuffer, unsigned int imageIndex) { Check(crv_ppm_record_photon_estimate(m_ppm, commandBuffer, imageIndex)); }
     void Download(crv_photon* photons, uint32_t* collisions, CommandStream stream = nullptr) { Check(crv_ppm_download(m_ppm, photons, collisions, stream)); }
     crv_ppm* Get() const { return m_ppm; }
 

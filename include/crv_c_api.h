@@ -313,29 +313,48 @@ int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_
  *   1 = lanes every lane owns one path plus one in reserve (kept for A/B measurements) */
 int  crv_pt_set_scheduler(crv_pt* pt, int scheduler);
 
-/* ---- RenderTechniquePPM, photon-tracing pass (RenderTechniquePPM.h / .cpp; shaders/PPM_PT.comp) -----------------
- * Only the first of the technique's two dispatches is built: emit 64 * groups_x photons from the sun
- * and the sky, delta-track them through the cloud with the path tracer's code, deposit one photon per scattering event
- * after the first into a uniform grid of cells (32 slots each, an atomic counter per cell).  The estimate pass
- * (PPM_PE.comp) is not built.  Bindings: 0 photon map, 1 PhotonMapProperties, 2 cloud sampler, 3 CloudProperties,
- * 4 Parameters, 5 collision map (RenderTechniquePPM.cpp:22-38). */
-int  crv_ppm_create(crv_ctx* ctx, const crv_photon_map_properties* props, const crv_push_constants* pc, crv_ppm** out);
+/* ---- RenderTechniquePPM (RenderTechniquePPM.h / .cpp; shaders/PPM_PT.comp + PPM_PE.comp) ------------------------
+ * Progressive photon mapping.  Every frame (RecordDrawCommands, RenderTechniquePPM.cpp:229-273):
+ *   UpdateRadius  pmRadius shrinks with the frame number (:302-312), written into the caller's PushConstants
+ *   tracing       64 * groups_x photons from the sun and the sky are delta-tracked through the cloud with the path
+ *                 tracer's code and deposited into a uniform grid of cells (32 slots each, an atomic counter per cell)
+ *   estimate      one thread per pixel marches the camera ray through the cloud and adds, per step, the sun term through
+ *                 the shadow volume, a sky term and the photon-map density estimate; running mean into the result image
+ * Tracing bindings: 0 photon map, 1 PhotonMapProperties, 2 cloud sampler, 3 CloudProperties, 4 Parameters, 5 collision
+ * map (RenderTechniquePPM.cpp:22-38).  Estimate bindings: 0 result image, 1 CameraProperties, 2 photon map,
+ * 3 CloudProperties, 4 Parameters, 5 PhotonMapProperties, 6 collision map, 7 cloud sampler, 8 shadow sampler,
+ * 9 ShadowVolumeProperties (:59-81).  The swapchain blit is crv_image_blit_srgb8. */
+int  crv_ppm_create(crv_ctx* ctx, const crv_photon_map_properties* props, crv_push_constants* pc, float initial_radius /* main.cpp:813: 10 */,
+                    crv_ppm** out);
 int  crv_ppm_destroy(crv_ppm* ppm);
 /* AllocateResources / FreeResources (RenderTechniquePPM.cpp:113-160): photon map = cells*32 photons, collision map =
  * cells uvec4, sized from the PhotonMapProperties given at creation; both start zeroed */
 int  crv_ppm_allocate_resources(crv_ppm* ppm);
 int  crv_ppm_free_resources(crv_ppm* ppm);
-int  crv_ppm_queue_update_cloud_data(crv_ppm* ppm, const crv_cloud_properties* cloud);             /* binding 3 */
-int  crv_ppm_queue_update_cloud_data_sampler(crv_ppm* ppm, crv_volume* cloud_image);                /* binding 2 */
-int  crv_ppm_queue_update_parameters(crv_ppm* ppm, const crv_parameters* params);                   /* binding 4 */
-int  crv_ppm_update_descriptor_sets(crv_ppm* ppm);      /* also snapshots the PhotonMapProperties (binding 1, SetData) */
-/* The tracing half of RecordDrawCommands (RenderTechniquePPM.cpp:229-254): clear both buffers, push the constants
- * (seed is read now), dispatch groups_x x 1 x 1 groups of 64 photons; groups_x = 0 means the reference's 200. */
+int  crv_ppm_set_frame_references(crv_ppm* ppm, crv_image* const* result_images, unsigned count);
+int  crv_ppm_queue_update_cloud_data(crv_ppm* ppm, const crv_cloud_properties* cloud);
+int  crv_ppm_queue_update_cloud_data_sampler(crv_ppm* ppm, crv_volume* cloud_image);
+int  crv_ppm_queue_update_parameters(crv_ppm* ppm, const crv_parameters* params);
+int  crv_ppm_queue_update_camera_properties(crv_ppm* ppm, const crv_camera_properties* cam);
+int  crv_ppm_queue_update_shadow_volume(crv_ppm* ppm, const crv_shadow_volume_properties* p);
+int  crv_ppm_queue_update_shadow_volume_sampler(crv_ppm* ppm, crv_volume* shadow_image);
+int  crv_ppm_update_descriptor_sets(crv_ppm* ppm);      /* also snapshots the PhotonMapProperties (SetData) */
+/* RecordDrawCommands (:229-273): UpdateRadius(frameCount), tracing with the reference's 200 groups, estimate */
+int  crv_ppm_record_draw_commands(crv_ppm* ppm, void* stream, unsigned image_index);
+/* its parts: the radius update, the tracing dispatch (clear both buffers, groups_x x 1 x 1 groups of 64 photons;
+ * groups_x = 0 means 200) and the estimate dispatch over the current photon map; seed / frameCount / pmRadius are read
+ * from the PushConstants at the call */
+int  crv_ppm_update_radius(crv_ppm* ppm, unsigned frame_number);
 int  crv_ppm_record_photon_tracing(crv_ppm* ppm, void* stream, uint32_t groups_x);
+int  crv_ppm_record_photon_estimate(crv_ppm* ppm, void* stream, unsigned image_index);
 /* photons: cells*32 records, collisions: cells*4 u32 (x = deposits in the cell; may exceed 32); either may be NULL */
 int  crv_ppm_download(crv_ppm* ppm, crv_photon* host_photons, uint32_t* host_collisions, void* stream);
-/* tracking iterations / deposits / deposits dropped because their cell was full, of the last dispatch; device ms */
+/* replace the photon map by host data (tests / tooling): an estimate over a known map */
+int  crv_ppm_upload(crv_ppm* ppm, const crv_photon* host_photons, const uint32_t* host_collisions, void* stream);
+/* tracking iterations / deposits / deposits dropped because their cell was full, of the last tracing dispatch; device ms */
 int  crv_ppm_last_trace_stats(crv_ppm* ppm, uint64_t* steps, uint64_t* deposits, uint64_t* dropped, float* ms);
+/* ray-march steps and device ms of the last estimate dispatch */
+int  crv_ppm_last_estimate_stats(crv_ppm* ppm, uint64_t* march_steps, float* ms);
 void crv_photon_map_init(crv_photon_map_properties* p);                                             /* :212-222 */
 void crv_photon_map_set_bounds(crv_photon_map_properties* p, const float bounds[2][4]);             /* :225-243 */
 uint32_t crv_photon_map_total_size(const crv_photon_map_properties* p);                             /* :245-248 */

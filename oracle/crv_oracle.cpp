@@ -495,6 +495,120 @@ void tracePhoton(const float* vol, const Cloud& cp, const Params& par, const Pho
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// PPM photon estimate: shaders/PPM_PE.comp (the second dispatch of RenderTechniquePPM::RecordDrawCommands).  One invocation
+// per pixel: the camera ray is marched through the cloud back to front in steps of stepSize; every step adds the sun term
+// through the shadow volume, a sky term along one phase-sampled direction, and the photon-map density estimate.
+// getCameraRay / intersectCloud / sampleCloud / sampleShadowVolume / samplePhase / scatterRay / sampleBackground are the
+// same text as PathTracer.comp's (scatterRay without PPM_PT's normalize, PPM_PE.comp:391-425).
+// ----------------------------------------------------------------------------------------------------------
+bool isInCloud(const Cloud& cp, vec3 p)                 // PPM_PE.comp:186-194
+{
+    return !(p.x < cp.bounds[0].x || p.y < cp.bounds[0].y || p.z < cp.bounds[0].z || p.x > cp.bounds[1].x || p.y > cp.bounds[1].y ||
+             p.z > cp.bounds[1].z);
+}
+
+struct PhotonMapView {
+    const Photon* photons;
+    const uint32_t* collisions;
+    uint64_t cells;
+};
+
+// :302-375.  Reads beyond the 32 slots of an overflowed cell run into the following cells' slots like the shader's loop
+// (`i < collisions[idx].x`); beyond the buffer the read returns zeros (robust buffer access).
+vec4 samplePhotonMap(const float* vol, const Cloud& cp, const Params& par, const PhotonMapProps& pm, const PhotonMapView& map, float pmRadius,
+                     Rng& rng, vec3 pos, vec3 dir, float scatter)
+{
+    (void)vol; (void)cp;
+    if (scatter == 0.0f) return {0, 0, 0, 0};
+    const vec3 gp = {pos.x - pm.bounds[0].x, pos.y - pm.bounds[0].y, pos.z - pm.bounds[0].z};
+    auto imax = [](int a, int b) { return a < b ? b : a; };
+    auto imin = [](int a, int b) { return b < a ? b : a; };
+    const int xMin = imax((int)((gp.x - pmRadius) / pm.voxelSize), 0), xMax = imin((int)((gp.x + pmRadius) / pm.voxelSize), pm.voxelCount[0] - 1);
+    const int yMin = imax((int)((gp.y - pmRadius) / pm.voxelSize), 0), yMax = imin((int)((gp.y + pmRadius) / pm.voxelSize), pm.voxelCount[1] - 1);
+    const int zMin = imax((int)((gp.z - pmRadius) / pm.voxelSize), 0), zMax = imin((int)((gp.z + pmRadius) / pm.voxelSize), pm.voxelCount[2] - 1);
+    vec4 acc = {0, 0, 0, 0};
+    const float sqrRadius = pmRadius * pmRadius;
+    for (int z = zMin; z <= zMax; ++z)
+        for (int y = yMin; y <= yMax; ++y)
+            for (int x = xMin; x <= xMax; ++x) {
+                const int idx = x + (y + z * pm.voxelCount[1]) * pm.voxelCount[0];
+                const uint32_t n = map.collisions[4 * (size_t)idx];
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint64_t o = (uint64_t)idx * ELEMENTS_PER_CELL + i;
+                    if (o >= map.cells * ELEMENTS_PER_CELL) continue;           // zeros: position (0,0,0), power 0 -> adds nothing
+                    const Photon& ph = map.photons[o];
+                    const vec3 dv = {ph.position[0] - pos.x, ph.position[1] - pos.y, ph.position[2] - pos.z};
+                    if (dot(dv, dv) <= sqrRadius) {
+                        const vec3 pdir = dirFromPolar(ph.theta, ph.phi);       // (theta, phi) in the ESTIMATE's argument order (:343)
+                        const float w = samplePhase(par, dir, pdir);
+                        acc = acc + vec4{w * ph.power[0], w * ph.power[1], w * ph.power[2], w * ph.power[3]};
+                    }
+                }
+            }
+    if (((((0.0f + acc.x) + acc.y) + acc.z) + acc.w) / 4.0f <= 0.0f) return {0, 0, 0, 0};      // average() :129-137
+    (void)(5.0f * rng.generateRandomNumber());      // sampleDistance: the six density samples that follow feed nothing (:357-366)
+    const float d = ((PI * 4.0f / 3.0f) * pmRadius * sqrRadius) * scatter;                    // PI4_3 * r * r^2 * scatter, left to right
+    return {acc.x / d, acc.y / d, acc.z / d, acc.w / d};
+}
+
+// PPM_PE.comp:430-545 without the final accumulate; returns `result`
+vec4 estimatePixel(const float* vol, const float* sv, const Camera& cam, const Cloud& cp, const Params& par, const Shadow& sp,
+                   const PhotonMapProps& pm, const PhotonMapView& map, int32_t seed, float pmRadius, uint32_t gx, uint32_t gy, uint32_t ngx,
+                   uint64_t& marchSteps)
+{
+    Rng rng;
+    rng.initializeRandom(seed_state(seed, gx, gy, ngx));
+    Ray ray;
+    getCameraRay(cam, (int)gx, (int)gy, ray);
+    vec4 result = sampleBackground(ray.dir);
+    float tmax = 0, tmin = 0;
+    if (intersectCloud(cp, ray, tmax, tmin) && cp.densityScaling > 0.0f) {
+        const vec3 closestPoint = ray.pos + ray.dir * tmin;
+        ray.pos = ray.pos + ray.dir * (tmax - pm.stepSize * rng.generateRandomNumber());
+        const float maxDistance = length(ray.pos - closestPoint);
+        float currentDistance = 0;
+        const vec3 L = {sp.lightDirection.x, sp.lightDirection.y, sp.lightDirection.z};
+        while (currentDistance < maxDistance) {
+            ++marchSteps;
+            const float currentStep = pm.stepSize;
+            ray.pos = ray.pos - ray.dir * currentStep;
+            currentDistance += currentStep;
+            const float extinction = (sampleCloud(vol, cp, ray.pos) * cp.densityScaling) / cp.baseScaling;
+            const float albedo = 1.0f - pm.absorption;
+            const float scatter = albedo * extinction;
+            const float pdf = samplePhase(par, -ray.dir, L);
+            float accumulatedDensity = sampleShadowVolume(sv, sp, ray.pos);
+            float direct = ((1.0f * par.lightIntensity) * pdf) * accumulatedDensity;              // all four channels equal
+            vec4 directRadiance = {direct, direct, direct, direct};
+            vec3 ambientRayDir{0, 0, 0};
+            scatterRay(par, rng, ray.dir, ambientRayDir);
+            accumulatedDensity = 0;
+            float accumulatedDistance = 0;
+            uint32_t samples = 0;
+            vec3 pos = ray.pos;
+            const float sampleDist = 100.0f;
+            vec4 ambientRadiance = sampleBackground(ambientRayDir);
+            while (isInCloud(cp, pos)) {
+                pos = pos + ambientRayDir * sampleDist;
+                accumulatedDensity += sampleCloud(vol, cp, pos);
+                accumulatedDistance += sampleDist;
+                samples++;
+            }
+            accumulatedDensity *= cp.densityScaling / cp.baseScaling;
+            const float e = std::exp(((-accumulatedDistance) * accumulatedDensity) / (float)samples);   // samples == 0: 0/0 -> NaN -> not added
+            ambientRadiance = ambientRadiance * e;
+            if (ambientRadiance.x > 0.0f) directRadiance = directRadiance + ambientRadiance;
+            const vec4 pmr = samplePhotonMap(vol, cp, par, pm, map, pmRadius, rng, ray.pos, -ray.dir, scatter);
+            const vec4 indirectRadiance = albedo * pmr;
+            const float attenuation = std::exp((-currentStep) * extinction);
+            result = result * attenuation;
+            result = result + (scatter * (directRadiance + indirectRadiance)) * currentStep;
+        }
+    }
+    return result;
+}
+
 // :366-425 without the final accumulate; returns `result`
 vec4 tracePixel(const float* vol, const float* sv, const Camera& cam, const Cloud& cp, const Params& par,
                 const Shadow& sp, int32_t seed, float absorption, uint32_t gx, uint32_t gy, uint32_t ngx, Counters& cnt)
@@ -706,6 +820,39 @@ uint64_t orc_ppm_trace(const float* cloud, const void* cloud60, const void* para
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps) num_threads(num_threads > 0 ? num_threads : omp_get_max_threads())
     for (int i = 0; i < total; ++i)
         tracePhoton(cloud, cp, par, pm, seed, (uint32_t)i, (uint32_t)total, static_cast<Photon*>(photons), collisions, steps);
+    return steps;
+}
+// One photon-estimate dispatch over rows y0 <= y < y1 (step row_step) of the image; accumulates into `image` like the shader
+// (:541-545).  Returns the number of ray-march steps.
+uint64_t orc_ppm_estimate(const float* cloud, const float* sv, const void* camera68, const void* cloud60, const void* params28,
+                          const void* pmprops76, const void* svprops152, int32_t seed, uint32_t frame_count, float pm_radius,
+                          const void* photons, const uint32_t* collisions, float* image, int y0, int y1, int row_step, int num_threads)
+{
+    const Camera cam = load_camera(camera68);
+    const Cloud cp = load_cloud(cloud60);
+    const Params par = load_params(params28);
+    const PhotonMapProps pm = load_photon_map_props(pmprops76);
+    const Shadow sp = load_shadow(svprops152);
+    const int W = cam.halfWidth * 2, H = cam.halfHeight * 2;
+    const uint32_t ngx = (uint32_t)(W / 32 + 1);
+    const PhotonMapView map{static_cast<const Photon*>(photons), collisions,
+                            (uint64_t)pm.voxelCount[0] * (uint64_t)pm.voxelCount[1] * (uint64_t)pm.voxelCount[2]};
+    if (y1 > H) y1 = H;
+    if (row_step < 1) row_step = 1;
+    const int nrows = y1 > y0 ? (y1 - y0 + row_step - 1) / row_step : 0;
+    uint64_t steps = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : steps) num_threads(num_threads > 0 ? num_threads : omp_get_max_threads())
+    for (int r = 0; r < nrows; ++r) {
+        const int y = y0 + r * row_step;
+        for (int x = 0; x < W; ++x) {
+            vec4 res = estimatePixel(cloud, sv, cam, cp, par, sp, pm, map, seed, pm_radius, (uint32_t)x, (uint32_t)y, ngx, steps);
+            float* px = image + ((size_t)y * W + x) * 4;
+            const vec4 old = {px[0], px[1], px[2], px[3]};
+            res = res + old * (float)frame_count;
+            const float d = (float)(frame_count + 1u);
+            px[0] = res.x / d; px[1] = res.y / d; px[2] = res.z / d; px[3] = res.w / d;
+        }
+    }
     return steps;
 }
 void orc_blit_srgb8(const float* rgba, size_t npix, unsigned char* bgra8)

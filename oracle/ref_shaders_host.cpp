@@ -26,6 +26,9 @@ namespace sv {
 namespace ppm {
 #include "_ref/PPM_PT.comp.inc"
 }
+namespace ppe {
+#include "_ref/PPM_PE.comp.inc"
+}
 }  // namespace glsl
 
 namespace {
@@ -153,6 +156,43 @@ void refsh_ppm_trace(const float* cloud, int nx, int ny, int nz, const void* clo
         glsl::invocation().global_id = glsl::uvec3((uint32_t)i, 0u, 0u);
         glsl::invocation().num_groups = glsl::uvec3(groups_x, 1u, 1u);
         P::shader_main();
+    }
+}
+
+// One photon-estimate dispatch of PPM_PE.comp (RenderTechniquePPM.cpp:260-273: (W/32+1) x (H/32+1) groups of 32x32) over a
+// given photon map; bindings 0-9 as RenderTechniquePPM.cpp:59-81 declares them.  image = W*H rgba32f, accumulated in place by
+// the shader.  Only rows y0 <= y < y1 with (y - y0) % row_step == 0 run.
+void refsh_ppm_estimate(const float* cloud, int nx, int ny, int nz, const float* sv, int nsv, const void* camera68, const void* cloud60,
+                        const void* params28, const void* pmprops76, const void* svprops152, const void* push24, const void* photons,
+                        const uint32_t* collisions, float* image, int y0, int y1, int row_step, int num_threads)
+{
+    namespace P = glsl::ppe;
+    bind_block(P::cameraProperties, camera68, 68, sizeof(P::CameraProperties_block));
+    bind_block(P::cloudProperties, cloud60, 60, sizeof(P::CloudProperties_block));
+    bind_block(P::parameters, params28, 28, sizeof(P::Parameters_block));
+    bind_block(P::photonMapProperties, pmprops76, 76, sizeof(P::PhotonMapProperties_block));
+    bind_block(P::shadowVolumeProperties, svprops152, 152, sizeof(P::ShadowVolumeProperties_block));
+    std::memset(&P::pushConstants, 0, sizeof(P::pushConstants));
+    std::memcpy(&P::pushConstants, push24, 24 < sizeof(P::pushConstants) ? 24 : sizeof(P::pushConstants));
+    P::cloudSampler.texels = cloud; P::cloudSampler.nx = nx; P::cloudSampler.ny = ny; P::cloudSampler.nz = nz; P::cloudSampler.slot = 0;
+    P::shadowVolumeSampler.texels = sv; P::shadowVolumeSampler.nx = nsv; P::shadowVolumeSampler.ny = nsv; P::shadowVolumeSampler.nz = nsv;
+    P::shadowVolumeSampler.slot = 1;
+    const int W = P::cameraProperties.halfWidth * 2, H = P::cameraProperties.halfHeight * 2;
+    P::resultImage.texels = image; P::resultImage.width = W; P::resultImage.height = H;
+    P::photons = static_cast<P::Photon*>(const_cast<void*>(photons));
+    P::collisions = reinterpret_cast<glsl::uvec4*>(const_cast<uint32_t*>(collisions));
+    const uint32_t gx = (uint32_t)(W / 32 + 1), gy = (uint32_t)(H / 32 + 1);
+    if (y1 > (int)(gy * 32u)) y1 = (int)(gy * 32u);
+    if (row_step < 1) row_step = 1;
+    const int nrows = (y1 - y0 + row_step - 1) / row_step;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(resolve_threads(num_threads))
+    for (int r = 0; r < nrows; ++r) {
+        const int y = y0 + r * row_step;
+        for (uint32_t x = 0; x < gx * 32u; ++x) {
+            glsl::invocation().global_id = glsl::uvec3(x, (uint32_t)y, 0u);
+            glsl::invocation().num_groups = glsl::uvec3(gx, gy, 1u);
+            P::shader_main();
+        }
     }
 }
 

@@ -44,6 +44,8 @@ lib.orc_sample_phase.restype = _f
 lib.orc_sample_phase.argtypes = [_vp, _fp, _fp]
 lib.orc_background.argtypes = [_fp, _fp]
 lib.orc_blit_srgb8.argtypes = [_vp, C.c_size_t, _vp]
+lib.orc_ppm_estimate.restype = C.c_uint64
+lib.orc_ppm_estimate.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u32, _f, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]
 lib.orc_ppm_trace.restype = C.c_uint64
 lib.orc_ppm_trace.argtypes = [_vp, _vp, _vp, _vp, _i32, _u32, _vp, _vp, C.c_uint64, C.c_int]
 lib.orc_texture3d.restype = _f
@@ -151,6 +153,36 @@ def refsh_ppm_trace(cloud, cloud_props, params, pm_props, seed, groups_x=200, th
     rl.refsh_ppm_trace(_ptr(np.ascontiguousarray(cloud, np.float32)), nx, ny, nz, _raw(cloud_props), _raw(params), _raw(pm_props),
                        push_constants_bytes(seed, 0), int(groups_x), _ptr(ph), _ptr(co), cells, threads)
     return ph, co
+
+
+def ppm_estimate(cloud, sv, cam, cloud_props, params, pm_props, sv_props, seed, frame_count, pm_radius, photons, collisions, image,
+                 rows=None, row_step=1, threads=0):
+    """one photon-estimate dispatch of PPM_PE.comp (restatement) over a given photon map; accumulates into image (H,W,4)"""
+    w, h = image_size(cam)
+    y0, y1 = rows if rows is not None else (0, h)
+    assert image.dtype == np.float32 and image.flags["C_CONTIGUOUS"] and image.size == w * h * 4
+    return int(lib.orc_ppm_estimate(_ptr(np.ascontiguousarray(cloud, np.float32)), _ptr(np.ascontiguousarray(sv, np.float32)), _raw(cam),
+                                    _raw(cloud_props), _raw(params), _raw(pm_props), _raw(sv_props), int(seed), int(frame_count),
+                                    float(pm_radius), _ptr(np.ascontiguousarray(photons, np.float32)),
+                                    _ptr(np.ascontiguousarray(collisions, np.uint32)), _ptr(image), int(y0), int(y1), int(row_step), threads))
+
+
+def refsh_ppm_estimate(cloud, sv, cam, cloud_props, params, pm_props, sv_props, seed, frame_count, pm_radius, photons, collisions, image,
+                       rows=None, row_step=1, threads=0):
+    """the same dispatch through the reference's own PPM_PE.comp compiled by g++ (oracle/_ref)"""
+    import struct
+    rl = ref_shaders_lib()
+    w, h = image_size(cam)
+    y0, y1 = rows if rows is not None else (0, h)
+    nx, ny, nz = _cloud_dims(cloud_props)
+    n = int(np.frombuffer(bytes(sv_props), np.uint32, 1, 144)[0])
+    push = (C.c_ubyte * 24).from_buffer_copy(struct.pack("<diIfI", 0.0, int(seed), int(frame_count), float(pm_radius), 0))
+    rl.refsh_ppm_estimate.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      C.c_int, C.c_int, C.c_int, C.c_int]
+    rl.refsh_ppm_estimate(_ptr(np.ascontiguousarray(cloud, np.float32)), nx, ny, nz, _ptr(np.ascontiguousarray(sv, np.float32)), n, _raw(cam),
+                          _raw(cloud_props), _raw(params), _raw(pm_props), _raw(sv_props), push,
+                          _ptr(np.ascontiguousarray(photons, np.float32)), _ptr(np.ascontiguousarray(collisions, np.uint32)), _ptr(image),
+                          int(y0), int(y1), int(row_step), threads)
 
 
 def blit_srgb8(rgba):

@@ -32,3 +32,22 @@ def case_scene(orc, case, crv=None):
     for i in range(4):
         pm.lightDirection[i] = float(L[i])
     return cloud, cp, par, pm
+
+
+ESTIMATE = {"width": 48, "height": 32, "nsv": 24, "radius": 60.0, "frame_count": 3, "seed": 7719, "old_value": 0.25, "groups_scale": 4}
+
+
+def estimate_scene(orc, case, crv=None):
+    """camera / shadow-volume structs and the CPU shadow volume for the photon-estimate cases"""
+    if crv is None:
+        import cloudrendering_vulkan_b200 as crv
+    cloud, cp, par, pm = case_scene(orc, case, crv)
+    cam = crv.CameraProperties()
+    cam.SetResolution(ESTIMATE["width"], ESTIMATE["height"])
+    cam.SetFOV(90.0)
+    sp = crv.ShadowVolumeProperties()
+    sp.voxelAxisCount = ESTIMATE["nsv"]
+    sp.SetLightDirection(case["light"])
+    sp.SetOrigin(tuple(cp.bounds[0])[:3], tuple(cp.bounds[1])[:3])
+    sv = orc.shadow_volume(cloud, cp, sp)
+    return cloud, cp, par, pm, cam, sp, sv
