@@ -1,6 +1,7 @@
 // oracle/glsl_compat.h -- a minimal GLSL 4.50 compute-shader environment in C++.  TEST INFRASTRUCTURE ONLY.
 //
-// Purpose: let the reference's OWN shader sources (/root/reference/shaders/PathTracer.comp, ShadowVolume.comp) be
+// Purpose: let the reference's OWN shader sources (/root/reference/shaders/PathTracer.comp, ShadowVolume.comp, PPM_PT.comp,
+// PPM_PE.comp) be
 // compiled by g++ WHERE THEY LIE and executed on the CPU, so that the hand-written restatement in crv_oracle.cpp
 // (and through it the CUDA kernels) is pinned against the reference's real code instead of against a reading of it.
 // oracle/glsl_to_cpp.py does the purely lexical part (layout qualifiers, in/out/inout, float-literal suffixes,

@@ -1,6 +1,6 @@
 // oracle/ref_shaders_host.cpp -- CPU dispatch of the reference's OWN compute shaders.  TEST INFRASTRUCTURE ONLY.
 //
-// The two #include lines below pull in /root/reference/shaders/PathTracer.comp and ShadowVolume.comp after the
+// The #include lines below pull in /root/reference/shaders/PathTracer.comp, ShadowVolume.comp, PPM_PT.comp and PPM_PE.comp after the
 // lexical rewrite of oracle/glsl_to_cpp.py (generated into the git-ignored oracle/_ref/, never committed); the GLSL
 // types and built-ins come from oracle/glsl_compat.h.  This file is only the "driver": it binds the descriptor set
 // (RenderTechniquePT.cpp:20-35 bindings 0-6, RenderTechniqueSV.cpp:13-22 bindings 0-3), pushes the constants
