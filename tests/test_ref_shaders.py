@@ -123,3 +123,19 @@ def test_off_image_invocations_are_discarded():
     orc.refsh_path_trace(cloud, sv, cam, cp, par, sp, pc, a)
     orc.refsh_path_trace(cloud, sv, cam, cp, par, sp, pc, b, rect=(0, 0, 10 ** 6, 10 ** 6))
     assert np.array_equal(_bits(a), _bits(b))
+
+
+def test_vulkan_oracle_probe_reports_instead_of_substituting_silently():
+    """the SPIR-V / lavapipe oracle of the north star needs glslc, the Vulkan loader and an ICD; the probe says which
+    are missing (all three in this image and on this round's GPU boxes) -- the g++ build of the same shader sources is what runs"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("vulkan_probe", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                                "oracle", "vulkan_probe.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    r = m.probe()
+    assert set(r) == {"available", "glsl_compiler", "loader", "icds", "reason"}
+    assert r["available"] == (r["reason"] is None)
+    if not r["available"]:
+        assert r["reason"].startswith("skipped: no ")
