@@ -118,10 +118,23 @@ def _cpu_kind(orc):
     return "reference" if orc.ref_shaders_lib() is not None else "port"
 
 
+def _vulkan_probe():
+    """oracle/vulkan_probe.py: is the north star's SPIR-V / lavapipe oracle available here?  (never, in this round's images)"""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("vulkan_probe", os.path.join(ROOT, "oracle", "vulkan_probe.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        r = m.probe()
+        return "available" if r["available"] else r["reason"]
+    except Exception as e:       # the probe is informational
+        return f"probe failed: {e}"
+
+
 def _cpu_note(kind, wl):
     if kind == "reference":
         note = ("the reference's own PathTracer.comp compiled by g++ through oracle/glsl_compat.h (OpenMP over image rows); "
-                "lavapipe / SPIR-V unavailable in this image")
+                "SPIR-V on lavapipe: " + _vulkan_probe())
         if wl.absorption > 0:
             note += (f"; the reference has no absorption term, so its paths run at albedo 1 on the same scene "
                      f"(the workload's absorption {wl.absorption:g} is an extension of this repo; `port_value` is the "

@@ -32,8 +32,8 @@ def probe():
         icds += sorted(glob.glob(os.path.join(d, "*.json")))
     if os.environ.get("VK_ICD_FILENAMES"):
         icds += [p for p in os.environ["VK_ICD_FILENAMES"].split(":") if os.path.exists(p)]
-    missing = [n for n, v in (("a GLSL->SPIR-V compiler (glslc / glslangValidator)", compiler), ("the Vulkan loader (libvulkan.so.1)", loader),
-                              ("a Vulkan ICD (lavapipe or the GPU driver's)", icds)) if not v]
+    missing = [n for n, v in (("GLSL->SPIR-V compiler (glslc / glslangValidator)", compiler), ("Vulkan loader (libvulkan.so.1)", loader),
+                              ("Vulkan ICD (lavapipe or the GPU driver's)", icds)) if not v]
     return {"available": not missing, "glsl_compiler": compiler, "loader": loader, "icds": icds,
             "reason": None if not missing else "skipped: no " + "; no ".join(missing)}
 
