@@ -181,11 +181,26 @@ def _sample_text(wl, frames, rows, paths, secs):
     return f"{what} of {frames} {wl.width}x{wl.height} frame(s) of this workload ({paths} path samples, {secs:.1f} s)"
 
 
+def _use_all_host_threads(log=None):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can, so the
+    OpenMP runtime the oracle libraries share is told so explicitly"""
+    try:
+        import ctypes
+        n = len(os.sched_getaffinity(0))
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+        if log:
+            log(f"[reference] OpenMP threads: {n} (OMP_NUM_THREADS was {os.environ.get('OMP_NUM_THREADS', 'unset')})")
+    except Exception as e:      # keep whatever the environment gave
+        if log:
+            log(f"[reference] could not raise the OpenMP thread count: {e}")
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     log = lambda s: print(s, file=sys.stderr, flush=True)
+    _use_all_host_threads(log)
     orc, cloud, cam, cp, par, sp = _oracle_scene(wl, log)
     kind = _cpu_kind(orc)
     t0 = time.perf_counter()
