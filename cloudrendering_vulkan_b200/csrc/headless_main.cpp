@@ -32,6 +32,7 @@ struct Options {
     float g = 0.85f, absorption = 0.0f, density_scaling = 50.0f, fov = 90.0f;
     float light[3] = {1.0f, -1.0f, 0.0f};
     bool isotropic = false, per_frame = false, warmup = false, math_driver = false;
+    unsigned ppm_frames = 0;          // --ppm N: after the path-traced image, N progressive-photon-mapping frames into a second image
 };
 
 bool parse(int argc, char** argv, Options& o)
@@ -59,6 +60,7 @@ bool parse(int argc, char** argv, Options& o)
         else if (a == "--pfm") o.pfm = next("--pfm");
         else if (a == "--png") o.png = next("--png");
         else if (a == "--warmup") o.warmup = true;
+        else if (a == "--ppm") o.ppm_frames = (unsigned)std::atoi(next("--ppm"));
         else if (a == "--math") { const std::string v = next("--math"); if (v != "strict" && v != "driver") return false; o.math_driver = v == "driver"; }
         else if (a == "--resume") o.resume = next("--resume");
         else if (a == "--checkpoint") o.checkpoint = next("--checkpoint");
@@ -130,7 +132,7 @@ int main(int argc, char** argv)
     if (!parse(argc, argv, o)) {
         std::fprintf(stderr, "usage: crv_headless [--xyz file | --fbm N] [--width W --height H] [--spp S] [--nsv N] [--g G | --isotropic]\n"
                              "                    [--absorption A] [--density-scaling D] [--light x,y,z] [--fov F] [--per-frame] [--device i] [--pfm out]\n"
-                             "                    [--png out.png] [--resume acc.ckpt] [--checkpoint acc.ckpt] [--warmup] [--math strict|driver]\n");
+                             "                    [--png out.png] [--resume acc.ckpt] [--checkpoint acc.ckpt] [--warmup] [--math strict|driver] [--ppm frames]\n");
         return 2;
     }
     try {
@@ -237,12 +239,57 @@ int main(int argc, char** argv)
         if (!o.pfm.empty()) app.resultImage->SavePfm(o.pfm.c_str());                 // linear RGB float
         if (!o.png.empty()) app.resultImage->SavePng(o.png.c_str());                 // what the sRGB swapchain image would show
         if (!o.checkpoint.empty()) app.resultImage->SaveCheckpoint(o.checkpoint.c_str(), app.pushConstants.frameCount, seeds.back());
+        // ---- ERenderTechnique::PhotonMapping (main.cpp:204-207, 813): the same scene through RenderTechniquePPM ----
+        double ppm_mean = 0.0, ppm_ms = 0.0;
+        float ppm_radius = 0.0f;
+        if (o.ppm_frames > 0) {
+            crv::PhotonMapProperties photonMapProperties;
+            photonMapProperties.SetBounds(app.cloudProperties.bounds);                                  // main.cpp:162
+            for (int i = 0; i < 3; ++i) photonMapProperties.lightDirection[i] = app.shadowVolumeProperties.lightDirection[i];   // :225
+            crv::PushConstants pc;
+            pc.frameCount = 0;
+            crv::Image ppmImage(app.device.get(), (uint32_t)o.width, (uint32_t)o.height);
+            crv::RenderTechniquePPM ppm(app.device.get(), &app.cameraProperties, &photonMapProperties, &pc, 10.0f);
+            ppm.AllocateResources();
+            std::vector<crv::FrameImage> frames{crv::FrameImage(&ppmImage)};
+            ppm.SetFrameReferences(frames);
+            crv::DescriptorBufferInfo cloudInfo{&app.cloudProperties, sizeof(app.cloudProperties)};
+            crv::DescriptorBufferInfo paramInfo2{&app.parameters, sizeof(app.parameters)};
+            crv::DescriptorBufferInfo cameraInfo2{&app.cameraProperties, sizeof(app.cameraProperties)};
+            crv::DescriptorBufferInfo svInfo{&app.shadowVolumeProperties, sizeof(app.shadowVolumeProperties)};
+            crv::DescriptorImageInfo cloudImageInfo{app.cloudImage.get()};
+            crv::DescriptorImageInfo svImageInfo2{app.shadowVolumeImage.get()};
+            ppm.QueueUpdateCloudData(cloudInfo, 0);
+            ppm.QueueUpdateCloudDataSampler(cloudImageInfo, 0);
+            ppm.QueueUpdateParameters(paramInfo2, 0);
+            ppm.QueueUpdateCameraProperties(cameraInfo2, 0);
+            ppm.QueueUpdateShadowVolume(svInfo, 0);
+            ppm.QueueUpdateShadowVolumeSampler(svImageInfo2, 0);
+            ppm.UpdateDescriptorSets();
+            std::vector<int32_t> ppm_seeds(o.ppm_frames);
+            crv::MsvcRandSequence(0, o.ppm_frames, ppm_seeds.data());
+            app.device->WaitIdle();
+            const auto p0 = std::chrono::steady_clock::now();
+            for (unsigned f = 0; f < o.ppm_frames; ++f) {
+                pc.seed = ppm_seeds[f];
+                ppm.RecordDrawCommands(nullptr, 0);
+                pc.frameCount++;
+            }
+            app.device->WaitIdle();
+            ppm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - p0).count() / o.ppm_frames;
+            std::vector<float> px((size_t)o.width * o.height * 4);
+            ppmImage.Download(px.data());
+            for (float v : px) ppm_mean += v;
+            ppm_mean /= (double)px.size();
+            ppm_radius = pc.pmRadius;
+        }
         std::printf("{\"width\": %d, \"height\": %d, \"spp\": %u, \"mode\": \"%s\", \"render_ms\": %.3f, \"mpath_samples_per_s\": %.1f, "
                     "\"sv_build_ms\": %.4f, \"paths\": %llu, \"tracking_steps\": %llu, \"collisions\": %llu, \"kernel_launches\": %llu, "
-                    "\"image_fnv1a\": \"%016llx\"}\n",
+                    "\"image_fnv1a\": \"%016llx\", \"ppm_frames\": %u, \"ppm_frame_ms\": %.3f, \"ppm_image_mean\": %.9g, \"ppm_radius\": %.9g}\n",
                     o.width, o.height, o.spp, o.per_frame ? "per-frame" : "batch", ms, (double)o.width * o.height * o.spp / ms / 1e3, sv_ms,
                     (unsigned long long)st.paths, (unsigned long long)st.tracking_steps, (unsigned long long)st.collisions,
-                    (unsigned long long)app.device->LaunchCount(), (unsigned long long)fnv1a(rgba.data(), rgba.size() * sizeof(float)));
+                    (unsigned long long)app.device->LaunchCount(), (unsigned long long)fnv1a(rgba.data(), rgba.size() * sizeof(float)),
+                    o.ppm_frames, ppm_ms, ppm_mean, (double)ppm_radius);
         return 0;
     } catch (const crv::Error& e) {
         std::fprintf(stderr, "crv_headless: error %d: %s\n", e.code(), e.what());

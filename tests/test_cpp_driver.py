@@ -54,3 +54,45 @@ def test_cpp_driver_matches_the_python_host_bitwise(crv, ctx):
     img = np.ascontiguousarray(r.resultImage.download(), np.float32)
     assert _fnv1a(img.tobytes()) == out[False]["image_fnv1a"]
     r.close()
+
+
+@pytest.mark.gpu
+def test_cpp_driver_photon_mapping_frames_match_the_python_host(crv, ctx):
+    """--ppm N: crv::RenderTechniquePPM (include/crv/render_technique.h) driven like main.cpp:204-207/813 over the scene
+    crv_headless already holds.  Photon slots are claimed with atomics, so two runs are not bit-identical (PPM_PT.comp's own
+    property); the frame mean, the radius schedule (RenderTechniquePPM.cpp:302-312) and finiteness are what is compared
+    against the Python mirror of the same class."""
+    n, w, h, nsv, frames = 40, 96, 64, 56, 4
+    r = _run(["--fbm", n, "--width", w, "--height", h, "--nsv", nsv, "--spp", 1, "--g", 0.85, "--absorption", 0.1, "--ppm", frames])
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out["ppm_frames"] == frames and out["ppm_frame_ms"] > 0 and np.isfinite(out["ppm_image_mean"]) and out["ppm_image_mean"] > 0
+    wl = crv.Workload("t", n, w, h, 1, nsv, 50.0, 0.1, 0.85)
+    rr = crv.make_renderer(ctx, wl, cloud_layout="brick")
+    rr.set_cloud_synthetic(n, 1234)
+    pm = crv.PhotonMapProperties()
+    pm.SetBounds(rr.cloudProperties.bounds)
+    for i in range(4):
+        pm.lightDirection[i] = rr.shadowVolumeProperties.lightDirection[i]
+    pc = crv.PushConstants()
+    img = crv.Image(ctx, w, h)
+    ppm = crv.RenderTechniquePPM(ctx, pm, pc, 10.0)
+    ppm.AllocateResources()
+    ppm.SetFrameReferences([img])
+    ppm.QueueUpdateCloudData(rr.cloudProperties)
+    ppm.QueueUpdateCloudDataSampler(rr.cloudImage)
+    ppm.QueueUpdateParameters(rr.parameters)
+    ppm.QueueUpdateCameraProperties(rr.cameraProperties)
+    ppm.QueueUpdateShadowVolume(rr.shadowVolumeProperties)
+    ppm.QueueUpdateShadowVolumeSampler(rr.shadowVolumeImage)
+    ppm.UpdateDescriptorSets()
+    seeds = crv.msvc_rand_sequence(frames)
+    for f in range(frames):
+        pc.seed, pc.frameCount = int(seeds[f]), f
+        ppm.RecordDrawCommands(0, 0)
+    mean = float(img.download().astype(np.float64).mean())
+    assert abs(pc.pmRadius - out["ppm_radius"]) <= 1e-6 * pc.pmRadius
+    assert abs(mean - out["ppm_image_mean"]) <= 2e-3 * mean, (mean, out["ppm_image_mean"])
+    ppm.close()
+    img.close()
+    rr.close()
