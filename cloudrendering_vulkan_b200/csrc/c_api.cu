@@ -133,7 +133,7 @@ struct crv_pt {
     // tuning
     int ctas_per_sm = 0;
     int track_threshold = 20;
-    int steps_per_decision = 6;
+    int steps_per_decision = 0;        // 0 = the scheduler's own default (pool: its unrolled round; lanes: 6)
     int scheduler = CRV_PT_SCHED_POOL;
     uint64_t sample_budget = 2ull << 30;
 };
@@ -1509,7 +1509,8 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
     c.job_counter = pt->job_counter;
     c.stats = pt->stats;
     c.track_threshold = pt->track_threshold;
-    c.steps_per_decision = pt->steps_per_decision;
+    c.steps_per_decision = pt->steps_per_decision > 0 ? pt->steps_per_decision
+                         : (pt->scheduler == CRV_PT_SCHED_POOL ? crv_pt_pool_round_steps() : 6);
     c.scheduler = pt->scheduler;
     return CRV_OK;
 }
