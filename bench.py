@@ -277,9 +277,10 @@ def run_ours(args, wl):
     r.resultImage.close()
     r.resultImage = img
     r.pathTracingTechnique.SetFrameReferences([img])
-    if args.track_threshold or args.ctas_per_sm or args.steps_per_decision:
+    if args.track_threshold or args.ctas_per_sm or args.steps_per_decision or args.sample_buffer_mib:
         r.pathTracingTechnique.SetTuning(ctas_per_sm=args.ctas_per_sm, track_threshold=args.track_threshold,
-                                         steps_per_decision=args.steps_per_decision)
+                                         steps_per_decision=args.steps_per_decision,
+                                         sample_buffer_bytes=args.sample_buffer_mib << 20)
     r.pathTracingTechnique.SetScheduler(args.scheduler)
     r.set_cloud_synthetic(wl.n_cloud, wl.fbm_seed, stream)
     ctx.synchronize(stream)
@@ -567,6 +568,7 @@ def main():
     ap.add_argument("--track-threshold", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--steps-per-decision", type=int, default=0)
+    ap.add_argument("--sample-buffer-mib", type=int, default=0, help="sample-record buffer of the tracker (0 = library default)")
     ap.add_argument("--math", default="driver", choices=["strict", "driver"],
                     help="free-flight update t += -log(zeta)/sigma: 'strict' = logf-accurate log, IEEE divide, IEEE add; "
                          "'driver' = lg2 on the SFU * (-ln2/sigma) in one FMA, the latitude GLSL gives a Vulkan driver "

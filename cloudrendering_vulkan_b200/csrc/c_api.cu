@@ -135,7 +135,7 @@ struct crv_pt {
     int track_threshold = 20;
     int steps_per_decision = 0;        // 0 = the scheduler's own default (pool: its unrolled round; lanes: 6)
     int scheduler = CRV_PT_SCHED_POOL;
-    uint64_t sample_budget = 2ull << 30;
+    uint64_t sample_budget = 6ull << 30;   // c2 (1080p, 256 frames) in one launch: every launch ends in a tail of ~0.1 ms
 };
 
 // volumes carry an upload generation so cached q-tables notice re-uploads
