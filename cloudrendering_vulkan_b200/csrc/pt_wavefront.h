@@ -87,7 +87,7 @@ struct PTConst {
     uint32_t* dbg_collisions;
     int scheduler;                     // CRV_PT_SCHED_POOL (default) or CRV_PT_SCHED_LANES
     int track_threshold;               // LANES: service collisions/regeneration once fewer lanes than this are tracking
-    int steps_per_decision;            // tracking steps between two scheduling decisions (POOL: steps per tracking round)
+    int steps_per_decision;            // LANES scheduler: tracking steps between two scheduling decisions (the POOL round is compile-time: crv_pt_pool_round_steps)
 };
 
 struct FoldConst {
@@ -111,7 +111,7 @@ int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_rcp_frames(crv_ctx* ctx, float* rcp, uint32_t first_frame_count, uint32_t n, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
 int crv_launch_qcoarse(crv_ctx* ctx, const float* absmax_wide, uint8_t* qc, int nbx, int nby, int nbz, int shift, float max_ext, cudaStream_t s);
-int crv_pt_pool_round_steps();     // tracking steps of the pool scheduler's unrolled round (its default steps_per_decision)
+int crv_pt_pool_round_steps();     // tracking steps of the pool scheduler's unrolled round
 int crv_pt_pool_smem_budget();     // bytes of shared memory the pool scheduler leaves for the coarse table
 int crv_launch_qtable_padded(crv_ctx* ctx, const float* absmax_wide, float* qpad, int nbx, int nby, int nbz, float max_ext, cudaStream_t s);
 int crv_launch_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t w, uint32_t h, uint32_t n_draws, uint32_t* d_out, cudaStream_t s);

@@ -306,7 +306,8 @@ int  crv_pt_rng_tap(crv_ctx* ctx, int32_t seed, uint32_t width, uint32_t height,
  * logf for EVERY float of that set; returns the number of inputs whose results differ in any bit (expected 0). */
 int  crv_pt_selftest_log(crv_ctx* ctx, uint64_t* mismatches, void* stream);
 /* tuning knobs (0 = library default): CTAs per SM, min tracking lanes before servicing, max
- * bytes of the per-round sample buffer, tracking steps between two scheduling decisions */
+ * bytes of the per-round sample buffer, tracking steps between two scheduling decisions (lanes scheduler only: the
+ * pool scheduler's round is unrolled at compile time) */
 int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes, int steps_per_decision);
 /* which persistent-thread scheduler runs the tracker (identical results, bit for bit):
  *   0 = pool  (default) every warp owns 128 paths in shared memory and runs one kind of work at a time on 32 of them
