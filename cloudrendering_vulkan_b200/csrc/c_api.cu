@@ -1572,7 +1572,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         pt->hitlist_elems = 0;
         pt->geom_valid = false;
         CRV_CUDA(cudaMalloc(&pt->hitlist, sizeof(uint32_t) * c.npix));
-        CRV_CUDA(cudaMalloc(&pt->start, sizeof(float) * 7 * (size_t)c.npix));
+        CRV_CUDA(cudaMalloc(&pt->start, sizeof(float) * 8 * (size_t)c.npix));
         CRV_CUDA(cudaMalloc(&pt->misslist, sizeof(uint32_t) * c.npix));
         CRV_CUDA(cudaMalloc(&pt->missdy, sizeof(float) * c.npix));
         pt->hitlist_elems = c.npix;
