@@ -22,7 +22,7 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:pt_
     python bench.py --spp 16 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_pt.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sv_ -s 8 -c 2 -f -o $OUT/${TAG}_sv \
     python bench.py --spp 1 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_sv.log 2>&1
-# DRAM bytes of ONE tracker launch of the default bench step (128 frames per launch): the `traffic` of bench.py's roofline
+# DRAM bytes of ONE tracker launch of the default bench step (256 frames per launch): the `traffic` of bench.py's roofline
 timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__inst_executed.avg.per_cycle_elapsed,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:pt_wavefront -s 2 -c 1 --csv \
     --log-file $OUT/${TAG}_pt_traffic.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_traffic.log 2>&1
 ls -la $OUT

@@ -184,7 +184,7 @@ def traffic(path):
         elif r[ni] == "smsp__issue_active.avg.pct_of_peak_sustained_active":
             extra["issue_active_pct"] = float(r[vi].replace(",", ""))
     print(json.dumps({"pt_wavefront_kernel_bytes_per_launch": tot, **extra, "kernel": kernel, "launch_duration_under_ncu": dur,
-                      "source": path, "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one 128-frame "
+                      "source": path, "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one 256-frame "
                                              "launch of the default bench.py step"}))
 
 
