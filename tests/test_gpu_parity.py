@@ -576,3 +576,32 @@ def test_more_frames_than_one_launch_carries(crv, orc, ctx):
         r.render(75, seeds=seeds[f:f + 75])
     assert np.array_equal(_bits(a), _bits(r.resultImage.download()))
     r.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["brick", "linear"])
+@pytest.mark.parametrize("n", [40, 44, 42])
+def test_upload_path_builds_the_same_skip_tables(crv, ctx, layout, n):
+    """the separable upload pass (four voxels per thread when nx % 4 == 0, one otherwise) against the per-brick gather kernels
+    the device generator uses: same image bits AND the same fetch counter -- a fetch happens exactly when a table entry
+    fails to reject, so equal counters over thousands of lookups mean equal tables where it matters"""
+    w, h, spp = 96, 64, 4
+    wl = crv.Workload("t", n, w, h, spp, 56, 50.0, 0.1, 0.85)
+    seeds = crv.msvc_rand_sequence(spp)
+    out = []
+    host = None
+    for upload in (False, True):
+        r = crv.make_renderer(ctx, wl, cloud_layout=layout)
+        if upload:
+            r.set_cloud_host(host, (n, n, n), (1.0 / n,) * 3)
+        else:
+            r.set_cloud_synthetic(n, 1234)
+            host = r.cloudImage.download().copy()
+        r.pathTracingTechnique.ResetStats()
+        r.pathTracingTechnique.RenderBatch(seeds, 0, crv.ACCUM_RUNNING_MEAN, 0, 0)
+        st = r.pathTracingTechnique.GetStats()
+        out.append((r.resultImage.download().copy(), int(st.tracking_steps), int(st.collisions), int(st.density_fetches)))
+        r.close()
+    assert np.array_equal(_bits(out[0][0]), _bits(out[1][0]))
+    assert out[0][1:] == out[1][1:], (out[0][1:], out[1][1:])
+    assert out[0][3] > 0
