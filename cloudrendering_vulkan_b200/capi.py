@@ -76,7 +76,7 @@ class PTExtensionsPOD(C.Structure):
 
 class PTStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("tracking_steps", C.c_uint64), ("collisions", C.c_uint64),
-                ("density_fetches", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("density_fetches", C.c_uint64), ("kernel_launches", C.c_uint64), ("tracked_paths", C.c_uint64)]
 
 
 assert C.sizeof(PushConstantsPOD) == 24
@@ -155,6 +155,7 @@ SIGNATURES = {
     "crv_pt_rng_tap": (C.c_int, [_vp, _i32, _u32, _u32, _u32, _vp, _vp]),
     "crv_pt_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "crv_pt_set_scheduler": (C.c_int, [_vp, C.c_int]),
+    "crv_pt_set_skip_level": (C.c_int, [_vp, C.c_int]),
     "crv_ppm_create": (C.c_int, [_vp, _P(PhotonMapPropertiesPOD), _P(PushConstantsPOD), C.c_float, _P(_vp)]),
     "crv_ppm_set_frame_references": (C.c_int, [_vp, _P(_vp), C.c_uint]),
     "crv_ppm_queue_update_camera_properties": (C.c_int, [_vp, _P(CameraPropertiesPOD)]),

@@ -103,12 +103,17 @@ struct crv_pt {
     uint32_t* misslist = nullptr;      // pixels whose camera ray misses the box
     float* missdy = nullptr;           // dir.y of those rays
     // the classification depends on the camera and the cloud box only: kept across render calls while those bytes stand
+    // ... and, through the occupied spans, on the cloud image's contents and the skip level
     bool geom_valid = false;
-    unsigned char geom_key[68 + 32 + 4] = {};
+    unsigned char geom_key[68 + 32 + 4 + 8 + 8 + 4 + 4] = {};
+    int* occ_ext = nullptr;            // brick-index extremes of the occupied bricks (6 ints)
+    float* occ_aabb = nullptr;         // world-space box around them (6 floats), PTConst::occ_aabb
+    int skip_level = 1;                // crv_pt_set_skip_level
     // q-table cache
     float* qtable_wide = nullptr;
     float* qtable = nullptr;
     size_t qtable_elems = 0;
+    uint32_t q_dims[3] = {0, 0, 0};   // brick counts per axis the tables were sized for
     uint8_t* qcoarse = nullptr;       // pool scheduler: byte thresholds per coarse cell (shared-memory resident)
     uint32_t qcoarse_bytes = 0;       // padded to 16
     int qcoarse_shift = 0;            // coarse cell = (8 << shift)^3 voxels
@@ -801,6 +806,8 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
     pt->sets.resize(1);
     CRV_CUDA(cudaMalloc(&pt->job_counter, sizeof(unsigned int)));
     CRV_CUDA(cudaMalloc(&pt->nhit, 2 * sizeof(uint32_t)));      // [0] hits, [1] misses
+    CRV_CUDA(cudaMalloc(&pt->occ_ext, 6 * sizeof(int)));
+    CRV_CUDA(cudaMalloc(&pt->occ_aabb, 6 * sizeof(float)));
     CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
     CRV_CUDA(cudaMemset(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT));
     *out = pt;
@@ -879,6 +886,7 @@ struct crv_ppm {
     unsigned long long cells = 0;
     float* qtable = nullptr;
     size_t qtable_elems = 0;
+    uint32_t q_dims[3] = {0, 0, 0};   // brick counts per axis the tables were sized for
     uint8_t* qcoarse = nullptr;               // shared-memory threshold table, like the path tracer's
     uint32_t qcoarse_bytes = 0;
     int qcoarse_shift = 0;
@@ -1247,6 +1255,8 @@ int crv_pt_destroy(crv_pt* pt)
     if (pt->hitlist) cudaFree(pt->hitlist);
     if (pt->start) cudaFree(pt->start);
     if (pt->nhit) cudaFree(pt->nhit);
+    if (pt->occ_ext) cudaFree(pt->occ_ext);
+    if (pt->occ_aabb) cudaFree(pt->occ_aabb);
     if (pt->misslist) cudaFree(pt->misslist);
     if (pt->missdy) cudaFree(pt->missdy);
     if (pt->samples) cudaFree(pt->samples);
@@ -1359,6 +1369,14 @@ int crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t
     return CRV_OK;
 }
 
+int crv_pt_set_skip_level(crv_pt* pt, int level)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_set_skip_level: null technique");
+    CRV_REQUIRE(level == 0 || level == 1, "crv_pt_set_skip_level: level must be 0 or 1");
+    pt->skip_level = level;
+    return CRV_OK;
+}
+
 int crv_pt_set_scheduler(crv_pt* pt, int scheduler)
 {
     CRV_REQUIRE(pt != nullptr, "crv_pt_set_scheduler: null technique");
@@ -1438,8 +1456,10 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
     crv_volume* cv = b.cloud_vol;
     const size_t nbricks = (size_t)cv->nbx * cv->nby * cv->nbz;
     if (!cv->brick_max_valid) CRV_TRY(crv_launch_brick_max(pt->ctx, cv, s));
-    if (pt->q_for_vol != cv || pt->q_for_generation != vol_generation(cv) || pt->q_for_max_ext != c.max_ext || pt->qtable_elems != nbricks) {
-        if (pt->qtable_elems != nbricks) {
+    // (the padded tables and the coarse cell size depend on the three brick counts separately, not on their product)
+    const bool same_dims = pt->qtable_elems == nbricks && pt->q_dims[0] == cv->nbx && pt->q_dims[1] == cv->nby && pt->q_dims[2] == cv->nbz;
+    if (pt->q_for_vol != cv || pt->q_for_generation != vol_generation(cv) || pt->q_for_max_ext != c.max_ext || !same_dims) {
+        if (!same_dims) {
             if (pt->qtable) CRV_CUDA(cudaFree(pt->qtable));
             if (pt->qtable_wide) CRV_CUDA(cudaFree(pt->qtable_wide));
             if (pt->qcoarse) CRV_CUDA(cudaFree(pt->qcoarse));
@@ -1452,6 +1472,7 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             coarse_table_shape(cv, pt->qcoarse_shift, pt->qcoarse_bytes);
             CRV_CUDA(cudaMalloc(&pt->qcoarse, pt->qcoarse_bytes));
             pt->qtable_elems = nbricks;
+            pt->q_dims[0] = cv->nbx; pt->q_dims[1] = cv->nby; pt->q_dims[2] = cv->nbz;
         }
         CRV_CUDA(cudaMemsetAsync(pt->qcoarse, 128, pt->qcoarse_bytes, s));
         CRV_TRY(crv_launch_qcoarse(pt->ctx, cv->brick_absmax_wide, pt->qcoarse, (int)cv->nbx, (int)cv->nby, (int)cv->nbz, pt->qcoarse_shift, c.max_ext, s));
@@ -1491,6 +1512,19 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             c.aof8[i] = (float)(of / 8.0 + 1.0);
         }
         coarse_pretest_geometry(c, pt->qcoarse_shift);  // pool scheduler: cell coordinate, strides, bias; decides c.use_wide
+        // occupied spans (pt_classify_kernel): exact-in-spirit brick coordinate; only where the fp32 error bound above holds
+        float min_texel = 3.0e38f;
+        for (int i = 0; i < 3; ++i) {
+            const double n = i == 0 ? c.cloud.nx : i == 1 ? c.cloud.ny : c.cloud.nz;
+            const double sc = n / (double)c.cext[i], of = -(double)c.cb0[i] * sc - 0.5;
+            c.bsc[i] = (float)(sc / 8.0);
+            c.bof[i] = (float)(of / 8.0);
+            min_texel = std::fmin(min_texel, (float)std::fabs((double)c.cext[i] / n));
+        }
+        c.span_margin = 0.25f * min_texel;
+        c.occ_wide = c.use_wide ? cv->brick_absmax_wide : nullptr;
+        c.occ_aabb = pt->occ_aabb;
+        c.skip_level = (c.use_wide && pt->skip_level > 0) ? 1 : 0;
         c.pnbx = (uint32_t)c.cloud.nbx + 2u;
         c.pnbxy = c.pnbx * ((uint32_t)c.cloud.nby + 2u);
         c.pbias = 0x4B000000u * (1u + c.pnbx + c.pnbxy);          // mod 2^32, like the device-side sum it cancels
@@ -1553,6 +1587,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         }
         c.dbg_steps = pt->dbg_steps;
         c.dbg_collisions = pt->dbg_coll;
+        c.skip_level = 0;              // the per-pixel counters are the reference's: every step is executed
         // the pool scheduler accumulates per-path counts round by round
         CRV_CUDA(cudaMemsetAsync(pt->dbg_steps, 0, sizeof(uint32_t) * c.npix, s));
         CRV_CUDA(cudaMemsetAsync(pt->dbg_coll, 0, sizeof(uint32_t) * c.npix, s));
@@ -1600,9 +1635,18 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         std::memcpy(key + 68, b.cloud.bounds, 32);
         const uint32_t off = b.cloud.densityScaling <= 0.0f ? 1u : 0u;
         std::memcpy(key + 100, &off, 4);
+        const uint64_t vol_id = (uint64_t)(uintptr_t)b.cloud_vol, vol_gen = vol_generation(b.cloud_vol);
+        const int32_t lvl = c.skip_level, spans = c.occ_wide != nullptr;
+        std::memcpy(key + 104, &vol_id, 8);
+        std::memcpy(key + 112, &vol_gen, 8);
+        std::memcpy(key + 120, &lvl, 4);
+        std::memcpy(key + 124, &spans, 4);
         if (!pt->geom_valid || std::memcmp(key, pt->geom_key, sizeof(key)) != 0) {
             CRV_CUDA(cudaMemsetAsync(pt->nhit, 0, 2 * sizeof(uint32_t), s));
             CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
+            if (c.occ_wide)
+                CRV_TRY(crv_launch_occ_aabb(pt->ctx, c.occ_wide, c.cloud.nbx, c.cloud.nby, c.cloud.nbz, pt->occ_ext, pt->occ_aabb, c.cb0, c.cext,
+                                            c.cloud.nx, c.cloud.ny, c.cloud.nz, s));
             CRV_TRY(crv_launch_classify(pt->ctx, c, pt->hitlist, pt->start, pt->nhit, pt->misslist, pt->missdy, s));
             pt->launches++;
             std::memcpy(pt->geom_key, key, sizeof(key));
@@ -1685,6 +1729,7 @@ int crv_pt_get_stats(crv_pt* pt, crv_pt_stats* out, void* stream)
     out->collisions = h[PT_STAT_COLLISIONS];
     out->density_fetches = h[PT_STAT_FETCHES];
     out->kernel_launches = pt->launches;
+    out->tracked_paths = h[PT_STAT_TRACKED];
     return CRV_OK;
 }
 

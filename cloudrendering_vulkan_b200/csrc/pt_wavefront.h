@@ -4,7 +4,7 @@
 
 // stats slots (u64 each)
 enum { CRV_PT_SCHED_POOL = 0, CRV_PT_SCHED_LANES = 1 };
-enum { PT_STAT_PATHS = 0, PT_STAT_STEPS = 1, PT_STAT_COLLISIONS = 2, PT_STAT_FETCHES = 3, PT_STAT_COUNT = 4 };
+enum { PT_STAT_PATHS = 0, PT_STAT_STEPS = 1, PT_STAT_COLLISIONS = 2, PT_STAT_FETCHES = 3, PT_STAT_TRACKED = 4, PT_STAT_COUNT = 5 };
 
 constexpr int PT_MAX_FRAMES_PER_LAUNCH = 256;
 constexpr int PT_THREADS = 256;
@@ -66,9 +66,23 @@ struct PTConst {
     uint32_t qcoarse_bytes;            // padded cell count + 1 (the last byte, 128 = never reject, is the disabled-test target)
     float ascc[3], aofc[3];            // approximate padded CELL coordinate, like asc8/aof8
     uint32_t cnx, cnxy, cbias, cmax;   // like pnbx/pnbxy/pbias/pmax for the coarse table
-    const uint32_t* hitlist;           // pixels whose camera ray enters the box (pt_classify_kernel), x | y << 16, *nhit entries
+    const uint32_t* hitlist;           // pixels whose path has to be tracked (pt_classify_kernel), x | y << 16, *nhit entries
     const uint32_t* nhit;
-    const float* start;                // per hit pixel, SoA with stride npix: entry point xyz, direction xyz, exit distance
+    const float* start;                // per tracked pixel, 32 bytes: entry point xyz, direction xyz, `lim`, `t_lo` (below)
+
+    // ---- occupancy spans (proof-based skipping of whole ray sections; see pt_classify_kernel) ----
+    // A brick b is OCCUPIED when occ_wide[b] != 0, i.e. some voxel of [8b-1, 8b+9]^3 is not +-0.  A sample position whose
+    // brick (and that within one texel) is unoccupied blends eight zeros: ext == +-0 and the shader's acceptance test
+    // `xi < ext / maxExt` (:351) is false for every draw.  So the part of a segment before its first occupied brick
+    // (t < t_lo) only advances the RNG and t, and once a segment is past its last occupied brick (t >= lim) the path is
+    // certain to leave the box without another collision: its sample is final.
+    const float* occ_wide;             // == cloud volume's brick_absmax_wide (nbx*nby*nbz)
+    const float* occ_aabb;             // device, 6 floats: world-space box around all occupied bricks (lo xyz, hi xyz), one
+                                       // texel of margin; lo = +inf / hi = -inf when nothing is occupied
+    float bsc[3], bof[3];              // brick coordinate of a point: v = q*bsc + bof = ((q - cb0)/cext * n - 0.5) / 8
+    float span_margin;                 // safety margin of t_lo / lim in world units (a quarter texel)
+    int skip_level;                    // 0: every step of the reference is executed (counters equal the oracle's);
+                                       // 1: rays that meet no occupied brick are background pixels, segments end at `lim`
 
     // ---- job description ----
     uint32_t npix;                     // width*height
@@ -108,6 +122,8 @@ struct FoldConst {
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
 int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t* hitlist, float* start, uint32_t* counts, uint32_t* misslist, float* missdy, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
+int crv_launch_occ_aabb(crv_ctx* ctx, const float* wide, int nbx, int nby, int nbz, int* ext6, float* aabb6, const float* b0, const float* extent,
+                        int nx, int ny, int nz, cudaStream_t s);
 int crv_launch_rcp_frames(crv_ctx* ctx, float* rcp, uint32_t first_frame_count, uint32_t n, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
 int crv_launch_qcoarse(crv_ctx* ctx, const float* absmax_wide, uint8_t* qc, int nbx, int nby, int nbz, int shift, float max_ext, cudaStream_t s);

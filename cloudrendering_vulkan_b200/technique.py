@@ -386,6 +386,11 @@ class RenderTechniquePT(RenderTechnique):
         """which persistent-thread scheduler runs the tracker; both produce the same bits"""
         check(lib.crv_pt_set_scheduler(self.handle, self.SCHEDULERS[scheduler] if isinstance(scheduler, str) else int(scheduler)))
 
+    def SetSkipLevel(self, level: int = 1):
+        """1 (default): ray sections that provably cannot collide are not tracked (same image bits);
+        0: every step of the reference is executed, so the statistics count the reference's work"""
+        check(lib.crv_pt_set_skip_level(self.handle, int(level)))
+
     def close(self):
         if self.handle:
             lib.crv_pt_destroy(self.handle)

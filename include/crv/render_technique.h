@@ -304,6 +304,8 @@ public:
     void ResetStats(CommandStream stream = nullptr) { Check(crv_pt_reset_stats(m_pt, stream)); }
     // 0 = pool scheduler (default), 1 = lane-owned scheduler; identical results
     void SetScheduler(int scheduler) { Check(crv_pt_set_scheduler(m_pt, scheduler)); }
+    // 1 (default): ray sections that provably cannot collide are not tracked; 0: every step of the reference is executed
+    void SetSkipLevel(int level) { Check(crv_pt_set_skip_level(m_pt, level)); }
     float LastRenderMs(unsigned* launches = nullptr)
     {
         float ms = 0.0f;

@@ -190,6 +190,9 @@ typedef struct crv_pt_stats {
     uint64_t collisions;       /* real collisions                                              */
     uint64_t density_fetches;  /* trilinear cloud fetches actually issued (rest proven empty)  */
     uint64_t kernel_launches;  /* kernels launched by this technique since creation            */
+    uint64_t tracked_paths;    /* of `paths`: those that went through the tracker; the others are camera rays that miss
+                                  the cloud box or (skip level 1) cross it without meeting an occupied brick, whose sample
+                                  is sampleBackground(dir) whatever their random numbers are                              */
 } crv_pt_stats;
 
 /* ---- library / context ------------------------------------------------------------------ */
@@ -309,6 +312,15 @@ int  crv_pt_selftest_log(crv_ctx* ctx, uint64_t* mismatches, void* stream);
  * bytes of the per-round sample buffer, tracking steps between two scheduling decisions (lanes scheduler only: the
  * pool scheduler's round is unrolled at compile time) */
 int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_t sample_buffer_bytes, int steps_per_decision);
+/* Proof-based skipping of ray sections that cannot collide (identical images, bit for bit; default 1):
+ *   1  a brick of 8^3 voxels whose texels (and the ring of texels around it) are all zero cannot produce a collision: every
+ *      tentative collision of PathTracer.comp:335-355 inside it is rejected whatever the random numbers are.  Camera rays
+ *      that cross the cloud box through such bricks only become background pixels; a segment is tracked up to its last
+ *      occupied brick only (the path's sample is final there); the stretch in front of the first occupied brick advances
+ *      the RNG and t without table lookups.  crv_pt_stats.tracking_steps then counts the steps that were executed.
+ *   0  every step the reference executes is executed (the stretch in front of the first occupied brick still without
+ *      lookups): tracking_steps / collisions and the debug counters equal the reference's.  The debug counters force 0. */
+int  crv_pt_set_skip_level(crv_pt* pt, int level);
 /* which persistent-thread scheduler runs the tracker (identical results, bit for bit):
  *   0 = pool  (default) every warp owns 128 paths in shared memory and runs one kind of work at a time on 32 of them
  *   1 = lanes every lane owns one path plus one in reserve (kept for A/B measurements) */

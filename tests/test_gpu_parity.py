@@ -381,6 +381,7 @@ def test_converged_image_within_noise(crv, orc, ctx):
 def test_stats_match_oracle_counters(crv, orc, ctx):
     r, cloud = make_scene(crv, orc, ctx, n=32, w=64, h=48, nsv=40, g=None)
     sv_cpu = orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties)
+    r.pathTracingTechnique.SetSkipLevel(0)         # count the reference's work: every step executed
     r.pathTracingTechnique.ResetStats()
     r.pushConstants.seed = 38
     r.pathTracingTechnique.RecordDrawCommands(0, 0)
@@ -394,6 +395,72 @@ def test_stats_match_oracle_counters(crv, orc, ctx):
     assert abs(int(st.collisions) - int(cc.sum())) <= 0.02 * cc.sum() + 2
     assert 0 < st.density_fetches < st.tracking_steps, "the brick-max skip must remove fetches (and not all of them)"
     r.close()
+
+
+SKIP_SCENES = {
+    # name: make_scene kwargs
+    "iso": dict(g=None),
+    "hg_absorbing": dict(g=0.85, absorption=0.1),
+    "back_scatter": dict(g=-0.4, absorption=0.3, light=(0.3, -0.8, 0.5)),
+    "dense": dict(g=0.85, absorption=0.01, density_scaling=200.0),
+    "ragged": dict(n=44, w=100, h=70, g=0.85, absorption=0.05),
+}
+
+
+@pytest.mark.parametrize("sched", ["pool", "lanes"])
+@pytest.mark.parametrize("layout", ["brick", "linear"])
+@pytest.mark.parametrize("name", sorted(SKIP_SCENES))
+def test_skip_levels_are_bit_identical(crv, orc, ctx, name, layout, sched):
+    """crv_pt_set_skip_level: background pixels for rays through empty bricks, segments cut at their last occupied brick
+    and the lookup-free stretch in front of the first one must not change a single bit of the image, in either math mode"""
+    for math in [crv.PT_MATH_STRICT, crv.PT_MATH_DRIVER]:
+        imgs, stats = [], []
+        for level in (0, 1):
+            r, _ = make_scene(crv, orc, ctx, layout=layout, **SKIP_SCENES[name])
+            r.extensions.math_mode = math
+            r.apply_parameters()
+            pt = r.pathTracingTechnique
+            pt.SetScheduler(sched)
+            pt.SetSkipLevel(level)
+            pt.ResetStats()
+            r.render(7)
+            imgs.append(r.resultImage.download().copy())
+            stats.append(pt.GetStats())
+            r.close()
+        assert np.array_equal(_bits(imgs[0]), _bits(imgs[1])), f"skip level changed the image ({name}, math {math})"
+        full, fast = stats
+        assert full.paths == fast.paths
+        assert fast.collisions == full.collisions, "skipping must not lose a collision"
+        assert fast.tracked_paths < full.tracked_paths, "the scene must contain rays that cross the box through empty bricks"
+        assert fast.tracking_steps < full.tracking_steps
+        print(f"{name}/{layout}/{sched}/math{math}: tracked {fast.tracked_paths}/{full.tracked_paths} paths, "
+              f"steps {fast.tracking_steps}/{full.tracking_steps}")
+
+
+def test_skip_level_camera_inside_and_sparse_cloud(crv, orc, ctx):
+    """occupied spans with the camera inside the box (segments start at t_min < 0 behind the camera) and with a cloud that
+    occupies a single brick far from the box centre; also a re-upload must re-classify (spans depend on the contents)"""
+    n = 40
+    cloud = orc.fbm_generate(n, 1234)
+    for level_imgs in [[]]:
+        for level in (0, 1):
+            r, _ = make_scene(crv, orc, ctx, layout="brick", g=0.85, absorption=0.05, cloud=cloud)
+            r.cameraProperties.position[2] = 300.0          # inside the box
+            r.apply_parameters()
+            r.pathTracingTechnique.SetSkipLevel(level)
+            r.render(5)
+            level_imgs.append(r.resultImage.download().copy())
+            # sparse contents through the same technique object: one occupied corner brick
+            sparse = np.zeros((n, n, n), np.float32)
+            sparse[2:6, 30:34, 33:37] = 0.8
+            r.set_cloud_host(sparse.ravel(), (n, n, n), (1.0 / n,) * 3)
+            r.reset_accumulation()
+            r.render(5)
+            level_imgs.append(r.resultImage.download().copy())
+            r.close()
+        assert np.array_equal(_bits(level_imgs[0]), _bits(level_imgs[2]))
+        assert np.array_equal(_bits(level_imgs[1]), _bits(level_imgs[3]))
+        assert not np.array_equal(level_imgs[0], level_imgs[1]), "the re-uploaded cloud must change the image"
 
 
 # ---------------------------------------------------------------------------------------------------------
