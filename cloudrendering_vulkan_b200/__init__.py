@@ -10,12 +10,12 @@ from .capi import PT_MATH_DRIVER, PT_MATH_STRICT, ACCUM_RUNNING_MEAN, ACCUM_SUM,
 from .scene import CONFIGS, HeadlessRenderer, Workload, make_renderer
 from .structs import (CameraProperties, CloudProperties, Grid3D, Parameters, PathTracerExtensions, PhotonMapProperties, PushConstants,
                       ShadowVolumeProperties, msvc_rand_sequence, orthonormal_basis)
-from .technique import Context, Image, RenderTechnique, RenderTechniquePPM, RenderTechniquePT, RenderTechniqueSV, Volume, rng_tap
+from .technique import Context, Group, Image, Stream, RenderTechnique, RenderTechniquePPM, RenderTechniquePT, RenderTechniqueSV, Volume, rng_tap
 
 __all__ = [
     "capi", "CrvError", "ACCUM_RUNNING_MEAN", "ACCUM_SUM", "PT_MATH_STRICT", "PT_MATH_DRIVER", "LAYOUT_LINEAR", "LAYOUT_BRICK", "LAYOUT_TEX3D",
     "CONFIGS", "HeadlessRenderer", "Workload", "make_renderer",
     "CameraProperties", "CloudProperties", "Grid3D", "Parameters", "PathTracerExtensions", "PhotonMapProperties", "PushConstants",
     "ShadowVolumeProperties", "msvc_rand_sequence", "orthonormal_basis",
-    "Context", "Image", "RenderTechnique", "RenderTechniquePPM", "RenderTechniquePT", "RenderTechniqueSV", "Volume", "rng_tap",
+    "Context", "Group", "Image", "Stream", "RenderTechnique", "RenderTechniquePPM", "RenderTechniquePT", "RenderTechniqueSV", "Volume", "rng_tap",
 ]

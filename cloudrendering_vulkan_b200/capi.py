@@ -79,6 +79,12 @@ class PTStats(C.Structure):
                 ("density_fetches", C.c_uint64), ("kernel_launches", C.c_uint64), ("tracked_paths", C.c_uint64)]
 
 
+class GroupHandle(C.Structure):
+    _fields_ = [("pid", C.c_uint64), ("device", C.c_int32), ("rank", C.c_uint32), ("base", C.c_uint64), ("bytes", C.c_uint64),
+                ("ipc", C.c_ubyte * 64)]
+
+
+assert C.sizeof(GroupHandle) == 96
 assert C.sizeof(PushConstantsPOD) == 24
 assert C.sizeof(CameraPropertiesPOD) == 68
 assert C.sizeof(CloudPropertiesPOD) == 60
@@ -102,6 +108,20 @@ SIGNATURES = {
     "crv_ctx_synchronize": (C.c_int, [_vp, _vp]),
     "crv_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "crv_ctx_sm_count": (C.c_int, [_vp, _P(C.c_int)]),
+    "crv_stream_create": (C.c_int, [_vp, _P(_vp)]),
+    "crv_stream_destroy": (C.c_int, [_vp, _vp]),
+    "crv_group_create": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _P(_vp)]),
+    "crv_group_destroy": (C.c_int, [_vp]),
+    "crv_group_export": (C.c_int, [_vp, _P(GroupHandle)]),
+    "crv_group_connect": (C.c_int, [_vp, _P(GroupHandle), _u32]),
+    "crv_group_image": (C.c_int, [_vp, _u32, _P(_vp)]),
+    "crv_group_all_reduce_sum_scale": (C.c_int, [_vp, _u32, C.c_float, _vp]),
+    "crv_group_set_timeout_ms": (C.c_int, [_vp, _u32]),
+    "crv_group_status": (C.c_int, [_vp, _vp]),
+    "crv_group_last_reduce_ms": (C.c_int, [_vp, _P(C.c_float)]),
+    "crv_group_nccl_unique_id": (C.c_int, [_vp]),
+    "crv_group_nccl_init": (C.c_int, [_vp, _vp]),
+    "crv_group_nccl_all_reduce_sum_scale": (C.c_int, [_vp, _u32, C.c_float, _vp]),
     "crv_volume_create": (C.c_int, [_vp, _u32, _u32, _u32, C.c_int, _P(_vp)]),
     "crv_volume_destroy": (C.c_int, [_vp]),
     "crv_volume_upload": (C.c_int, [_vp, _vp, C.c_int, _vp]),

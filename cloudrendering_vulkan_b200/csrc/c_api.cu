@@ -227,6 +227,23 @@ int crv_ctx_synchronize(crv_ctx* ctx, void* stream)
     return CRV_OK;
 }
 
+int crv_stream_create(crv_ctx* ctx, void** out)
+{
+    CRV_ENTER(ctx);
+    CRV_REQUIRE(out != nullptr, "crv_stream_create: out is null");
+    cudaStream_t s = nullptr;
+    CRV_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = s;
+    return CRV_OK;
+}
+
+int crv_stream_destroy(crv_ctx* ctx, void* stream)
+{
+    CRV_ENTER(ctx);
+    if (stream) CRV_CUDA(cudaStreamDestroy(as_stream(stream)));
+    return CRV_OK;
+}
+
 int crv_ctx_launch_count(crv_ctx* ctx, uint64_t* out)
 {
     CRV_REQUIRE(ctx && out, "crv_ctx_launch_count: null argument");

@@ -1,0 +1,460 @@
+// group.cu -- the multi-GPU half of the path: the spp-split's accumulation buffers are combined and divided by
+// the sample count in ONE kernel per GPU that reads and writes its peers' memory over NVLink.
+//
+// The reference is a single-GPU program; north_star partitions its path by samples: every GPU holds a replica of the density
+// grid and the shadow volume, renders its share of the frame list into a private fp32 SUM image (CRV_ACCUM_SUM) and the
+// images are combined.  (pixel, frame) samples are independent (PathTracer.comp:368: the seed depends on the frame seed and
+// the pixel only) and the running mean (:420-424) is the only coupling, so the combination is sum / spp_total.
+//
+// crv_group: one member per GPU (one per process under torchrun, or all in one process for crv_headless --gpus N).  Every
+// member owns one cudaMalloc'd block -- a flag page followed by `nbuf` RGBA32F images, the render targets -- and maps the
+// blocks of its peers (cudaIpc between processes, peer access inside one).  crv_group_all_reduce_sum_scale launches, on every
+// member, one kernel:
+//   start barrier  every member tells every peer "my image is complete" (system-scope release store into the peer's flag page)
+//                  and waits for the same word from everybody;
+//   band reduce    member r owns rows band r (1/N of the image): it loads that band from all N images (peer loads, issued
+//                  together), adds them in rank order, multiplies by `scale` and stores the result into all N images -- a
+//                  reduce-scatter, the scale epilogue and an all-gather in one pass, 2 x 33 MB over NVLink at 1080p;
+//   end barrier    the last CTA to finish tells every peer "my band is in your image" and waits for theirs: when the kernel
+//                  completes, the member's image holds the final picture and no peer touches it before the next call.
+// The result is deterministic (fixed summation order, computed once per pixel) and identical on all members.
+// Spins carry a deadline (default 10 s, crv_group_set_timeout_ms): a member whose peer never arrives sets a sticky error that
+// crv_group_status reports, instead of hanging the GPU.
+//
+// The NCCL route north_star names is kept beside it for comparison (crv_group_nccl_*: ncclAllReduce in place through the
+// libnccl.so.2 the process has loaded, then the scale kernel); bench.py times both.
+#include <dlfcn.h>
+#include <unistd.h>
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "crv_internal.h"
+
+namespace {
+
+constexpr int GROUP_MAX = 16;
+constexpr size_t FLAG_PAGE = 4096;                 // start[16], end[16], done counter, error word
+constexpr int RED_THREADS = 512;
+
+struct GroupFlags {
+    uint32_t start[GROUP_MAX];
+    uint32_t end[GROUP_MAX];
+    uint32_t done;                                 // CTAs of the local kernel that have stored their part of the band
+    uint32_t error;                                // sticky: 1 = start barrier timed out, 2 = end barrier timed out
+};
+static_assert(sizeof(GroupFlags) <= FLAG_PAGE, "flag page");
+
+struct ReduceArgs {
+    unsigned char* peer[GROUP_MAX];                // base of every member's block (own included), in THIS device's address space
+    size_t image_offset;                           // byte offset of the image inside a block
+    uint32_t n4;                                   // float4 elements per image
+    uint32_t rank, nranks;
+    uint32_t epoch;
+    float scale;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// wait until *flag has reached `epoch` (wrap-safe); false on timeout
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch, unsigned long long timeout_ns)
+{
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+        if ((++spins & 1023u) == 0u && global_ns() - t0 > timeout_ns) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+template <int N>
+__global__ void __launch_bounds__(RED_THREADS) group_reduce_kernel(const __grid_constant__ ReduceArgs a)
+{
+    __shared__ int s_ok;
+    GroupFlags* mine = reinterpret_cast<GroupFlags*>(a.peer[a.rank]);
+    const int nr = N > 0 ? N : (int)a.nranks;
+
+    // ---- start barrier: everything this GPU rendered into its image precedes this kernel in stream order ----
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (blockIdx.x == 0 && (int)threadIdx.x < nr) {
+        __threadfence_system();
+        st_release_sys(&reinterpret_cast<GroupFlags*>(a.peer[threadIdx.x])->start[a.rank], a.epoch);
+    }
+    if ((int)threadIdx.x < nr) {
+        if (!wait_flag(&mine->start[threadIdx.x], a.epoch, a.timeout_ns)) {
+            atomicExch(&mine->error, 1u);
+            s_ok = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- band reduce: rows band `rank`, all peers' loads in flight together, fixed summation order ----
+    if (s_ok) {
+        const uint32_t per = (a.n4 + a.nranks - 1u) / a.nranks;
+        const uint32_t lo = min(a.rank * per, a.n4), hi = min(lo + per, a.n4);
+        for (uint32_t i = lo + blockIdx.x * RED_THREADS + threadIdx.x; i < hi; i += gridDim.x * RED_THREADS) {
+            float4 v[N > 0 ? N : GROUP_MAX];
+#pragma unroll
+            for (int p = 0; p < (N > 0 ? N : GROUP_MAX); ++p)
+                if (p < nr) v[p] = __ldcv(reinterpret_cast<const float4*>(a.peer[p] + a.image_offset) + i);
+            float4 s = v[0];
+#pragma unroll
+            for (int p = 1; p < (N > 0 ? N : GROUP_MAX); ++p)
+                if (p < nr) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+            s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
+#pragma unroll
+            for (int p = 0; p < (N > 0 ? N : GROUP_MAX); ++p)
+                if (p < nr) reinterpret_cast<float4*>(a.peer[p] + a.image_offset)[i] = s;
+        }
+    }
+
+    // ---- end barrier: the last CTA of this kernel speaks for all of them ----
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->done, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) mine->done = 0u;         // re-armed for the next call (nobody else touches it any more)
+    if ((int)threadIdx.x < nr) {
+        __threadfence_system();
+        st_release_sys(&reinterpret_cast<GroupFlags*>(a.peer[threadIdx.x])->end[a.rank], a.epoch);
+        if (!wait_flag(&mine->end[threadIdx.x], a.epoch, a.timeout_ns)) atomicExch(&mine->error, 2u);
+    }
+}
+
+__global__ void group_scale_kernel(float4* __restrict__ img, uint32_t n4, float scale)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 v = img[i];
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        img[i] = v;
+    }
+}
+
+// ---- NCCL through the library the process has loaded (no link-time dependency) ------------------------------------------
+struct Id128 { char b[128]; };                     // ncclUniqueId, passed by value
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool nccl_load()
+{
+    if (g_nccl.lib) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        dlclose(h);
+        return false;
+    }
+    g_nccl.lib = h;
+    return true;
+}
+
+}  // namespace
+
+struct crv_group {
+    crv_ctx* ctx = nullptr;
+    uint32_t rank = 0, nranks = 1, nbuf = 1;
+    uint32_t width = 0, height = 0;
+    size_t image_bytes = 0, block_bytes = 0;
+    unsigned char* block = nullptr;                // own allocation
+    unsigned char* peer[GROUP_MAX] = {};           // mapped peers (own block at [rank])
+    bool peer_ipc[GROUP_MAX] = {};                 // opened with cudaIpcOpenMemHandle (to be closed)
+    bool connected = false;
+    std::vector<crv_image*> images;
+    uint32_t epoch = 0;
+    unsigned long long timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+    void* nccl_comm = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, crv_group** out)
+{
+    CRV_REQUIRE(ctx && out, "crv_group_create: null argument");
+    *out = nullptr;
+    CRV_REQUIRE(nranks >= 1 && nranks <= (uint32_t)GROUP_MAX && rank < nranks, "crv_group_create: rank / nranks out of range (at most 16 members)");
+    CRV_REQUIRE(width > 0 && height > 0 && nbuf >= 1 && nbuf <= 8, "crv_group_create: bad image size or buffer count");
+    CRV_CUDA(cudaSetDevice(ctx->device));
+    crv_group* g = new (std::nothrow) crv_group();
+    if (!g) return CRV_ERR_OOM;
+    g->ctx = ctx;
+    g->rank = rank;
+    g->nranks = nranks;
+    g->nbuf = nbuf;
+    g->width = width;
+    g->height = height;
+    g->image_bytes = ((size_t)width * height * 16 + 255) / 256 * 256;
+    g->block_bytes = FLAG_PAGE + g->image_bytes * nbuf;
+    cudaError_t e = cudaMalloc(&g->block, g->block_bytes);
+    if (e != cudaSuccess) {
+        crv_set_error("crv_group_create: cudaMalloc of %zu bytes failed: %s", g->block_bytes, cudaGetErrorString(e));
+        delete g;
+        return CRV_ERR_OOM;
+    }
+    e = cudaMemset(g->block, 0, g->block_bytes);
+    if (e == cudaSuccess) e = cudaEventCreate(&g->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&g->ev1);
+    if (e != cudaSuccess) {
+        crv_set_error("crv_group_create: %s", cudaGetErrorString(e));
+        cudaFree(g->block);
+        delete g;
+        return CRV_ERR_CUDA;
+    }
+    g->peer[rank] = g->block;
+    for (uint32_t k = 0; k < nbuf; ++k) {
+        crv_image* img = nullptr;
+        const int rc = crv_image_wrap(ctx, reinterpret_cast<float*>(g->block + FLAG_PAGE + k * g->image_bytes), width, height, &img);
+        if (rc != CRV_OK) {
+            for (crv_image* i : g->images) crv_image_destroy(i);
+            cudaFree(g->block);
+            delete g;
+            return rc;
+        }
+        g->images.push_back(img);
+    }
+    g->connected = nranks == 1;
+    *out = g;
+    return CRV_OK;
+}
+
+int crv_group_destroy(crv_group* g)
+{
+    if (!g) return CRV_OK;
+    cudaSetDevice(g->ctx->device);
+    cudaDeviceSynchronize();
+    if (g->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->nccl_comm);
+    for (uint32_t p = 0; p < g->nranks; ++p)
+        if (p != g->rank && g->peer[p] && g->peer_ipc[p]) cudaIpcCloseMemHandle(g->peer[p]);
+    for (crv_image* i : g->images) crv_image_destroy(i);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->block) cudaFree(g->block);
+    delete g;
+    return CRV_OK;
+}
+
+int crv_group_export(crv_group* g, crv_group_handle* out)
+{
+    CRV_REQUIRE(g && out, "crv_group_export: null argument");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    std::memset(out, 0, sizeof(*out));
+    out->pid = (uint64_t)getpid();
+    out->device = g->ctx->device;
+    out->rank = g->rank;
+    out->base = (uint64_t)(uintptr_t)g->block;
+    out->bytes = (uint64_t)g->block_bytes;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(out->ipc), "ipc handle size");
+    cudaIpcMemHandle_t h;
+    CRV_CUDA(cudaIpcGetMemHandle(&h, g->block));
+    std::memcpy(out->ipc, &h, sizeof(h));
+    return CRV_OK;
+}
+
+int crv_group_connect(crv_group* g, const crv_group_handle* handles, uint32_t count)
+{
+    CRV_REQUIRE(g && handles, "crv_group_connect: null argument");
+    CRV_REQUIRE(count == g->nranks, "crv_group_connect: one handle per member, in rank order");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    for (uint32_t p = 0; p < count; ++p) {
+        const crv_group_handle& h = handles[p];
+        CRV_REQUIRE(h.rank == p, "crv_group_connect: handles are not in rank order");
+        CRV_REQUIRE(h.bytes == (uint64_t)g->block_bytes, "crv_group_connect: a member was created with another image size or buffer count");
+        if (p == g->rank) continue;
+        if (g->peer[p]) continue;
+        if (h.pid == (uint64_t)getpid()) {
+            // same process: the pointer is valid as it is once peer access is on (same device: nothing to do)
+            if (h.device != g->ctx->device) {
+                int can = 0;
+                CRV_CUDA(cudaDeviceCanAccessPeer(&can, g->ctx->device, h.device));
+                CRV_REQUIRE(can, "crv_group_connect: no peer access between two member devices");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CRV_CUDA(e);
+                (void)cudaGetLastError();
+            }
+            g->peer[p] = reinterpret_cast<unsigned char*>((uintptr_t)h.base);
+        } else {
+            cudaIpcMemHandle_t ih;
+            std::memcpy(&ih, h.ipc, sizeof(ih));
+            void* ptr = nullptr;
+            CRV_CUDA(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+            g->peer[p] = static_cast<unsigned char*>(ptr);
+            g->peer_ipc[p] = true;
+        }
+    }
+    g->connected = true;
+    return CRV_OK;
+}
+
+int crv_group_image(crv_group* g, uint32_t buffer, crv_image** out)
+{
+    CRV_REQUIRE(g && out, "crv_group_image: null argument");
+    CRV_REQUIRE(buffer < g->nbuf, "crv_group_image: buffer index out of range");
+    *out = g->images[buffer];
+    return CRV_OK;
+}
+
+int crv_group_set_timeout_ms(crv_group* g, uint32_t ms)
+{
+    CRV_REQUIRE(g && ms > 0, "crv_group_set_timeout_ms: bad argument");
+    g->timeout_ns = (unsigned long long)ms * 1000000ull;
+    return CRV_OK;
+}
+
+int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream)
+{
+    CRV_REQUIRE(g != nullptr, "crv_group_all_reduce_sum_scale: null group");
+    CRV_REQUIRE(buffer < g->nbuf, "crv_group_all_reduce_sum_scale: buffer index out of range");
+    CRV_REQUIRE(g->connected, "crv_group_all_reduce_sum_scale: crv_group_connect has not been called");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = as_stream(stream);
+    const uint32_t n4 = g->width * g->height;
+    CRV_CUDA(cudaEventRecord(g->ev0, s));
+    if (g->nranks == 1) {
+        group_scale_kernel<<<g->ctx->sm_count * 2, 512, 0, s>>>(reinterpret_cast<float4*>(g->block + FLAG_PAGE + buffer * g->image_bytes), n4, scale);
+    } else {
+        ReduceArgs a{};
+        for (uint32_t p = 0; p < g->nranks; ++p) a.peer[p] = g->peer[p];
+        a.image_offset = FLAG_PAGE + buffer * g->image_bytes;
+        a.n4 = n4;
+        a.rank = g->rank;
+        a.nranks = g->nranks;
+        a.epoch = ++g->epoch;
+        a.scale = scale;
+        a.timeout_ns = g->timeout_ns;
+        // few, fat CTAs: the band is 1/N of the image and every element costs N loads + N stores over NVLink; all members'
+        // kernels have to be resident at the same time (also when several members share one device, as the tests do)
+        const uint32_t band = (n4 + g->nranks - 1) / g->nranks;
+        unsigned blocks = (band + RED_THREADS * 4 - 1) / (RED_THREADS * 4);
+        if (blocks > 32u) blocks = 32u;
+        if (blocks < 1u) blocks = 1u;
+        switch (g->nranks) {
+            case 2: group_reduce_kernel<2><<<blocks, RED_THREADS, 0, s>>>(a); break;
+            case 4: group_reduce_kernel<4><<<blocks, RED_THREADS, 0, s>>>(a); break;
+            case 8: group_reduce_kernel<8><<<blocks, RED_THREADS, 0, s>>>(a); break;
+            default: group_reduce_kernel<0><<<blocks, RED_THREADS, 0, s>>>(a); break;
+        }
+    }
+    g->ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    CRV_CUDA(cudaEventRecord(g->ev1, s));
+    g->timed = true;
+    return CRV_OK;
+}
+
+int crv_group_status(crv_group* g, void* stream)
+{
+    CRV_REQUIRE(g != nullptr, "crv_group_status: null group");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    uint32_t err = 0;
+    CRV_CUDA(cudaMemcpyAsync(&err, g->block + offsetof(GroupFlags, error), sizeof(err), cudaMemcpyDeviceToHost, as_stream(stream)));
+    CRV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    if (err != 0) {
+        crv_set_error("crv_group: member %u gave up waiting for a peer at the %s barrier (timeout %llu ms)", g->rank, err == 1 ? "start" : "end",
+                      g->timeout_ns / 1000000ull);
+        return CRV_ERR_CUDA;
+    }
+    return CRV_OK;
+}
+
+int crv_group_last_reduce_ms(crv_group* g, float* ms)
+{
+    CRV_REQUIRE(g && ms, "crv_group_last_reduce_ms: null argument");
+    CRV_REQUIRE(g->timed, "crv_group_last_reduce_ms: nothing reduced yet");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    CRV_CUDA(cudaEventSynchronize(g->ev1));
+    CRV_CUDA(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+    return CRV_OK;
+}
+
+// ---- NCCL variant ----------------------------------------------------------------------------------------------------------
+int crv_group_nccl_unique_id(unsigned char id_out[128])
+{
+    CRV_REQUIRE(id_out != nullptr, "crv_group_nccl_unique_id: null argument");
+    CRV_REQUIRE(nccl_load(), "crv_group_nccl_unique_id: libnccl.so.2 is not loadable in this process");
+    const int rc = g_nccl.GetUniqueId(id_out);
+    if (rc != 0) {
+        crv_set_error("ncclGetUniqueId failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        return CRV_ERR_CUDA;
+    }
+    return CRV_OK;
+}
+
+int crv_group_nccl_init(crv_group* g, const unsigned char id[128])
+{
+    CRV_REQUIRE(g && id, "crv_group_nccl_init: null argument");
+    CRV_REQUIRE(nccl_load(), "crv_group_nccl_init: libnccl.so.2 is not loadable in this process");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    Id128 uid;
+    std::memcpy(uid.b, id, 128);
+    const int rc = g_nccl.CommInitRank(&g->nccl_comm, (int)g->nranks, uid, (int)g->rank);
+    if (rc != 0) {
+        crv_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        g->nccl_comm = nullptr;
+        return CRV_ERR_CUDA;
+    }
+    return CRV_OK;
+}
+
+int crv_group_nccl_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream)
+{
+    CRV_REQUIRE(g != nullptr, "crv_group_nccl_all_reduce_sum_scale: null group");
+    CRV_REQUIRE(buffer < g->nbuf, "crv_group_nccl_all_reduce_sum_scale: buffer index out of range");
+    CRV_REQUIRE(g->nccl_comm != nullptr || g->nranks == 1, "crv_group_nccl_all_reduce_sum_scale: crv_group_nccl_init has not been called");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = as_stream(stream);
+    float* img = reinterpret_cast<float*>(g->block + FLAG_PAGE + buffer * g->image_bytes);
+    const size_t n = (size_t)g->width * g->height * 4;
+    CRV_CUDA(cudaEventRecord(g->ev0, s));
+    if (g->nranks > 1) {
+        const int rc = g_nccl.AllReduce(img, img, n, /* ncclFloat32 */ 7, /* ncclSum */ 0, g->nccl_comm, s);
+        if (rc != 0) {
+            crv_set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+            return CRV_ERR_CUDA;
+        }
+    }
+    group_scale_kernel<<<g->ctx->sm_count * 2, 512, 0, s>>>(reinterpret_cast<float4*>(img), (uint32_t)(n / 4), scale);
+    g->ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    CRV_CUDA(cudaEventRecord(g->ev1, s));
+    g->timed = true;
+    return CRV_OK;
+}
+
+}  // extern "C"

@@ -10,6 +10,8 @@
 //
 //   crv_headless [--xyz file | --fbm N] [--width W --height H] [--spp S] [--nsv N] [--g G] [--absorption A]
 //                [--density-scaling D] [--light x,y,z] [--per-frame] [--device i] [--pfm out.pfm]
+//                [--gpus N [--same-device]]   the picture's frames split over N GPUs (frame f -> member f mod N), every member
+//                                             with its own replica of the grid and the shadow volume, combined by crv_group_*
 // prints one JSON line: resolution, spp, ms, Mpath-samples/s, SV build ms, FNV-1a hash of the RGBA32F image.
 #include <chrono>
 #include <cstdio>
@@ -33,6 +35,9 @@ struct Options {
     float light[3] = {1.0f, -1.0f, 0.0f};
     bool isotropic = false, per_frame = false, warmup = false, math_driver = false;
     unsigned ppm_frames = 0;          // --ppm N: after the path-traced image, N progressive-photon-mapping frames into a second image
+    unsigned gpus = 1;                // --gpus N: the frames of the picture are split over N group members
+    bool same_device = false;         // --same-device: all members on --device (functional test of the group on one GPU)
+    int skip_level = 1;               // --skip-level 0|1 (crv_pt_set_skip_level)
 };
 
 bool parse(int argc, char** argv, Options& o)
@@ -62,11 +67,18 @@ bool parse(int argc, char** argv, Options& o)
         else if (a == "--warmup") o.warmup = true;
         else if (a == "--ppm") o.ppm_frames = (unsigned)std::atoi(next("--ppm"));
         else if (a == "--math") { const std::string v = next("--math"); if (v != "strict" && v != "driver") return false; o.math_driver = v == "driver"; }
+        else if (a == "--gpus") o.gpus = (unsigned)std::atoi(next("--gpus"));
+        else if (a == "--same-device") o.same_device = true;
+        else if (a == "--skip-level") o.skip_level = std::atoi(next("--skip-level"));
         else if (a == "--resume") o.resume = next("--resume");
         else if (a == "--checkpoint") o.checkpoint = next("--checkpoint");
         else return false;
     }
-    return o.width > 0 && o.height > 0 && o.spp > 0 && o.nsv > 0;
+    if (o.gpus > 1 && (o.per_frame || !o.resume.empty() || o.ppm_frames > 0)) {
+        std::fprintf(stderr, "crv_headless: --gpus N renders one batch picture (no --per-frame / --resume / --ppm)\n");
+        return false;
+    }
+    return o.width > 0 && o.height > 0 && o.spp > 0 && o.nsv > 0 && o.gpus >= 1 && o.gpus <= 16;
 }
 
 uint64_t fnv1a(const void* data, size_t n)
@@ -91,6 +103,9 @@ struct App {
     std::unique_ptr<crv::Image> resultImage;
     std::unique_ptr<crv::RenderTechniqueSV> shadowVolumeTechnique;
     std::unique_ptr<crv::RenderTechniquePT> pathTracingTechnique;
+    // --gpus N: this replica's membership of the sample split; its result image then lives in the group's memory
+    std::unique_ptr<crv::DeviceGroup> group;
+    std::unique_ptr<crv::Stream> stream;
 
     // main.cpp:223-264
     void UpdateShadowVolume()
@@ -136,57 +151,78 @@ int main(int argc, char** argv)
         return 2;
     }
     try {
-        App app;
-        app.device = std::make_unique<crv::Device>(o.device);
-        std::memcpy(app.lightDirection, o.light, sizeof(o.light));
-        app.shadowVolumeProperties.voxelAxisCount = o.nsv;
-        app.pushConstants.frameCount = 0;
-        // SetResolution before SetFOV (main.cpp:383-384)
-        app.cameraProperties.SetResolution(o.width, o.height);
-        app.cameraProperties.SetFOV(o.fov);
-        app.cloudProperties.densityScaling = o.density_scaling;
-        if (!o.isotropic) app.parameters.SetPhaseG(o.g);
-
-        // ---- InitializeVulkan (main.cpp:765-910), minus Vulkan ----
-        app.shadowVolumeImage = std::make_unique<crv::Volume>(app.device.get(), o.nsv, o.nsv, o.nsv);
-        app.resultImage = std::make_unique<crv::Image>(app.device.get(), (uint32_t)o.width, (uint32_t)o.height);
-        app.shadowVolumeTechnique = std::make_unique<crv::RenderTechniqueSV>(app.device.get(), &app.shadowVolumeProperties, &app.pushConstants);
-        app.pathTracingTechnique = std::make_unique<crv::RenderTechniquePT>(app.device.get(), &app.cameraProperties, &app.pushConstants);
-        std::vector<crv::FrameImage> svFrames{crv::FrameImage(app.shadowVolumeImage.get())};
-        std::vector<crv::FrameImage> ptFrames{crv::FrameImage(app.resultImage.get())};
-        app.shadowVolumeTechnique->SetFrameReferences(svFrames);
-        app.pathTracingTechnique->SetFrameReferences(ptFrames);
-        crv::DescriptorBufferInfo paramInfo{&app.parameters, sizeof(app.parameters)};
-        crv::DescriptorBufferInfo cameraInfo{&app.cameraProperties, sizeof(app.cameraProperties)};
-        crv::DescriptorImageInfo svImageInfo{app.shadowVolumeImage.get()};
-        app.pathTracingTechnique->QueueUpdateParameters(paramInfo, 0);
-        app.pathTracingTechnique->QueueUpdateCameraProperties(cameraInfo, 0);
-        app.pathTracingTechnique->QueueUpdateShadowVolumeSampler(svImageInfo, 0);
-        app.pathTracingTechnique->UpdateDescriptorSets();
-        crv::PathTracerExtensions ext;
-        ext.absorption = o.absorption;
-        ext.math_mode = o.math_driver ? CRV_PT_MATH_DRIVER : CRV_PT_MATH_STRICT;
-        app.pathTracingTechnique->SetExtensions(ext);
-
-        // ---- LoadCloudFile (main.cpp:166-190) or the synthetic fBm scene, then SetCloudProperties (main.cpp:144-163) ----
-        uint32_t counts[3];
-        double voxel[3];
+        // one replica of the whole scene per group member (one member = the reference's single-GPU program)
+        std::vector<std::unique_ptr<App>> apps;
+        std::unique_ptr<crv::Grid3D<float>> grid;
         if (!o.xyz.empty()) {
-            std::unique_ptr<crv::Grid3D<float>> grid(crv::Grid3D<float>::Load(o.xyz));
+            grid.reset(crv::Grid3D<float>::Load(o.xyz));
             if (!grid) { std::fprintf(stderr, "crv_headless: cannot open %s\n", o.xyz.c_str()); return 1; }
-            const auto c = grid->GetVoxelCount();
-            const auto v = grid->GetVoxelSize();
-            for (int i = 0; i < 3; ++i) { counts[i] = c[i]; voxel[i] = v[i]; }
-            app.cloudImage = std::make_unique<crv::Volume>(app.device.get(), counts[0], counts[1], counts[2]);
-            app.cloudImage->Upload(grid->data());
-            app.device->WaitIdle();
-        } else {
-            for (int i = 0; i < 3; ++i) { counts[i] = o.fbm; voxel[i] = 1.0 / o.fbm; }
-            app.cloudImage = std::make_unique<crv::Volume>(app.device.get(), o.fbm, o.fbm, o.fbm);
-            app.cloudImage->GenerateFbm(1234);
         }
-        app.cloudProperties.SetFromGrid(counts, voxel, app.cloudImage->GetMajorant());
-        app.UpdateCloudData();
+        for (unsigned m = 0; m < o.gpus; ++m) {
+            apps.emplace_back(new App());
+            App& app = *apps.back();
+            app.device = std::make_unique<crv::Device>(o.same_device ? o.device : o.device + (int)m);
+            std::memcpy(app.lightDirection, o.light, sizeof(o.light));
+            app.shadowVolumeProperties.voxelAxisCount = o.nsv;
+            app.pushConstants.frameCount = 0;
+            // SetResolution before SetFOV (main.cpp:383-384)
+            app.cameraProperties.SetResolution(o.width, o.height);
+            app.cameraProperties.SetFOV(o.fov);
+            app.cloudProperties.densityScaling = o.density_scaling;
+            if (!o.isotropic) app.parameters.SetPhaseG(o.g);
+
+            // ---- InitializeVulkan (main.cpp:765-910), minus Vulkan ----
+            app.shadowVolumeImage = std::make_unique<crv::Volume>(app.device.get(), o.nsv, o.nsv, o.nsv);
+            if (o.gpus > 1) {
+                app.group = std::make_unique<crv::DeviceGroup>(app.device.get(), m, o.gpus, (uint32_t)o.width, (uint32_t)o.height);
+                app.resultImage.reset(new crv::Image(app.group->GetImage(0)));
+                app.stream = std::make_unique<crv::Stream>(app.device.get());
+            } else {
+                app.resultImage = std::make_unique<crv::Image>(app.device.get(), (uint32_t)o.width, (uint32_t)o.height);
+            }
+            app.shadowVolumeTechnique = std::make_unique<crv::RenderTechniqueSV>(app.device.get(), &app.shadowVolumeProperties, &app.pushConstants);
+            app.pathTracingTechnique = std::make_unique<crv::RenderTechniquePT>(app.device.get(), &app.cameraProperties, &app.pushConstants);
+            std::vector<crv::FrameImage> svFrames{crv::FrameImage(app.shadowVolumeImage.get())};
+            std::vector<crv::FrameImage> ptFrames{crv::FrameImage(app.resultImage.get())};
+            app.shadowVolumeTechnique->SetFrameReferences(svFrames);
+            app.pathTracingTechnique->SetFrameReferences(ptFrames);
+            crv::DescriptorBufferInfo paramInfo{&app.parameters, sizeof(app.parameters)};
+            crv::DescriptorBufferInfo cameraInfo{&app.cameraProperties, sizeof(app.cameraProperties)};
+            crv::DescriptorImageInfo svImageInfo{app.shadowVolumeImage.get()};
+            app.pathTracingTechnique->QueueUpdateParameters(paramInfo, 0);
+            app.pathTracingTechnique->QueueUpdateCameraProperties(cameraInfo, 0);
+            app.pathTracingTechnique->QueueUpdateShadowVolumeSampler(svImageInfo, 0);
+            app.pathTracingTechnique->UpdateDescriptorSets();
+            crv::PathTracerExtensions ext;
+            ext.absorption = o.absorption;
+            ext.math_mode = o.math_driver ? CRV_PT_MATH_DRIVER : CRV_PT_MATH_STRICT;
+            app.pathTracingTechnique->SetExtensions(ext);
+            app.pathTracingTechnique->SetSkipLevel(o.skip_level);
+
+            // ---- LoadCloudFile (main.cpp:166-190) or the synthetic fBm scene, then SetCloudProperties (main.cpp:144-163) ----
+            uint32_t counts[3];
+            double voxel[3];
+            if (grid) {
+                const auto c = grid->GetVoxelCount();
+                const auto v = grid->GetVoxelSize();
+                for (int i = 0; i < 3; ++i) { counts[i] = c[i]; voxel[i] = v[i]; }
+                app.cloudImage = std::make_unique<crv::Volume>(app.device.get(), counts[0], counts[1], counts[2]);
+                app.cloudImage->Upload(grid->data());
+                app.device->WaitIdle();
+            } else {
+                for (int i = 0; i < 3; ++i) { counts[i] = o.fbm; voxel[i] = 1.0 / o.fbm; }
+                app.cloudImage = std::make_unique<crv::Volume>(app.device.get(), o.fbm, o.fbm, o.fbm);
+                app.cloudImage->GenerateFbm(1234);
+            }
+            app.cloudProperties.SetFromGrid(counts, voxel, app.cloudImage->GetMajorant());
+            app.UpdateCloudData();
+        }
+        if (o.gpus > 1) {        // every member maps everybody else's accumulation image
+            std::vector<crv_group_handle> handles;
+            for (auto& a : apps) handles.push_back(a->group->Export());
+            for (auto& a : apps) a->group->Connect(handles);
+        }
+        App& app = *apps[0];
         const float sv_ms = app.shadowVolumeTechnique->LastBuildMs();
 
         // ---- RenderLoop (main.cpp:714-736): srand(0); per frame seed = rand() ----
@@ -202,7 +238,21 @@ int main(int argc, char** argv)
         crv::MsvcRandSequence(0, first_frame + o.spp, all_seeds.data());
         std::vector<int32_t> seeds(all_seeds.begin() + first_frame, all_seeds.end());
         auto render = [&]() {
-            if (o.per_frame) {
+            if (o.gpus > 1) {
+                // frame f -> member f mod N; every member sums its frames, one kernel per member combines and divides.
+                // All renders are enqueued before the first combine: a member's combine kernel waits for its peers' on the device.
+                for (unsigned m = 0; m < o.gpus; ++m) {
+                    App& a = *apps[m];
+                    std::vector<int32_t> mine;
+                    for (unsigned f = m; f < o.spp; f += o.gpus) mine.push_back(seeds[f]);
+                    a.resultImage->Clear(a.stream->Get());
+                    if (!mine.empty()) a.pathTracingTechnique->RenderBatch(mine.data(), (unsigned)mine.size(), 0, CRV_ACCUM_SUM, a.stream->Get(), 0);
+                }
+                for (auto& a : apps) a->group->AllReduceSumScale(1.0f / (float)o.spp, a->stream->Get());
+                for (auto& a : apps) a->device->WaitIdle(a->stream->Get());
+                for (auto& a : apps) a->group->CheckStatus(a->stream->Get());
+                app.pushConstants.frameCount += o.spp;
+            } else if (o.per_frame) {
                 for (unsigned f = 0; f < o.spp; ++f) {
                     app.pushConstants.seed = seeds[f];
                     app.pathTracingTechnique->RecordDrawCommands(nullptr, 0);
@@ -217,7 +267,7 @@ int main(int argc, char** argv)
             // --warmup: the same render once untimed (first-use allocations, table builds), then the accumulation is put back
             // where it was -- cleared, or the checkpoint reloaded -- so that the timed run produces the same image
             render();
-            app.device->WaitIdle();
+            for (auto& a : apps) a->device->WaitIdle();
             app.resultImage->Clear();
             app.pushConstants.frameCount = 0;
             if (!o.resume.empty()) {
@@ -225,17 +275,28 @@ int main(int argc, char** argv)
                 app.resultImage->LoadCheckpoint(o.resume.c_str(), &first_frame, &last_seed);
                 app.pushConstants.frameCount = first_frame;
             }
-            app.pathTracingTechnique->ResetStats();
+            for (auto& a : apps) a->pathTracingTechnique->ResetStats();
         }
-        app.device->WaitIdle();
+        for (auto& a : apps) a->device->WaitIdle();
         const auto t0 = std::chrono::steady_clock::now();
         render();
-        app.device->WaitIdle();
+        for (auto& a : apps) a->device->WaitIdle();
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
         std::vector<float> rgba((size_t)o.width * o.height * 4);
         app.resultImage->Download(rgba.data());
-        const crv_pt_stats st = app.pathTracingTechnique->GetStats();
+        crv_pt_stats st = app.pathTracingTechnique->GetStats();
+        // --gpus N: every member must hold the same final picture; the statistics are the members' sums
+        bool members_identical = true;
+        uint64_t launches = app.device->LaunchCount();
+        for (unsigned m = 1; m < o.gpus; ++m) {
+            std::vector<float> other(rgba.size());
+            apps[m]->resultImage->Download(other.data());
+            members_identical = members_identical && std::memcmp(other.data(), rgba.data(), rgba.size() * sizeof(float)) == 0;
+            const crv_pt_stats sm = apps[m]->pathTracingTechnique->GetStats();
+            st.paths += sm.paths; st.tracking_steps += sm.tracking_steps; st.collisions += sm.collisions; st.tracked_paths += sm.tracked_paths;
+            if (!o.same_device) launches += apps[m]->device->LaunchCount();
+        }
         if (!o.pfm.empty()) app.resultImage->SavePfm(o.pfm.c_str());                 // linear RGB float
         if (!o.png.empty()) app.resultImage->SavePng(o.png.c_str());                 // what the sRGB swapchain image would show
         if (!o.checkpoint.empty()) app.resultImage->SaveCheckpoint(o.checkpoint.c_str(), app.pushConstants.frameCount, seeds.back());
@@ -283,12 +344,14 @@ int main(int argc, char** argv)
             ppm_mean /= (double)px.size();
             ppm_radius = pc.pmRadius;
         }
-        std::printf("{\"width\": %d, \"height\": %d, \"spp\": %u, \"mode\": \"%s\", \"render_ms\": %.3f, \"mpath_samples_per_s\": %.1f, "
-                    "\"sv_build_ms\": %.4f, \"paths\": %llu, \"tracking_steps\": %llu, \"collisions\": %llu, \"kernel_launches\": %llu, "
+        std::printf("{\"width\": %d, \"height\": %d, \"spp\": %u, \"mode\": \"%s\", \"gpus\": %u, \"members_identical\": %s, \"render_ms\": %.3f, "
+                    "\"mpath_samples_per_s\": %.1f, "
+                    "\"sv_build_ms\": %.4f, \"paths\": %llu, \"tracked_paths\": %llu, \"tracking_steps\": %llu, \"collisions\": %llu, \"kernel_launches\": %llu, "
                     "\"image_fnv1a\": \"%016llx\", \"ppm_frames\": %u, \"ppm_frame_ms\": %.3f, \"ppm_image_mean\": %.9g, \"ppm_radius\": %.9g}\n",
-                    o.width, o.height, o.spp, o.per_frame ? "per-frame" : "batch", ms, (double)o.width * o.height * o.spp / ms / 1e3, sv_ms,
-                    (unsigned long long)st.paths, (unsigned long long)st.tracking_steps, (unsigned long long)st.collisions,
-                    (unsigned long long)app.device->LaunchCount(), (unsigned long long)fnv1a(rgba.data(), rgba.size() * sizeof(float)),
+                    o.width, o.height, o.spp, o.gpus > 1 ? "split" : o.per_frame ? "per-frame" : "batch", o.gpus, members_identical ? "true" : "false", ms,
+                    (double)o.width * o.height * o.spp / ms / 1e3, sv_ms,
+                    (unsigned long long)st.paths, (unsigned long long)st.tracked_paths, (unsigned long long)st.tracking_steps, (unsigned long long)st.collisions,
+                    (unsigned long long)launches, (unsigned long long)fnv1a(rgba.data(), rgba.size() * sizeof(float)),
                     o.ppm_frames, ppm_ms, ppm_mean, (double)ppm_radius);
         return 0;
     } catch (const crv::Error& e) {

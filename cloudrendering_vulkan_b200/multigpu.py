@@ -1,14 +1,25 @@
-"""spp split across GPUs: one process per GPU, grid + shadow volume replicated, fp32 accumulation buffers summed.
+"""spp split across GPUs: host side of the multi-GPU path, on top of crv_group_* (csrc/group.cu).
 
-The reference is single-GPU; (pixel, frame) samples are independent (RNG state depends only on the frame seed and the
-pixel index, PathTracer.comp:368), so the natural shard is the FRAME list: rank r renders frames {f : f mod world = r}
-into a local fp32 SUM (CRV_ACCUM_SUM), one all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests) adds the
-partial sums, and a divide by the total spp turns the sum into the mean the single-GPU running mean converges to.
-No other collective exists on the path.
+The reference is single-GPU; (pixel, frame) samples are independent (the RNG state depends only on the frame seed and the
+pixel index, PathTracer.comp:368), so the natural shard is the FRAME list: the density grid and the shadow volume are
+replicated, member r renders frames {f : f mod world = r} into a private fp32 SUM image (CRV_ACCUM_SUM), and one kernel per
+member -- crv_group_all_reduce_sum_scale, peer loads and stores over NVLink -- adds the members' images in rank order,
+divides by the total sample count and leaves the same final picture in every member's image.  No other exchange exists on
+the path.  torch.distributed is only the messenger that carries the 96-byte memory handles between the ranks at set-up
+(any backend: gloo in the CPU tests, nccl under torchrun).
+
+    split = SampleSplit(renderer, rank, world)          # one per process; collective: exchanges the handles
+    split.render_picture(all_seeds, stream)             # clear + my frames + reduce/scale, asynchronous
+    picture = split.image.download(stream)              # identical on every member
 """
 from __future__ import annotations
 
+from typing import Optional, Sequence
+
 import numpy as np
+
+from . import capi
+from .technique import Group
 
 
 def frames_for_rank(all_seeds, rank: int, world: int) -> np.ndarray:
@@ -22,17 +33,76 @@ def frame_indices_for_rank(n_frames: int, rank: int, world: int) -> np.ndarray:
     return np.arange(n_frames, dtype=np.int64)[rank::world]
 
 
-def reduce_accumulation(accum, spp_total: int, group=None, scale_fn=None):
-    """In-place all-reduce(sum) of a torch accumulation tensor (any device) followed by the divide by spp_total.
-
-    scale_fn(factor), when given, performs the divide on the device through the C ABI (crv_image_scale) instead of a
-    torch op; returns `accum`.
-    """
+def all_gather_bytes(payload: bytes, world: int, dist_group=None) -> list:
+    """every rank's `payload` (equal lengths), in rank order, through torch.distributed; a single process returns [payload]"""
+    if world == 1:
+        return [payload]
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
-    if scale_fn is not None:
-        scale_fn(1.0 / float(spp_total))
-    else:
-        accum.mul_(1.0 / float(spp_total))
-    return accum
+    out = [None] * world
+    dist.all_gather_object(out, payload, group=dist_group)
+    if any(len(b) != len(payload) for b in out):
+        raise RuntimeError("all_gather_bytes: ranks sent payloads of different sizes")
+    return out
+
+
+def broadcast_bytes(payload: Optional[bytes], src: int, world: int, dist_group=None) -> bytes:
+    if world == 1:
+        return payload
+    import torch.distributed as dist
+    box = [payload]
+    dist.broadcast_object_list(box, src=src, group=dist_group)
+    return box[0]
+
+
+def connect_group(group: Group, dist_group=None) -> None:
+    """collective: publish this member's handle, map everybody else's"""
+    group.connect(all_gather_bytes(group.export(), group.nranks, dist_group))
+
+
+def init_group_nccl(group: Group, dist_group=None) -> None:
+    """collective: rank 0 draws the ncclUniqueId, everybody joins the communicator behind crv_group_nccl_*"""
+    uid = broadcast_bytes(Group.nccl_unique_id() if group.rank == 0 else None, 0, group.nranks, dist_group)
+    group.nccl_init(uid)
+
+
+class SampleSplit:
+    """One member of the split around a HeadlessRenderer: re-targets the renderer's path tracer at the group's image and
+    renders pictures whose frames are spread over the members."""
+
+    def __init__(self, renderer, rank: int, world: int, nbuf: int = 1, dist_group=None, connect: bool = True):
+        self.r = renderer
+        self.rank, self.world = int(rank), int(world)
+        img = renderer.resultImage
+        self.group = Group(renderer.ctx, rank, world, img.width, img.height, nbuf)
+        if connect:
+            connect_group(self.group, dist_group)
+        self.use_buffer(0)
+
+    def use_buffer(self, k: int):
+        self.buffer = int(k)
+        self.image = self.group.image(k)
+        self.r.resultImage = self.image
+        self.r.pathTracingTechnique.SetFrameReferences([self.image])
+
+    def my_seeds(self, all_seeds) -> np.ndarray:
+        return frames_for_rank(all_seeds, self.rank, self.world)
+
+    def render_picture(self, all_seeds, stream=0, backend: str = "peer"):
+        """clear, this member's frames as a plain sum, combine + divide by len(all_seeds): every member ends with the mean"""
+        seeds = self.my_seeds(all_seeds)
+        self.image.clear(stream)
+        if len(seeds):
+            self.r.pathTracingTechnique.RenderBatch(seeds, 0, capi.ACCUM_SUM, stream, 0)
+        self.reduce(len(all_seeds), stream, backend)
+
+    def reduce(self, spp_total: int, stream=0, backend: str = "peer"):
+        scale = 1.0 / float(spp_total)
+        if backend == "peer":
+            self.group.all_reduce_sum_scale(scale, stream, self.buffer)
+        elif backend == "nccl":
+            self.group.nccl_all_reduce_sum_scale(scale, stream, self.buffer)
+        else:
+            raise ValueError(f"unknown reduce backend {backend!r}")
+
+    def close(self):
+        self.group.close()

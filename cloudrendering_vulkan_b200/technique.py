@@ -59,6 +59,27 @@ class Context:
             self.handle = C.c_void_p()
 
 
+class Stream:
+    """A command stream of the context's device (VkQueue + VkCommandBuffer role): a non-blocking cudaStream_t."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib.crv_stream_create(ctx.handle, C.byref(h)))
+        self.handle = h.value or 0
+
+    def __int__(self):
+        return self.handle
+
+    def synchronize(self):
+        self.ctx.synchronize(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib.crv_stream_destroy(self.ctx.handle, C.c_void_p(self.handle))
+            self.handle = 0
+
+
 class Volume:
     """R32_SFLOAT 3D image + LINEAR/CLAMP_TO_EDGE sampler (main.cpp:277-285, Initializers.cpp:408-418)."""
 
@@ -109,11 +130,14 @@ class Volume:
 class Image:
     """R32G32B32A32_SFLOAT 2D storage image (main.cpp:405-414), zero-cleared on creation."""
 
-    def __init__(self, ctx: Context, width: int, height: int, device_ptr: Optional[int] = None):
+    def __init__(self, ctx: Context, width: int, height: int, device_ptr: Optional[int] = None, borrowed_handle=None):
         self.ctx = ctx
         self.width, self.height = int(width), int(height)
         self.handle = C.c_void_p()
-        if device_ptr is None:
+        self.borrowed = borrowed_handle is not None
+        if self.borrowed:                      # an image owned by another object (crv_group_image)
+            self.handle = C.c_void_p(borrowed_handle)
+        elif device_ptr is None:
             check(lib.crv_image_create(ctx.handle, width, height, C.byref(self.handle)))
         else:
             check(lib.crv_image_wrap(ctx.handle, C.c_void_p(int(device_ptr)), width, height, C.byref(self.handle)))
@@ -166,9 +190,83 @@ class Image:
         return p.value or 0
 
     def close(self):
-        if self.handle:
+        if self.handle and not self.borrowed:
             lib.crv_image_destroy(self.handle)
+        self.handle = C.c_void_p()
+
+
+class Group:
+    """One member of a multi-GPU sample split (crv_group_*): owns the accumulation image(s) its technique renders
+    into, in memory the other members map over NVLink, and combines them -- sum over members x scale -- in one kernel.
+
+        g = Group(ctx, rank, world, W, H); handles = <all members' g.export(), in rank order>; g.connect(handles)
+        pt.SetFrameReferences([g.image(0)]) ... RenderBatch(my_seeds, 0, ACCUM_SUM) ... g.all_reduce_sum_scale(1 / spp_total)
+    """
+
+    def __init__(self, ctx: Context, rank: int, nranks: int, width: int, height: int, nbuf: int = 1):
+        self.ctx = ctx
+        self.rank, self.nranks, self.nbuf = int(rank), int(nranks), int(nbuf)
+        self.width, self.height = int(width), int(height)
+        self.handle = C.c_void_p()
+        check(lib.crv_group_create(ctx.handle, rank, nranks, width, height, nbuf, C.byref(self.handle)))
+        self._images = {}
+
+    def export(self) -> bytes:
+        h = capi.GroupHandle()
+        check(lib.crv_group_export(self.handle, C.byref(h)))
+        return bytes(h)
+
+    def connect(self, handles: Sequence[bytes]):
+        if len(handles) != self.nranks:
+            raise ValueError("Group.connect: one handle per member, in rank order")
+        arr = (capi.GroupHandle * self.nranks)()
+        for i, b in enumerate(handles):
+            if len(b) != C.sizeof(capi.GroupHandle):
+                raise ValueError("Group.connect: not a group handle")
+            C.memmove(C.byref(arr[i]), bytes(b), C.sizeof(capi.GroupHandle))
+        check(lib.crv_group_connect(self.handle, arr, self.nranks))
+
+    def image(self, buffer: int = 0) -> "Image":
+        if buffer not in self._images:
+            h = C.c_void_p()
+            check(lib.crv_group_image(self.handle, buffer, C.byref(h)))
+            self._images[buffer] = Image(self.ctx, self.width, self.height, borrowed_handle=h.value)
+        return self._images[buffer]
+
+    def all_reduce_sum_scale(self, scale: float, stream=0, buffer: int = 0):
+        check(lib.crv_group_all_reduce_sum_scale(self.handle, buffer, C.c_float(scale), _stream(stream)))
+
+    def set_timeout_ms(self, ms: int):
+        check(lib.crv_group_set_timeout_ms(self.handle, int(ms)))
+
+    def status(self, stream=0):
+        """raises CrvError if a barrier of an earlier reduce timed out (synchronises the stream)"""
+        check(lib.crv_group_status(self.handle, _stream(stream)))
+
+    def last_reduce_ms(self) -> float:
+        ms = C.c_float()
+        check(lib.crv_group_last_reduce_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    # ---- the NCCL route (north_star's wording), for comparison ----
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_ubyte * 128)()
+        check(lib.crv_group_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def nccl_init(self, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        check(lib.crv_group_nccl_init(self.handle, buf))
+
+    def nccl_all_reduce_sum_scale(self, scale: float, stream=0, buffer: int = 0):
+        check(lib.crv_group_nccl_all_reduce_sum_scale(self.handle, buffer, C.c_float(scale), _stream(stream)))
+
+    def close(self):
+        if self.handle:
+            lib.crv_group_destroy(self.handle)
             self.handle = C.c_void_p()
+            self._images = {}
 
 
 class RenderTechnique:

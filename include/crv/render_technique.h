@@ -102,7 +102,9 @@ public:
     {
         Check(crv_image_create(device->Get(), width, height, &m_img));
     }
-    ~Image() { crv_image_destroy(m_img); }
+    // an image owned by somebody else (a DeviceGroup's accumulation image): not destroyed with this object
+    Image(crv_image* borrowed, uint32_t width, uint32_t height) : m_img(borrowed), m_width(width), m_height(height), m_owned(false) {}
+    ~Image() { if (m_owned) crv_image_destroy(m_img); }
     Image(const Image&) = delete;
     Image& operator=(const Image&) = delete;
     crv_image* Get() const { return m_img; }
@@ -126,6 +128,62 @@ public:
 
 private:
     crv_image* m_img = nullptr;
+    uint32_t m_width, m_height;
+    bool m_owned = true;
+};
+
+// a command stream of the device (VkQueue role): a non-blocking cudaStream_t
+class Stream {
+public:
+    explicit Stream(Device* device) : m_device(device) { Check(crv_stream_create(device->Get(), &m_stream)); }
+    ~Stream() { crv_stream_destroy(m_device->Get(), m_stream); }
+    Stream(const Stream&) = delete;
+    Stream& operator=(const Stream&) = delete;
+    CommandStream Get() const { return m_stream; }
+
+private:
+    Device* m_device;
+    void* m_stream = nullptr;
+};
+
+// One member of a multi-GPU sample split (crv_group_*; SURVEY 8e -- no counterpart in the single-GPU reference).  Owns the
+// accumulation image(s) its RenderTechniquePT renders into with CRV_ACCUM_SUM, in memory the other members map over NVLink;
+// AllReduceSumScale adds all members' images in rank order, scales and leaves the same picture in every member's image.
+class DeviceGroup {
+public:
+    DeviceGroup(Device* device, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf = 1) : m_width(width), m_height(height)
+    {
+        Check(crv_group_create(device->Get(), rank, nranks, width, height, nbuf, &m_group));
+    }
+    ~DeviceGroup() { crv_group_destroy(m_group); }
+    DeviceGroup(const DeviceGroup&) = delete;
+    DeviceGroup& operator=(const DeviceGroup&) = delete;
+    crv_group_handle Export()
+    {
+        crv_group_handle h{};
+        Check(crv_group_export(m_group, &h));
+        return h;
+    }
+    void Connect(const std::vector<crv_group_handle>& handlesInRankOrder) { Check(crv_group_connect(m_group, handlesInRankOrder.data(), (uint32_t)handlesInRankOrder.size())); }
+    // the member's accumulation image `buffer` as a (borrowed) crv::Image, e.g. for SetFrameReferences
+    Image GetImage(uint32_t buffer = 0)
+    {
+        crv_image* img = nullptr;
+        Check(crv_group_image(m_group, buffer, &img));
+        return Image(img, m_width, m_height);
+    }
+    void AllReduceSumScale(float scale, CommandStream stream = nullptr, uint32_t buffer = 0) { Check(crv_group_all_reduce_sum_scale(m_group, buffer, scale, stream)); }
+    void CheckStatus(CommandStream stream = nullptr) { Check(crv_group_status(m_group, stream)); }
+    float LastReduceMs()
+    {
+        float ms = 0.0f;
+        Check(crv_group_last_reduce_ms(m_group, &ms));
+        return ms;
+    }
+    void SetTimeoutMs(uint32_t ms) { Check(crv_group_set_timeout_ms(m_group, ms)); }
+
+private:
+    crv_group* m_group = nullptr;
     uint32_t m_width, m_height;
 };
 

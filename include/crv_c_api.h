@@ -182,6 +182,18 @@ typedef struct crv_image  crv_image;    /* R32G32B32A32_SFLOAT 2D storage image 
 typedef struct crv_sv     crv_sv;       /* RenderTechniqueSV                                   */
 typedef struct crv_pt     crv_pt;       /* RenderTechniquePT                                   */
 typedef struct crv_ppm    crv_ppm;      /* RenderTechniquePPM, photon-tracing pass             */
+typedef struct crv_group  crv_group;    /* one member of a multi-GPU sample split              */
+
+/* what a group member publishes so that its peers can map its accumulation images (crv_group_export / crv_group_connect);
+ * plain bytes, to be carried by whatever the host uses between ranks (torch.distributed, MPI, a pipe) */
+typedef struct crv_group_handle {
+    uint64_t pid;            /* exporting process: members of one process use `base` directly            */
+    int32_t  device;         /* CUDA device ordinal of the member                                        */
+    uint32_t rank;
+    uint64_t base;           /* device address of the member's block in the exporting process            */
+    uint64_t bytes;          /* size of the block (flag page + images)                                   */
+    unsigned char ipc[64];   /* cudaIpcMemHandle_t of the block                                          */
+} crv_group_handle;
 
 /* per-render statistics, filled by crv_pt_get_stats (all counts are exact u64 sums) */
 typedef struct crv_pt_stats {
@@ -204,6 +216,10 @@ int  crv_ctx_create(int device, crv_ctx** out);
 int  crv_ctx_destroy(crv_ctx* ctx);
 int  crv_ctx_synchronize(crv_ctx* ctx, void* stream);                 /* vkQueueWaitIdle        */
 int  crv_ctx_launch_count(crv_ctx* ctx, uint64_t* out);               /* kernels launched so far */
+/* a command stream of the context's device (a non-blocking cudaStream_t, usable wherever a `void* stream` is taken);
+ * any cudaStream_t of the same device created by the caller works as well, NULL is the default stream */
+int  crv_stream_create(crv_ctx* ctx, void** out);
+int  crv_stream_destroy(crv_ctx* ctx, void* stream);
 int  crv_ctx_sm_count(crv_ctx* ctx, int* out);
 
 /* ---- volumes: VulkanImage(R32_SFLOAT, 3D) + VulkanSampler (main.cpp:277-285,802-804) ------ */
@@ -244,6 +260,41 @@ int  crv_image_load_checkpoint(crv_image* img, uint32_t* frame_count, int32_t* s
 int  crv_write_png_rgba8(const char* path, uint32_t width, uint32_t height, const unsigned char* rgba);
 /* out = in * scale (the divide-by-spp epilogue after the multi-GPU sum reduce) */
 int  crv_image_scale(crv_image* img, float scale, void* stream);
+
+/* ---- multi-GPU sample split (no counterpart in the single-GPU reference) -----------------------------------
+ * north_star: the density grid and the shadow volume are replicated, the frames (samples per pixel) of one picture are
+ * split across the GPUs of one node -- legal because a sample depends on (frame seed, pixel) only, PathTracer.comp:368,
+ * and the mean is the only coupling, :420-424 -- every GPU accumulates a plain fp32 SUM of its frames (CRV_ACCUM_SUM)
+ * and the buffers are combined and divided by the total sample count.
+ *
+ * A group has one member per GPU: one per process (torchrun, MPI) or several in one process (crv_headless --gpus N).
+ * Each member owns `nbuf` RGBA32F accumulation images (render targets for crv_pt_set_frame_references) in memory its
+ * peers can map over NVLink:
+ *     crv_group_create(ctx, rank, nranks, w, h, nbuf, &g); crv_group_export(g, &mine);
+ *     ... exchange the handles, all members ...            crv_group_connect(g, all_handles_in_rank_order, nranks);
+ *     crv_group_image(g, 0, &img); crv_pt_set_frame_references(pt, &img, 1);
+ *     per picture, on every member:  crv_image_clear(img) ; crv_pt_render_batch(pt, my_seeds, n, 0, CRV_ACCUM_SUM, ...)
+ *                                    crv_group_all_reduce_sum_scale(g, 0, 1.0f / spp_total, stream)
+ * crv_group_all_reduce_sum_scale is ONE kernel per member that synchronises with its peers through flags in mapped
+ * memory, sums its band of rows from all members' images in rank order, scales it and writes it into all members'
+ * images: afterwards every member's image holds the same, final picture (bit-identical on all members, and independent
+ * of timing).  All members must call it the same number of times with the same buffer index; each call is asynchronous
+ * on the caller's stream.  A member whose peers never arrive gives up after crv_group_set_timeout_ms (default 10 s) and
+ * crv_group_status reports it.
+ * crv_group_nccl_*: the same operation as ncclAllReduce + a scale kernel through the libnccl.so.2 already loaded in the
+ * process (rank 0 creates the id, everybody passes it to crv_group_nccl_init). */
+int  crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, crv_group** out);
+int  crv_group_destroy(crv_group* g);
+int  crv_group_export(crv_group* g, crv_group_handle* out);
+int  crv_group_connect(crv_group* g, const crv_group_handle* handles, uint32_t count);
+int  crv_group_image(crv_group* g, uint32_t buffer, crv_image** out);              /* owned by the group */
+int  crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream);
+int  crv_group_set_timeout_ms(crv_group* g, uint32_t ms);
+int  crv_group_status(crv_group* g, void* stream);                                  /* CRV_OK, or the barrier that timed out */
+int  crv_group_last_reduce_ms(crv_group* g, float* ms);                             /* device time of the last reduce call of this member */
+int  crv_group_nccl_unique_id(unsigned char id_out[128]);
+int  crv_group_nccl_init(crv_group* g, const unsigned char id[128]);
+int  crv_group_nccl_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream);
 
 /* ---- RenderTechniqueSV (RenderTechniqueSV.h:7-39, .cpp:4-113) ----------------------------- */
 int  crv_sv_create(crv_ctx* ctx, const crv_shadow_volume_properties* props, const crv_push_constants* pc, crv_sv** out);

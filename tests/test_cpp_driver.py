@@ -57,6 +57,37 @@ def test_cpp_driver_matches_the_python_host_bitwise(crv, ctx):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gpus,same_device", [(2, True), (3, True), (2, False)])
+def test_cpp_driver_sample_split(crv, gpus, same_device):
+    """crv_headless --gpus N: crv::DeviceGroup (crv_group_*) from C++ -- one replica per member, frames f mod N, one combine
+    kernel per member.  Every member must hold the same picture, equal to the 1-GPU picture within summation order (1e-6)."""
+    if not same_device and crv.capi.lib.crv_device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    n, w, h, nsv, spp = 40, 96, 64, 56, 7
+    args = ["--fbm", n, "--width", w, "--height", h, "--nsv", nsv, "--spp", spp, "--g", 0.85, "--absorption", 0.1]
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        one, many = os.path.join(d, "one.pfm"), os.path.join(d, "many.pfm")
+        r1 = _run(args + ["--pfm", one])
+        assert r1.returncode == 0, r1.stderr
+        rn = _run(args + ["--pfm", many, "--gpus", gpus] + (["--same-device"] if same_device else []))
+        assert rn.returncode == 0, rn.stderr
+        o1, on = json.loads(r1.stdout), json.loads(rn.stdout)
+        assert on["gpus"] == gpus and on["members_identical"] is True and on["mode"] == "split"
+        assert on["paths"] == o1["paths"] == w * h * spp and on["collisions"] == o1["collisions"]
+
+        def pfm(path):
+            with open(path, "rb") as f:
+                assert f.readline().strip() == b"PF"
+                ww, hh = map(int, f.readline().split())
+                f.readline()
+                return np.frombuffer(f.read(), np.float32).reshape(hh, ww, 3)
+        a, b = pfm(one), pfm(many)
+        assert a.max() > 0.1
+        assert (np.abs(a - b) / np.maximum(np.abs(a), 1e-3)).max() <= 1e-5      # running mean (1 GPU) vs sum / spp (split)
+
+
+@pytest.mark.gpu
 def test_cpp_driver_photon_mapping_frames_match_the_python_host(crv, ctx):
     """--ppm N: crv::RenderTechniquePPM (include/crv/render_technique.h) driven like main.cpp:204-207/813 over the scene
     crv_headless already holds.  Photon slots are claimed with atomics, so two runs are not bit-identical (PPM_PT.comp's own

@@ -1,6 +1,8 @@
 """N > 1 path on the CPU: two gloo ranks split the frame list, each accumulates a local fp32 SUM (computed by the
-oracle here -- no GPU in this container), one all-reduce adds them, a divide by spp_total gives the mean.  Checks the
-host logic bench.py uses (cloudrendering_vulkan_b200.multigpu) and the <= 1e-6 agreement with the 1-rank result."""
+oracle here -- no GPU in this container), the sums are added in rank order and divided by spp_total -- the arithmetic of
+crv_group_all_reduce_sum_scale (csrc/group.cu; its device side is tests/test_group.py).  Checks the host logic of
+cloudrendering_vulkan_b200.multigpu (frame partition, the handle exchange between ranks) and the <= 1e-6 agreement with the
+1-rank result."""
 import os
 import socket
 import sys
@@ -47,15 +49,26 @@ def _worker(rank, world, port, spp, out_dir):
     import torch
     import torch.distributed as dist
     crv, orc, size, cloud, sv, cam, cp, par, sp = _scene()
-    from cloudrendering_vulkan_b200.multigpu import frames_for_rank, reduce_accumulation
+    from cloudrendering_vulkan_b200.multigpu import all_gather_bytes, broadcast_bytes, frames_for_rank
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the messenger that carries the members' 96-byte memory handles (and the 128-byte NCCL id) between the ranks
+    mine = bytes([rank]) * crv.capi.C.sizeof(crv.capi.GroupHandle)
+    got = all_gather_bytes(mine, world)
+    assert [b[0] for b in got] == list(range(world)) and all(len(b) == 96 for b in got)
+    assert broadcast_bytes(b"x" * 128 if rank == 0 else None, 0, world) == b"x" * 128
     seeds = frames_for_rank(crv.msvc_rand_sequence(spp), rank, world)
-    acc = torch.from_numpy(_local_sum(orc, (size, cloud, sv, cam, cp, par, sp), seeds))
-    reduce_accumulation(acc, spp)
+    acc = _local_sum(orc, (size, cloud, sv, cam, cp, par, sp), seeds)
+    # what the combine kernel computes: members' sums added in rank order, times 1 / spp_total
+    parts = [torch.zeros(acc.shape, dtype=torch.float32) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(acc))
+    total = parts[0].numpy().copy()
+    for p in parts[1:]:
+        total = total + p.numpy()
+    total = total * np.float32(1.0 / spp)
     if rank == 0:
-        np.save(os.path.join(out_dir, "reduced.npy"), acc.numpy())
+        np.save(os.path.join(out_dir, "reduced.npy"), total)
     dist.barrier()
     dist.destroy_process_group()
 
