@@ -110,7 +110,10 @@ SIGNATURES = {
     "crv_ctx_sm_count": (C.c_int, [_vp, _P(C.c_int)]),
     "crv_stream_create": (C.c_int, [_vp, _P(_vp)]),
     "crv_stream_destroy": (C.c_int, [_vp, _vp]),
-    "crv_group_create": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _P(_vp)]),
+    "crv_group_create": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, C.c_uint64, _P(_vp)]),
+    "crv_group_staging_ptr": (C.c_int, [_vp, _u32, _P(_vp)]),
+    "crv_group_staging_all_gather": (C.c_int, [_vp, _u32, _vp, C.c_uint64, _vp]),
+    "crv_group_staging_release": (C.c_int, [_vp, _u32, _vp]),
     "crv_group_destroy": (C.c_int, [_vp]),
     "crv_group_export": (C.c_int, [_vp, _P(GroupHandle)]),
     "crv_group_connect": (C.c_int, [_vp, _P(GroupHandle), _u32]),

@@ -140,7 +140,13 @@ struct crv_pt {
     int track_threshold = 20;
     int steps_per_decision = 0;        // 0 = the scheduler's own default (pool: its unrolled round; lanes: 6)
     int scheduler = CRV_PT_SCHED_POOL;
-    uint64_t sample_budget = 6ull << 30;   // c2 (1080p, 256 frames) in one launch: every launch ends in a tail of ~0.1 ms
+    // Sample records are sized by the hit count once it is known on the host (copied back asynchronously after a
+    // classification, never waited for), by the pixel count until then: c2's 256 frames need 290 MB, not 4.2 GB.
+    uint64_t sample_budget = 2ull << 30;
+    uint32_t* counts_host = nullptr;       // pinned: [hits, misses] of the last classification
+    cudaEvent_t counts_ev = nullptr;
+    bool counts_pending = false, nhit_valid = false;
+    uint32_t nhit_known = 0;
 };
 
 // volumes carry an upload generation so cached q-tables notice re-uploads
@@ -823,6 +829,8 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
     pt->sets.resize(1);
     CRV_CUDA(cudaMalloc(&pt->job_counter, sizeof(unsigned int)));
     CRV_CUDA(cudaMalloc(&pt->nhit, 2 * sizeof(uint32_t)));      // [0] hits, [1] misses
+    CRV_CUDA(cudaMallocHost(&pt->counts_host, 2 * sizeof(uint32_t)));
+    CRV_CUDA(cudaEventCreateWithFlags(&pt->counts_ev, cudaEventDisableTiming));
     CRV_CUDA(cudaMalloc(&pt->occ_ext, 6 * sizeof(int)));
     CRV_CUDA(cudaMalloc(&pt->occ_aabb, 6 * sizeof(float)));
     CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
@@ -1272,6 +1280,8 @@ int crv_pt_destroy(crv_pt* pt)
     if (pt->hitlist) cudaFree(pt->hitlist);
     if (pt->start) cudaFree(pt->start);
     if (pt->nhit) cudaFree(pt->nhit);
+    if (pt->counts_host) cudaFreeHost(pt->counts_host);
+    if (pt->counts_ev) cudaEventDestroy(pt->counts_ev);
     if (pt->occ_ext) cudaFree(pt->occ_ext);
     if (pt->occ_aabb) cudaFree(pt->occ_aabb);
     if (pt->misslist) cudaFree(pt->misslist);
@@ -1668,11 +1678,21 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
             pt->launches++;
             std::memcpy(pt->geom_key, key, sizeof(key));
             pt->geom_valid = true;
+            // the counts travel to the host behind the classification; a later render call picks them up if they have arrived
+            CRV_CUDA(cudaMemcpyAsync(pt->counts_host, pt->nhit, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CRV_CUDA(cudaEventRecord(pt->counts_ev, s));
+            pt->counts_pending = true;
+            pt->nhit_valid = false;
+        } else if (pt->counts_pending && cudaEventQuery(pt->counts_ev) == cudaSuccess) {
+            pt->nhit_known = pt->counts_host[0];
+            pt->nhit_valid = true;
+            pt->counts_pending = false;
         }
+        (void)cudaGetLastError();          // cudaErrorNotReady from the query is not an error
     }
 
     // rounds of `per_round` frames through the sample buffer (sized for the worst case: every pixel hits)
-    const size_t frame_bytes = (size_t)c.npix * sizeof(float2);
+    const size_t frame_bytes = (size_t)(pt->nhit_valid ? (pt->nhit_known > 0 ? pt->nhit_known : 1u) : c.npix) * sizeof(float2);
     uint64_t per_round = pt->sample_budget / frame_bytes;
     if (per_round < 1) per_round = 1;
     // job ids are 32-bit, and every warp may bump the job counter once more after the queue ran dry (<= 32 per warp, a few

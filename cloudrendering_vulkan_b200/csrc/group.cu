@@ -38,11 +38,17 @@ constexpr int GROUP_MAX = 16;
 constexpr size_t FLAG_PAGE = 4096;                 // start[16], end[16], done counter, error word
 constexpr int RED_THREADS = 512;
 
+constexpr int GROUP_MAX_BUF = 8;
 struct GroupFlags {
     uint32_t start[GROUP_MAX];
     uint32_t end[GROUP_MAX];
     uint32_t done;                                 // CTAs of the local kernel that have stored their part of the band
-    uint32_t error;                                // sticky: 1 = start barrier timed out, 2 = end barrier timed out
+    uint32_t error;                                // sticky: 1 = start barrier timed out, 2 = end barrier timed out, 3 = staging wait
+    uint32_t pad[30];
+    // staging all-gather: arrived[b][p] = epoch of the last slice member p has pushed into MY staging buffer b;
+    // released[b][p] = last epoch of ITS staging buffer b that member p has finished reading
+    uint32_t arrived[GROUP_MAX_BUF][GROUP_MAX];
+    uint32_t released[GROUP_MAX_BUF][GROUP_MAX];
 };
 static_assert(sizeof(GroupFlags) <= FLAG_PAGE, "flag page");
 
@@ -142,6 +148,23 @@ __global__ void __launch_bounds__(RED_THREADS) group_reduce_kernel(const __grid_
     }
 }
 
+// fallbacks for cuStreamWriteValue32 / cuStreamWaitValue32 where the driver does not offer them
+struct FlagList {
+    uint32_t* addr[GROUP_MAX];
+    uint32_t n;
+};
+__global__ void flag_write_kernel(const __grid_constant__ FlagList f, uint32_t value)
+{
+    if (threadIdx.x < f.n) {
+        __threadfence_system();
+        st_release_sys(f.addr[threadIdx.x], value);
+    }
+}
+__global__ void flag_wait_kernel(const __grid_constant__ FlagList f, uint32_t value, unsigned long long timeout_ns, uint32_t* error)
+{
+    if (threadIdx.x < f.n && !wait_flag(f.addr[threadIdx.x], value, timeout_ns)) atomicExch(error, 3u);
+}
+
 __global__ void group_scale_kernel(float4* __restrict__ img, uint32_t n4, float scale)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
@@ -184,11 +207,32 @@ bool nccl_load()
 
 }  // namespace
 
+// cuStreamWriteValue32 / cuStreamWaitValue32 through the runtime's driver entry points (no link-time libcuda dependency)
+typedef int (*StreamValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+static StreamValue32Fn g_stream_write32 = nullptr, g_stream_wait32 = nullptr;
+static bool g_memops_probed = false;
+static void probe_stream_memops()
+{
+    if (g_memops_probed) return;
+    g_memops_probed = true;
+    void *w = nullptr, *q = nullptr;
+    cudaDriverEntryPointQueryResult rw, rq;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &rw) == cudaSuccess && rw == cudaDriverEntryPointSuccess &&
+        cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &rq) == cudaSuccess && rq == cudaDriverEntryPointSuccess && w && q) {
+        g_stream_write32 = reinterpret_cast<StreamValue32Fn>(w);
+        g_stream_wait32 = reinterpret_cast<StreamValue32Fn>(q);
+    }
+    (void)cudaGetLastError();
+}
+
 struct crv_group {
     crv_ctx* ctx = nullptr;
     uint32_t rank = 0, nranks = 1, nbuf = 1;
     uint32_t width = 0, height = 0;
     size_t image_bytes = 0, block_bytes = 0;
+    size_t staging_bytes = 0, staging_offset = 0;  // per-buffer size (256-aligned) and offset of staging buffer 0 in the block
+    uint32_t stage_epoch[GROUP_MAX_BUF] = {};
+    bool use_memops = false;
     unsigned char* block = nullptr;                // own allocation
     unsigned char* peer[GROUP_MAX] = {};           // mapped peers (own block at [rank])
     bool peer_ipc[GROUP_MAX] = {};                 // opened with cudaIpcOpenMemHandle (to be closed)
@@ -202,10 +246,16 @@ struct crv_group {
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+#define CRV_TRY_G(expr)                \
+    do {                               \
+        const int _rc = (expr);        \
+        if (_rc != CRV_OK) return _rc; \
+    } while (0)
 
 extern "C" {
 
-int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, crv_group** out)
+int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, uint64_t staging_bytes,
+                     crv_group** out)
 {
     CRV_REQUIRE(ctx && out, "crv_group_create: null argument");
     *out = nullptr;
@@ -221,7 +271,11 @@ int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t widt
     g->width = width;
     g->height = height;
     g->image_bytes = ((size_t)width * height * 16 + 255) / 256 * 256;
-    g->block_bytes = FLAG_PAGE + g->image_bytes * nbuf;
+    g->staging_bytes = ((size_t)staging_bytes + 255) / 256 * 256;
+    g->staging_offset = FLAG_PAGE + g->image_bytes * nbuf;
+    g->block_bytes = g->staging_offset + g->staging_bytes * nbuf;
+    probe_stream_memops();
+    g->use_memops = g_stream_write32 != nullptr;
     cudaError_t e = cudaMalloc(&g->block, g->block_bytes);
     if (e != cudaSuccess) {
         crv_set_error("crv_group_create: cudaMalloc of %zu bytes failed: %s", g->block_bytes, cudaGetErrorString(e));
@@ -386,8 +440,8 @@ int crv_group_status(crv_group* g, void* stream)
     CRV_CUDA(cudaMemcpyAsync(&err, g->block + offsetof(GroupFlags, error), sizeof(err), cudaMemcpyDeviceToHost, as_stream(stream)));
     CRV_CUDA(cudaStreamSynchronize(as_stream(stream)));
     if (err != 0) {
-        crv_set_error("crv_group: member %u gave up waiting for a peer at the %s barrier (timeout %llu ms)", g->rank, err == 1 ? "start" : "end",
-                      g->timeout_ns / 1000000ull);
+        crv_set_error("crv_group: member %u gave up waiting for a peer at the %s (timeout %llu ms)", g->rank,
+                      err == 1 ? "start barrier" : err == 2 ? "end barrier" : "staging exchange", g->timeout_ns / 1000000ull);
         return CRV_ERR_CUDA;
     }
     return CRV_OK;
@@ -401,6 +455,97 @@ int crv_group_last_reduce_ms(crv_group* g, float* ms)
     CRV_CUDA(cudaEventSynchronize(g->ev1));
     CRV_CUDA(cudaEventElapsedTime(ms, g->ev0, g->ev1));
     return CRV_OK;
+}
+
+// ---- staging all-gather: a replicated input (the density grid) crosses PCIe once per job, 1/N on every member's link ----------
+static int flags_write(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s)
+{
+    if (g->use_memops) {
+        bool ok = true;
+        for (uint32_t i = 0; i < n && ok; ++i) ok = g_stream_write32(s, (unsigned long long)(uintptr_t)addrs[i], value, 0u) == 0;
+        if (ok) return CRV_OK;
+        g->use_memops = false;                     // e.g. peer addresses not accepted: the kernels do the same (re-writing a flag is harmless)
+    }
+    FlagList f{};
+    f.n = n;
+    for (uint32_t i = 0; i < n; ++i) f.addr[i] = addrs[i];
+    flag_write_kernel<<<1, 32, 0, s>>>(f, value);
+    g->ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    return CRV_OK;
+}
+
+static int flags_wait(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s)
+{
+    if (g->use_memops) {
+        bool ok = true;
+        for (uint32_t i = 0; i < n && ok; ++i) ok = g_stream_wait32(s, (unsigned long long)(uintptr_t)addrs[i], value, /* CU_STREAM_WAIT_VALUE_GEQ */ 0u) == 0;
+        if (ok) return CRV_OK;
+        g->use_memops = false;
+    }
+    FlagList f{};
+    f.n = n;
+    for (uint32_t i = 0; i < n; ++i) f.addr[i] = addrs[i];
+    flag_wait_kernel<<<1, 32, 0, s>>>(f, value, g->timeout_ns, &reinterpret_cast<GroupFlags*>(g->block)->error);
+    g->ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    return CRV_OK;
+}
+
+int crv_group_staging_ptr(crv_group* g, uint32_t buffer, void** out)
+{
+    CRV_REQUIRE(g && out, "crv_group_staging_ptr: null argument");
+    CRV_REQUIRE(buffer < g->nbuf && g->staging_bytes > 0, "crv_group_staging_ptr: no such staging buffer");
+    *out = g->block + g->staging_offset + buffer * g->staging_bytes;
+    return CRV_OK;
+}
+
+int crv_group_staging_all_gather(crv_group* g, uint32_t buffer, const void* host_src, uint64_t bytes, void* stream)
+{
+    CRV_REQUIRE(g && host_src, "crv_group_staging_all_gather: null argument");
+    CRV_REQUIRE(buffer < g->nbuf && bytes > 0 && bytes <= g->staging_bytes, "crv_group_staging_all_gather: buffer index or size out of range");
+    CRV_REQUIRE(g->connected, "crv_group_staging_all_gather: crv_group_connect has not been called");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = as_stream(stream);
+    const size_t off0 = g->staging_offset + buffer * g->staging_bytes;
+    const uint32_t epoch = ++g->stage_epoch[buffer];
+    if (g->nranks == 1) {
+        CRV_CUDA(cudaMemcpyAsync(g->block + off0, host_src, bytes, cudaMemcpyHostToDevice, s));
+        return CRV_OK;
+    }
+    const size_t slice = ((bytes + g->nranks - 1) / g->nranks + 255) / 256 * 256;
+    const size_t lo = (size_t)g->rank * slice < bytes ? (size_t)g->rank * slice : bytes;
+    const size_t len = lo + slice <= bytes ? slice : bytes - lo;
+    GroupFlags* mine = reinterpret_cast<GroupFlags*>(g->block);
+    uint32_t* addrs[GROUP_MAX];
+    uint32_t n = 0;
+    // the peers must have finished reading what the previous round left in their buffers
+    for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->released[buffer][p];
+    CRV_TRY_G(flags_wait(g, addrs, n, epoch - 1u, s));
+    if (len > 0) {
+        CRV_CUDA(cudaMemcpyAsync(g->block + off0 + lo, static_cast<const unsigned char*>(host_src) + lo, len, cudaMemcpyHostToDevice, s));
+        for (uint32_t p = 0; p < g->nranks; ++p)       // copy engines, NVLink: my slice into every peer's buffer
+            if (p != g->rank) CRV_CUDA(cudaMemcpyAsync(g->peer[p] + off0 + lo, g->block + off0 + lo, len, cudaMemcpyDefault, s));
+    }
+    n = 0;
+    for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[p])->arrived[buffer][g->rank];
+    CRV_TRY_G(flags_write(g, addrs, n, epoch, s));
+    n = 0;
+    for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->arrived[buffer][p];
+    CRV_TRY_G(flags_wait(g, addrs, n, epoch, s));
+    return CRV_OK;
+}
+
+int crv_group_staging_release(crv_group* g, uint32_t buffer, void* stream)
+{
+    CRV_REQUIRE(g != nullptr, "crv_group_staging_release: null group");
+    CRV_REQUIRE(buffer < g->nbuf && g->staging_bytes > 0, "crv_group_staging_release: no such staging buffer");
+    if (g->nranks == 1) return CRV_OK;
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    uint32_t* addrs[GROUP_MAX];
+    uint32_t n = 0;
+    for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[p])->released[buffer][g->rank];
+    return flags_write(g, addrs, n, g->stage_epoch[buffer], as_stream(stream));
 }
 
 // ---- NCCL variant ----------------------------------------------------------------------------------------------------------

@@ -69,11 +69,11 @@ class SampleSplit:
     """One member of the split around a HeadlessRenderer: re-targets the renderer's path tracer at the group's image and
     renders pictures whose frames are spread over the members."""
 
-    def __init__(self, renderer, rank: int, world: int, nbuf: int = 1, dist_group=None, connect: bool = True):
+    def __init__(self, renderer, rank: int, world: int, nbuf: int = 1, dist_group=None, connect: bool = True, staging_bytes: int = 0):
         self.r = renderer
         self.rank, self.world = int(rank), int(world)
         img = renderer.resultImage
-        self.group = Group(renderer.ctx, rank, world, img.width, img.height, nbuf)
+        self.group = Group(renderer.ctx, rank, world, img.width, img.height, nbuf, staging_bytes)
         if connect:
             connect_group(self.group, dist_group)
         self.use_buffer(0)

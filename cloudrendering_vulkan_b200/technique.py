@@ -90,13 +90,17 @@ class Volume:
         self.handle = C.c_void_p()
         check(lib.crv_volume_create(ctx.handle, nx, ny, nz, self.layout, C.byref(self.handle)))
 
-    def upload(self, data: np.ndarray, stream=0):
-        """x-fastest host floats (what Grid3D::GetData holds; staging copy of main.cpp:288-295)."""
+    def upload(self, data: np.ndarray, stream=0, wait: bool = True):
+        """x-fastest host floats (what Grid3D::GetData holds; staging copy of main.cpp:288-295).
+        wait=False: asynchronous on `stream`; the caller keeps `data` (contiguous float32, ideally pinned) alive."""
         a = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
         if a.size != self.shape[0] * self.shape[1] * self.shape[2]:
             raise ValueError("volume upload: size mismatch")
+        if not wait and a.ctypes.data != np.asarray(data).ctypes.data:
+            raise ValueError("volume upload: wait=False needs a contiguous float32 array (no temporary copy)")
         check(lib.crv_volume_upload(self.handle, a.ctypes.data_as(C.c_void_p), 0, _stream(stream)))
-        self.ctx.synchronize(stream)          # `a` may be a temporary
+        if wait:
+            self.ctx.synchronize(stream)      # `a` may be a temporary
 
     def upload_device(self, device_ptr: int, stream=0):
         check(lib.crv_volume_upload(self.handle, C.c_void_p(int(device_ptr)), 1, _stream(stream)))
@@ -203,12 +207,12 @@ class Group:
         pt.SetFrameReferences([g.image(0)]) ... RenderBatch(my_seeds, 0, ACCUM_SUM) ... g.all_reduce_sum_scale(1 / spp_total)
     """
 
-    def __init__(self, ctx: Context, rank: int, nranks: int, width: int, height: int, nbuf: int = 1):
+    def __init__(self, ctx: Context, rank: int, nranks: int, width: int, height: int, nbuf: int = 1, staging_bytes: int = 0):
         self.ctx = ctx
         self.rank, self.nranks, self.nbuf = int(rank), int(nranks), int(nbuf)
         self.width, self.height = int(width), int(height)
         self.handle = C.c_void_p()
-        check(lib.crv_group_create(ctx.handle, rank, nranks, width, height, nbuf, C.byref(self.handle)))
+        check(lib.crv_group_create(ctx.handle, rank, nranks, width, height, nbuf, C.c_uint64(staging_bytes), C.byref(self.handle)))
         self._images = {}
 
     def export(self) -> bytes:
@@ -235,6 +239,19 @@ class Group:
 
     def all_reduce_sum_scale(self, scale: float, stream=0, buffer: int = 0):
         check(lib.crv_group_all_reduce_sum_scale(self.handle, buffer, C.c_float(scale), _stream(stream)))
+
+    # ---- replicated host input: 1/N per member over PCIe, exchanged GPU to GPU by the copy engines ----
+    def staging_ptr(self, buffer: int = 0) -> int:
+        p = C.c_void_p()
+        check(lib.crv_group_staging_ptr(self.handle, buffer, C.byref(p)))
+        return p.value or 0
+
+    def staging_all_gather(self, buffer: int, host_ptr: int, nbytes: int, stream=0):
+        """host_ptr: address of the whole array in (pinned) host memory; asynchronous on `stream`"""
+        check(lib.crv_group_staging_all_gather(self.handle, buffer, C.c_void_p(int(host_ptr)), C.c_uint64(nbytes), _stream(stream)))
+
+    def staging_release(self, buffer: int = 0, stream=0):
+        check(lib.crv_group_staging_release(self.handle, buffer, _stream(stream)))
 
     def set_timeout_ms(self, ms: int):
         check(lib.crv_group_set_timeout_ms(self.handle, int(ms)))

@@ -151,10 +151,20 @@ private:
 // AllReduceSumScale adds all members' images in rank order, scales and leaves the same picture in every member's image.
 class DeviceGroup {
 public:
-    DeviceGroup(Device* device, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf = 1) : m_width(width), m_height(height)
+    DeviceGroup(Device* device, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf = 1, uint64_t stagingBytes = 0)
+        : m_width(width), m_height(height)
     {
-        Check(crv_group_create(device->Get(), rank, nranks, width, height, nbuf, &m_group));
+        Check(crv_group_create(device->Get(), rank, nranks, width, height, nbuf, stagingBytes, &m_group));
     }
+    // replicated host input: 1/N per member over PCIe, exchanged GPU to GPU by the copy engines (crv_group_staging_*)
+    void* StagingAllGather(const void* hostSrc, uint64_t bytes, CommandStream stream = nullptr, uint32_t buffer = 0)
+    {
+        void* p = nullptr;
+        Check(crv_group_staging_all_gather(m_group, buffer, hostSrc, bytes, stream));
+        Check(crv_group_staging_ptr(m_group, buffer, &p));
+        return p;
+    }
+    void StagingRelease(CommandStream stream = nullptr, uint32_t buffer = 0) { Check(crv_group_staging_release(m_group, buffer, stream)); }
     ~DeviceGroup() { crv_group_destroy(m_group); }
     DeviceGroup(const DeviceGroup&) = delete;
     DeviceGroup& operator=(const DeviceGroup&) = delete;

@@ -270,7 +270,7 @@ int  crv_image_scale(crv_image* img, float scale, void* stream);
  * A group has one member per GPU: one per process (torchrun, MPI) or several in one process (crv_headless --gpus N).
  * Each member owns `nbuf` RGBA32F accumulation images (render targets for crv_pt_set_frame_references) in memory its
  * peers can map over NVLink:
- *     crv_group_create(ctx, rank, nranks, w, h, nbuf, &g); crv_group_export(g, &mine);
+ *     crv_group_create(ctx, rank, nranks, w, h, nbuf, 0, &g); crv_group_export(g, &mine);
  *     ... exchange the handles, all members ...            crv_group_connect(g, all_handles_in_rank_order, nranks);
  *     crv_group_image(g, 0, &img); crv_pt_set_frame_references(pt, &img, 1);
  *     per picture, on every member:  crv_image_clear(img) ; crv_pt_render_batch(pt, my_seeds, n, 0, CRV_ACCUM_SUM, ...)
@@ -283,7 +283,8 @@ int  crv_image_scale(crv_image* img, float scale, void* stream);
  * crv_group_status reports it.
  * crv_group_nccl_*: the same operation as ncclAllReduce + a scale kernel through the libnccl.so.2 already loaded in the
  * process (rank 0 creates the id, everybody passes it to crv_group_nccl_init). */
-int  crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, crv_group** out);
+int  crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, uint64_t staging_bytes,
+                      crv_group** out);
 int  crv_group_destroy(crv_group* g);
 int  crv_group_export(crv_group* g, crv_group_handle* out);
 int  crv_group_connect(crv_group* g, const crv_group_handle* handles, uint32_t count);
@@ -292,6 +293,16 @@ int  crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, 
 int  crv_group_set_timeout_ms(crv_group* g, uint32_t ms);
 int  crv_group_status(crv_group* g, void* stream);                                  /* CRV_OK, or the barrier that timed out */
 int  crv_group_last_reduce_ms(crv_group* g, float* ms);                             /* device time of the last reduce call of this member */
+/* Replicated input from the host (the density grid is the same on every member): with staging_bytes > 0 every member also
+ * owns `nbuf` staging buffers.  crv_group_staging_all_gather: member r copies slice r (1/N) of the host array into its
+ * buffer and pushes it into every peer's buffer with copy-engine peer copies; when the call has completed on `stream` the
+ * member's staging buffer (crv_group_staging_ptr, e.g. for crv_volume_upload(..., is_device = 1)) holds the whole array.
+ * So the array crosses PCIe once per job, on N links in parallel, and no kernel is involved (the waits and signals are
+ * stream memory operations): the exchange overlaps a kernel that holds every SM.  crv_group_staging_release tells the
+ * peers that this member has finished reading its buffer; the next all-gather into the same buffer index waits for it. */
+int  crv_group_staging_ptr(crv_group* g, uint32_t buffer, void** device_ptr_out);
+int  crv_group_staging_all_gather(crv_group* g, uint32_t buffer, const void* host_src, uint64_t bytes, void* stream);
+int  crv_group_staging_release(crv_group* g, uint32_t buffer, void* stream);
 int  crv_group_nccl_unique_id(unsigned char id_out[128]);
 int  crv_group_nccl_init(crv_group* g, const unsigned char id[128]);
 int  crv_group_nccl_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream);
@@ -338,7 +349,8 @@ int  crv_pt_record_draw_commands(crv_pt* pt, void* stream, unsigned image_index)
 int  crv_pt_set_extensions(crv_pt* pt, const crv_pt_extensions* ext);
 /* n progressive frames in one call: identical, bit for bit, to n crv_pt_record_draw_commands
  * calls with seed = seeds[i] and frameCount = first_frame_count + i (CRV_ACCUM_RUNNING_MEAN),
- * or a plain fp32 sum of the n samples added to the image in frame order (CRV_ACCUM_SUM).
+ * or the fp32 sum of the n samples added to the image (CRV_ACCUM_SUM: the multi-GPU split's mode; deterministic, but the
+ * order of the additions is the library's choice -- a pixel whose sample is the same in every frame gets n * sample).
  * This is the persistent-thread wavefront fast path.  PushConstants are not modified. */
 int  crv_pt_render_batch(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t first_frame_count,
                          int accum_mode, void* stream, unsigned image_index);

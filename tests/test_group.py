@@ -122,6 +122,37 @@ def test_epochs_and_double_buffering(crv):
     _close(ms)
 
 
+@pytest.mark.parametrize("n,distinct", [(2, False), (3, False), (1, False), (2, True), (4, True)])
+def test_staging_all_gather(crv, n, distinct):
+    """a replicated host array: every member uploads 1/N and pushes it to its peers on the copy engines; two rounds into the
+    same buffer (the second must wait for the peers' release) and a ragged size"""
+    import ctypes as C
+    elems = 1_000_003
+    ctxs = [crv.Context(d) for d in _devices(crv, n, distinct)]
+    groups = [crv.Group(c, k, n, 16, 16, nbuf=2, staging_bytes=4 * elems) for k, c in enumerate(ctxs)]
+    hs = [g.export() for g in groups]
+    for g in groups:
+        g.connect(hs)
+    streams = [crv.Stream(c) for c in ctxs]
+    vols = [crv.Volume(c, elems, 1, 1, layout="linear") for c in ctxs]
+    rng = np.random.default_rng(3)
+    for rnd in range(3):
+        data = rng.random(elems, dtype=np.float32)
+        buf = rnd % 2
+        for g, s, v in zip(groups, streams, vols):
+            g.staging_all_gather(buf, data.ctypes.data, 4 * elems, int(s))
+            v.upload_device(g.staging_ptr(buf), int(s))
+            g.staging_release(buf, int(s))
+        for g, s, v in zip(groups, streams, vols):
+            assert np.array_equal(v.download(int(s)), data), f"round {rnd}: member {g.rank} holds another array"
+            g.status(int(s))
+    for g, s, v, c in zip(groups, streams, vols, ctxs):
+        v.close()
+        s.close()
+        g.close()
+        c.close()
+
+
 def test_single_member_group_is_a_scale(crv, ctx):
     g = crv.Group(ctx, 0, 1, 32, 8)
     img = g.image(0)
