@@ -117,6 +117,8 @@ struct crv_pt {
     uint8_t* qcoarse = nullptr;       // pool scheduler: byte thresholds per coarse cell (shared-memory resident)
     uint32_t qcoarse_bytes = 0;       // padded to 16
     int qcoarse_shift = 0;            // coarse cell = (8 << shift)^3 voxels
+    int forced_shift = -1;            // crv_pt_set_coarse_shift: >= 0 asks for at least this shift (tests: the 512^3 / 1024^3 table shapes on small grids)
+    int q_forced_for = -1;            // forced_shift the tables were built for
     const crv_volume* q_for_vol = nullptr;
     float q_for_max_ext = -1.0f;
     uint64_t q_for_generation = 0;
@@ -841,10 +843,10 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
 
 // Coarse threshold table (pt_wavefront.h: PTConst::qcoarse): cell size and padded byte count for a cloud volume, and the
 // approximate-cell-coordinate constants of the tracker's pre-test for the geometry in c (cb0 / cb1 / cext / cloud set).
-static void coarse_table_shape(const crv_volume* cv, int& shift, uint32_t& bytes)
+static void coarse_table_shape(const crv_volume* cv, int min_shift, int& shift, uint32_t& bytes)
 {
     size_t cells = 0;
-    for (shift = 0;; ++shift) {
+    for (shift = min_shift > 0 ? min_shift : 0;; ++shift) {
         const size_t ncx = ((cv->nbx - 1) >> shift) + 1, ncy = ((cv->nby - 1) >> shift) + 1, ncz = ((cv->nbz - 1) >> shift) + 1;
         cells = (ncx + 2) * (ncy + 2) * (ncz + 2);
         if (cells + 1 <= (size_t)crv_pt_pool_smem_budget()) break;
@@ -1091,16 +1093,18 @@ static int ppm_build_const(crv_ppm* ppm, cudaStream_t s, PPMConst& k)
                 "RenderTechniquePPM: cloud image size differs from CloudProperties.voxelCount");
     const size_t nbricks = (size_t)cv->nbx * cv->nby * cv->nbz;
     if (!cv->brick_max_valid) CRV_TRY(crv_launch_brick_max(ppm->ctx, cv, s));
-    if (ppm->qtable_elems != nbricks) {
+    // (keyed on the three brick counts: the padded coarse table depends on them separately)
+    if (ppm->qtable_elems != nbricks || ppm->q_dims[0] != cv->nbx || ppm->q_dims[1] != cv->nby || ppm->q_dims[2] != cv->nbz) {
         if (ppm->qtable) CRV_CUDA(cudaFree(ppm->qtable));
         ppm->qtable = nullptr;
         ppm->qtable_elems = 0;
         CRV_CUDA(cudaMalloc(&ppm->qtable, nbricks * sizeof(float)));
         if (ppm->qcoarse) CRV_CUDA(cudaFree(ppm->qcoarse));
         ppm->qcoarse = nullptr;
-        coarse_table_shape(cv, ppm->qcoarse_shift, ppm->qcoarse_bytes);
+        coarse_table_shape(cv, 0, ppm->qcoarse_shift, ppm->qcoarse_bytes);
         CRV_CUDA(cudaMalloc(&ppm->qcoarse, ppm->qcoarse_bytes));
         ppm->qtable_elems = nbricks;
+        ppm->q_dims[0] = cv->nbx; ppm->q_dims[1] = cv->nby; ppm->q_dims[2] = cv->nbz;
     }
     CRV_CUDA(cudaMemsetAsync(ppm->qcoarse, 128, ppm->qcoarse_bytes, s));
     CRV_TRY(crv_launch_qcoarse(ppm->ctx, cv->brick_absmax_wide, ppm->qcoarse, (int)cv->nbx, (int)cv->nby, (int)cv->nbz, ppm->qcoarse_shift, c.max_ext, s));
@@ -1404,6 +1408,21 @@ int crv_pt_set_skip_level(crv_pt* pt, int level)
     return CRV_OK;
 }
 
+int crv_pt_set_coarse_shift(crv_pt* pt, int min_shift)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_set_coarse_shift: null technique");
+    CRV_REQUIRE(min_shift >= -1 && min_shift <= 6, "crv_pt_set_coarse_shift: shift must be -1 (automatic) or 0..6");
+    pt->forced_shift = min_shift;
+    return CRV_OK;
+}
+
+int crv_pt_get_coarse_shift(crv_pt* pt, int* shift)
+{
+    CRV_REQUIRE(pt && shift, "crv_pt_get_coarse_shift: null argument");
+    *shift = pt->qcoarse_shift;
+    return CRV_OK;
+}
+
 int crv_pt_set_scheduler(crv_pt* pt, int scheduler)
 {
     CRV_REQUIRE(pt != nullptr, "crv_pt_set_scheduler: null technique");
@@ -1484,7 +1503,8 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
     const size_t nbricks = (size_t)cv->nbx * cv->nby * cv->nbz;
     if (!cv->brick_max_valid) CRV_TRY(crv_launch_brick_max(pt->ctx, cv, s));
     // (the padded tables and the coarse cell size depend on the three brick counts separately, not on their product)
-    const bool same_dims = pt->qtable_elems == nbricks && pt->q_dims[0] == cv->nbx && pt->q_dims[1] == cv->nby && pt->q_dims[2] == cv->nbz;
+    const bool same_dims = pt->qtable_elems == nbricks && pt->q_dims[0] == cv->nbx && pt->q_dims[1] == cv->nby && pt->q_dims[2] == cv->nbz &&
+                           pt->q_forced_for == pt->forced_shift;
     if (pt->q_for_vol != cv || pt->q_for_generation != vol_generation(cv) || pt->q_for_max_ext != c.max_ext || !same_dims) {
         if (!same_dims) {
             if (pt->qtable) CRV_CUDA(cudaFree(pt->qtable));
@@ -1496,10 +1516,11 @@ static int pt_build_const(crv_pt* pt, unsigned idx, cudaStream_t s, PTConst& c)
             CRV_CUDA(cudaMalloc(&pt->qtable, nbricks * sizeof(float)));
             CRV_CUDA(cudaMalloc(&pt->qtable_wide, ((size_t)(cv->nbx + 2) * (cv->nby + 2) * (cv->nbz + 2) + 1) * sizeof(float)));   // + the +inf entry
             // coarse table: the smallest cell size whose padded table fits the pool scheduler's shared-memory budget
-            coarse_table_shape(cv, pt->qcoarse_shift, pt->qcoarse_bytes);
+            coarse_table_shape(cv, pt->forced_shift, pt->qcoarse_shift, pt->qcoarse_bytes);
             CRV_CUDA(cudaMalloc(&pt->qcoarse, pt->qcoarse_bytes));
             pt->qtable_elems = nbricks;
             pt->q_dims[0] = cv->nbx; pt->q_dims[1] = cv->nby; pt->q_dims[2] = cv->nbz;
+            pt->q_forced_for = pt->forced_shift;
         }
         CRV_CUDA(cudaMemsetAsync(pt->qcoarse, 128, pt->qcoarse_bytes, s));
         CRV_TRY(crv_launch_qcoarse(pt->ctx, cv->brick_absmax_wide, pt->qcoarse, (int)cv->nbx, (int)cv->nby, (int)cv->nbz, pt->qcoarse_shift, c.max_ext, s));

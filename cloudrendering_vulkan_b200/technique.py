@@ -501,6 +501,15 @@ class RenderTechniquePT(RenderTechnique):
         """which persistent-thread scheduler runs the tracker; both produce the same bits"""
         check(lib.crv_pt_set_scheduler(self.handle, self.SCHEDULERS[scheduler] if isinstance(scheduler, str) else int(scheduler)))
 
+    def SetCoarseShift(self, min_shift: int = -1):
+        """at least this cell size (8 << shift voxels) for the tracker's coarse threshold table; -1 = automatic"""
+        check(lib.crv_pt_set_coarse_shift(self.handle, int(min_shift)))
+
+    def GetCoarseShift(self) -> int:
+        v = C.c_int()
+        check(lib.crv_pt_get_coarse_shift(self.handle, C.byref(v)))
+        return v.value
+
     def SetSkipLevel(self, level: int = 1):
         """1 (default): ray sections that provably cannot collide are not tracked (same image bits);
         0: every step of the reference is executed, so the statistics count the reference's work"""

@@ -374,6 +374,8 @@ public:
     void SetScheduler(int scheduler) { Check(crv_pt_set_scheduler(m_pt, scheduler)); }
     // 1 (default): ray sections that provably cannot collide are not tracked; 0: every step of the reference is executed
     void SetSkipLevel(int level) { Check(crv_pt_set_skip_level(m_pt, level)); }
+    // minimum cell size (8 << shift voxels) of the tracker's coarse threshold table; -1 = automatic
+    void SetCoarseShift(int minShift) { Check(crv_pt_set_coarse_shift(m_pt, minShift)); }
     float LastRenderMs(unsigned* launches = nullptr)
     {
         float ms = 0.0f;

@@ -384,6 +384,12 @@ int  crv_pt_set_tuning(crv_pt* pt, int ctas_per_sm, int track_threshold, uint64_
  *   0  every step the reference executes is executed (the stretch in front of the first occupied brick still without
  *      lookups): tracking_steps / collisions and the debug counters equal the reference's.  The debug counters force 0. */
 int  crv_pt_set_skip_level(crv_pt* pt, int level);
+/* The tracker's coarse threshold table holds one byte per cell of (8 << shift)^3 voxels; shift is the smallest that fits
+ * its shared-memory budget (0 up to 304^3 voxels, 1 at 512^3, 2 at 1024^3).  A larger minimum can be requested (identical
+ * results, bit for bit; -1 = automatic): the tests run the production table shapes on small grids with it.
+ * crv_pt_get_coarse_shift: the shift of the tables built by the last render call. */
+int  crv_pt_set_coarse_shift(crv_pt* pt, int min_shift);
+int  crv_pt_get_coarse_shift(crv_pt* pt, int* shift);
 /* which persistent-thread scheduler runs the tracker (identical results, bit for bit):
  *   0 = pool  (default) every warp owns 128 paths in shared memory and runs one kind of work at a time on 32 of them
  *   1 = lanes every lane owns one path plus one in reserve (kept for A/B measurements) */

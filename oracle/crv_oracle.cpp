@@ -929,6 +929,35 @@ void orc_shadow_volume(const float* cloud, const void* cloud60, const void* svpr
     }
 }
 
+// the same for selected columns only (large shadow volumes in the tests): out[(iy * nxs + ix) * N + z] = T(xs[ix], ys[iy], z)
+void orc_shadow_volume_columns(const float* cloud, const void* cloud60, const void* svprops152, const uint32_t* xs, uint32_t nxs,
+                               const uint32_t* ys, uint32_t nys, float* out, int num_threads)
+{
+    const Cloud cp = load_cloud(cloud60);
+    const Shadow sp = load_shadow(svprops152);
+    const uint32_t N = sp.voxelAxisCount;
+#ifdef _OPENMP
+    if (num_threads <= 0) num_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads)
+#endif
+    for (int64_t col = 0; col < static_cast<int64_t>(nxs) * nys; ++col) {
+        const uint32_t x = xs[col % nxs], y = ys[col / nxs];
+        float accumulatedValue = 0.0f;
+        float accumulatedDistance = 0.0f;
+        for (uint32_t z = 0; z < N; ++z) {
+            const vec4 p4 = sp.bounds[0] + ((static_cast<float>(x) * sp.right + static_cast<float>(y) * sp.up) +
+                                            static_cast<float>(z) * sp.lightDirection) * sp.voxelSize;
+            const vec3 p{p4.x, p4.y, p4.z};
+            const bool inside = !(p.x < cp.bounds[0].x || p.y < cp.bounds[0].y || p.z < cp.bounds[0].z ||
+                                  p.x > cp.bounds[1].x || p.y > cp.bounds[1].y || p.z > cp.bounds[1].z);
+            if (inside) accumulatedValue = accumulatedValue + (sampleCloud(cloud, cp, p) * cp.densityScaling) / cp.baseScaling;
+            accumulatedDistance = accumulatedDistance + sp.voxelSize;
+            const float e = ((-accumulatedDistance) * accumulatedValue) / static_cast<float>(z + 1u);
+            out[static_cast<size_t>(col) * N + z] = std::exp(e);
+        }
+    }
+}
+
 void orc_path_trace_frame(const float* cloud, const float* sv, const void* camera68, const void* cloud60,
                           const void* params28, const void* svprops152, const void* push24, float absorption,
                           int accum_sum, float* image, float* sample, uint32_t* steps, uint32_t* collisions,

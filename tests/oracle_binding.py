@@ -56,6 +56,7 @@ lib.orc_sample_shadow_volume.restype = _f
 lib.orc_sample_shadow_volume.argtypes = [_vp, _vp, _fp]
 lib.orc_scatter_ray.argtypes = [_vp, C.POINTER(_u32), _fp, _fp]
 lib.orc_shadow_volume.argtypes = [_vp, _vp, _vp, _vp, C.c_int]
+lib.orc_shadow_volume_columns.argtypes = [_vp, _vp, _vp, _vp, _u32, _vp, _u32, _vp, C.c_int]
 lib.orc_path_trace_frame.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, C.c_int, _vp, _vp, _vp, _vp, C.c_int]
 lib.orc_path_trace_rect.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     _vp, _vp, _vp, _vp, C.c_int]
@@ -220,6 +221,16 @@ def shadow_volume(cloud, cloud_props, sv_props, threads=0):
     v = np.ascontiguousarray(cloud, np.float32)
     out = np.empty(n * n * n, np.float32)
     lib.orc_shadow_volume(_ptr(v), _raw(cloud_props), _raw(sv_props), _ptr(out), threads)
+    return out
+
+
+def shadow_volume_columns(cloud, cloud_props, sv_props, xs, ys, threads=0):
+    """ShadowVolume.comp for the columns (x, y) in xs x ys only: array [len(ys), len(xs), N] (z last)"""
+    n = int(np.frombuffer(bytes(sv_props), np.uint32, 1, 144)[0])
+    v = cloud if (isinstance(cloud, np.ndarray) and cloud.dtype == np.float32 and cloud.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(cloud, np.float32)
+    xa, ya = np.ascontiguousarray(xs, np.uint32), np.ascontiguousarray(ys, np.uint32)
+    out = np.empty((len(ya), len(xa), n), np.float32)
+    lib.orc_shadow_volume_columns(_ptr(v), _raw(cloud_props), _raw(sv_props), _ptr(xa), len(xa), _ptr(ya), len(ya), _ptr(out), threads)
     return out
 
 
