@@ -174,9 +174,9 @@ def _cpu_kind(orc, wl):
 
 
 def _vulkan_probe():
-    """oracle/vulkan_harness.py: is the north star's SPIR-V / lavapipe oracle available here?  (never, in this image)"""
+    """oracle/vulkan_probe.py: is the north star's SPIR-V / lavapipe oracle available here?  (never, in this image)"""
     try:
-        spec = importlib.util.spec_from_file_location("vulkan_harness", os.path.join(ROOT, "oracle", "vulkan_harness.py"))
+        spec = importlib.util.spec_from_file_location("vulkan_probe", os.path.join(ROOT, "oracle", "vulkan_probe.py"))
         m = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(m)
         r = m.probe()

@@ -774,7 +774,7 @@ int crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned /*image_index
     if (!crv_sv_fast_path_ok(c)) mode = CRV_SV_MODE_GENERIC;       // preconditions of the fast kernels not met
     sv->last_mode = mode;
     CRV_CUDA(cudaEventRecord(sv->ev0, s));
-    if (mode == CRV_SV_MODE_FUSED && sv->dist_for_vs != c.voxel_size) {       // inside the timed region when it is needed
+    if ((mode == CRV_SV_MODE_FUSED || mode == CRV_SV_MODE_FUSED_V1) && sv->dist_for_vs != c.voxel_size) {       // inside the timed region when it is needed
         CRV_TRY(crv_launch_sv_dist(sv->ctx, sv->dist_z, c.n, c.voxel_size, s));
         sv->dist_for_vs = c.voxel_size;
     } else if (mode == CRV_SV_MODE_TWO_PASS) {
@@ -792,7 +792,7 @@ int crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned /*image_index
 int crv_sv_set_tuning(crv_sv* sv, int mode)
 {
     CRV_REQUIRE(sv != nullptr, "crv_sv_set_tuning: null technique");
-    CRV_REQUIRE(mode >= CRV_SV_MODE_AUTO && mode <= CRV_SV_MODE_FUSED, "crv_sv_set_tuning: unknown mode");
+    CRV_REQUIRE(mode >= CRV_SV_MODE_AUTO && mode <= CRV_SV_MODE_FUSED_V1, "crv_sv_set_tuning: unknown mode");
     sv->mode = mode;
     return CRV_OK;
 }

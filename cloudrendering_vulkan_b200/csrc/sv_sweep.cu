@@ -250,6 +250,28 @@ __device__ __forceinline__ int range_bisect(const SVConst& c, float a_ax, int ax
     return lo;
 }
 
+// The same first-true index, found from the real-number crossing instead of by bisection: the predicate is monotone in z
+// (every operation of the position chain is weakly monotone), so the candidate ceil(z*) is put right by stepping while the
+// predicate disagrees -- the result is the bisection's, for two or three evaluations instead of log2(N) + 1.
+__device__ __forceinline__ int range_seek(const SVConst& c, float a_ax, int ax, bool leave)
+{
+    const int N = c.n;
+    const bool inc = c.light[ax] >= 0.0f;
+    auto pred = [&](int z) -> bool {
+        const float p = c.b0[ax] + ((a_ax + (float)z * c.light[ax]) * c.voxel_size);
+        return leave ? (inc ? (p > c.cb1[ax]) : (p < c.cb0[ax])) : (inc ? !(p < c.cb0[ax]) : !(p > c.cb1[ax]));
+    };
+    // position reaches `bound` at z* = ((bound - b0) / voxel_size - a_ax) / light
+    const float bound = (leave == inc) ? c.cb1[ax] : c.cb0[ax];
+    const float zs = __fdividef(__fdividef(bound - c.b0[ax], c.voxel_size) - a_ax, c.light[ax]);
+    int k = (zs == zs) ? (int)fminf(fmaxf(ceilf(zs), 0.0f), (float)N) : 0;      // light == 0: NaN / inf, any start will do
+    int guard = 0;
+    while (k > 0 && pred(k - 1) && guard < 8) { --k; ++guard; }
+    while (k < N && !pred(k) && guard < 16) { ++k; ++guard; }
+    if (guard >= 8) return range_bisect(c, a_ax, ax, leave);                    // estimate far off (degenerate direction): bisect
+    return k;
+}
+
 template <int CL, int OL>
 __global__ void __launch_bounds__(512) sv_gather_kernel(const __grid_constant__ SVConst c)
 {
@@ -568,10 +590,220 @@ __global__ void __launch_bounds__(512, 4) sv_fused_kernel(const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Fused build, brick output (the default): the same per-column arithmetic as sv_fused_kernel, organised around what the
+// profile of that kernel showed (profiles/r2c_sv_ncu.txt: 0.93 warp instructions per voxel, issue-active 70 %, DRAM at 41 %):
+// it was bound by instructions spent on voxels that end up holding exactly 1.0f.
+//   * Every 8-slice chunk of the bundle (an 8^3 block of shadow voxels = one output brick) is classified first, one warp
+//     per chunk: the chunk's sample positions lie in a small box of cloud bricks (<= 4 per axis); if every one of them has
+//     a zero wide maximum, every addend of the chunk is +-0 -- what the per-voxel pre-test of sv_fused_kernel would find 512
+//     times -- and the running sums pass through unchanged.  Chunks outside [lo, hi) are empty by the AABB interval.
+//   * Empty chunks while no column has met density are all ones: a warp stores the whole 2 KiB brick with four 128-bit
+//     stores per lane (st.global.cs.v4), 16 bricks per CTA iteration, no per-voxel work at all.  That is ~85 % of the volume.
+//   * Empty chunks after density has been met need exp((-dist*acc)/(z+1)) per voxel with the sums as they stand: no
+//     shared memory, no barrier.
+//   * Only the remaining chunks (inside the cloud's occupied bricks) run the gather / serial sum / exp sequence.
+// Per column the shader's operations happen in the shader's order, so the bits equal the other build modes'.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_ones_brick(float* brick, unsigned lane)
+{
+    float4* p = reinterpret_cast<float4*>(brick) + lane;
+    const float4 one = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    __stcs(p, one);
+    __stcs(p + 32, one);
+    __stcs(p + 64, one);
+    __stcs(p + 96, one);
+}
+
+template <int CL>
+__global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_constant__ SVConst c)
+{
+    constexpr int OL = CRV_LAYOUT_BRICK;
+    constexpr int MAX_CHUNK_WORDS = SV_MAX_FAST_N / 8 / 32;
+    __shared__ int s_lo, s_hi;
+    __shared__ int s_search[6][64];
+    __shared__ int s_zin[64], s_zend[64];
+    __shared__ float s_add[16][64];     // two chunks' addends, then the running sums after each slice
+    __shared__ float s_acc[64];         // running sum of every column after the previous chunk
+    __shared__ uint32_t s_full[MAX_CHUNK_WORDS];      // bit k: chunk k may add density
+    const int N = c.n;
+    const int t = threadIdx.x;
+    const unsigned lane = t & 31u, warp = t >> 5;
+    const int bx = centre_out(blockIdx.x, gridDim.x), by = centre_out(blockIdx.y, gridDim.y);
+    const int nchunks = (N + 7) >> 3;
+
+    // ---- [z_in, z_end) of the bundle's 64 columns: 6 bisections per column spread over 384 threads ----
+    if (t == 0) { s_lo = N; s_hi = 0; }
+    if (t < MAX_CHUNK_WORDS) s_full[t] = 0u;
+    if (t < 384) {
+        const int col = t & 63, search = t >> 6;
+        const int cx = bx * 8 + (col & 7), cy = by * 8 + (col >> 3);
+        const int ax = search >> 1;
+        const float a_ax = (float)cx * c.right[ax] + (float)cy * c.up[ax];
+        s_search[search][col] = range_seek(c, a_ax, ax, (search & 1) != 0);
+    }
+    __syncthreads();
+    if (t < 64) {
+        const int cx = bx * 8 + (t & 7), cy = by * 8 + (t >> 3);
+        int z_in = max(max(s_search[0][t], s_search[2][t]), s_search[4][t]);
+        int z_end = min(min(s_search[1][t], s_search[3][t]), s_search[5][t]);
+        if (z_end < z_in) z_end = z_in;
+        if (cx >= N || cy >= N) z_in = z_end = 0;
+        s_zin[t] = z_in;
+        s_zend[t] = z_end;
+        s_acc[t] = 0.0f;
+        if (z_in < z_end) {
+            atomicMin(&s_lo, z_in);
+            atomicMax(&s_hi, z_end);
+        }
+    }
+    __syncthreads();
+    const int hi = s_hi;
+    const int lo = hi > 0 ? (s_lo & ~7) : N;      // bundle never enters the cloud: every chunk is "before"
+
+    // ---- classification of the chunks in [lo, hi): one warp per chunk, lanes over the cloud bricks its samples can touch ----
+    const bool pre = c.brick_absmax_wide != nullptr;
+    for (int k = (lo >> 3) + (int)warp; k * 8 < hi; k += 16) {
+        bool occupied = !pre;
+        if (pre) {
+            // approximate brick coordinate of the chunk's corner voxel and its extent over the chunk (affine in x, y, z)
+            int b0i[3], cnt[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v0 = c.pre_c[a] + (float)(bx * 8) * c.pre_r[a] + (float)(by * 8) * c.pre_u[a] + (float)(k * 8) * c.pre_l[a];
+                const float er = 7.0f * c.pre_r[a], eu = 7.0f * c.pre_u[a], el = 7.0f * c.pre_l[a];
+                const float vmin = v0 + fminf(er, 0.0f) + fminf(eu, 0.0f) + fminf(el, 0.0f) - 0.01f;
+                const float vmax = v0 + fmaxf(er, 0.0f) + fmaxf(eu, 0.0f) + fmaxf(el, 0.0f) + 0.01f;
+                const int nb = a == 0 ? c.cloud.nbx : a == 1 ? c.cloud.nby : c.cloud.nbz;
+                const int i0 = min(max(__float2int_rd(vmin), 0), nb - 1), i1 = min(max(__float2int_rd(vmax), 0), nb - 1);
+                b0i[a] = i0;
+                cnt[a] = i1 - i0 + 1;
+            }
+            // lanes as a 4 x 4 x 2 block of bricks, twice along z (the extent of a chunk is < 3 bricks per axis: at most 4 touched)
+            const int ix = (int)(lane & 3u), iy = (int)((lane >> 2) & 3u);
+            bool mine = false;
+            if (ix < cnt[0] && iy < cnt[1]) {
+                const unsigned row = (unsigned)(b0i[1] + iy) * c.cloud.nbx + (unsigned)(b0i[0] + ix);
+                const unsigned slab = (unsigned)c.cloud.nby * c.cloud.nbx;
+                for (int iz = (int)(lane >> 4); iz < cnt[2]; iz += 2)
+                    mine = mine || !(__ldg(c.brick_absmax_wide + ((unsigned)(b0i[2] + iz) * slab + row)) == 0.0f);
+            }
+            occupied = __any_sync(0xffffffffu, mine) || cnt[0] > 4 || cnt[1] > 4;
+        }
+        if (occupied && lane == 0) atomicOr(&s_full[k >> 5], 1u << (k & 31));
+    }
+    __syncthreads();
+
+    const int col = t & 63, lz = t >> 6;
+    const int x = bx * 8 + (t & 7), y = by * 8 + ((t >> 3) & 7);
+    const bool inb = x < N && y < N;
+    const bool whole_bundle = bx * 8 + 8 <= N && by * 8 + 8 <= N;
+    const int z_in = s_zin[col], z_end = s_zend[col];
+    const float fx = (float)x, fy = (float)y;
+    const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
+    const float pa[3] = {__fmaf_rn(fy, c.pre_u[0], __fmaf_rn(fx, c.pre_r[0], c.pre_c[0])),
+                         __fmaf_rn(fy, c.pre_u[1], __fmaf_rn(fx, c.pre_r[1], c.pre_c[1])),
+                         __fmaf_rn(fy, c.pre_u[2], __fmaf_rn(fx, c.pre_r[2], c.pre_c[2]))};
+    auto addend = [&](int z) -> float {
+        if (!(z >= z_in && z < z_end)) return 0.0f;       // + 0 outside the interval leaves the sum unchanged (it is never -0)
+        if (pre) {
+            const float fz = (float)z;
+            const int bi = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[0], pa[0]), 8388608.0f)) - 0x4B000000, 0);
+            const int bj = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[1], pa[1]), 8388608.0f)) - 0x4B000000, 0);
+            const int bk = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[2], pa[2]), 8388608.0f)) - 0x4B000000, 0);
+            const unsigned b = ((unsigned)min(bk, c.cloud.nbz - 1) * c.cloud.nby + (unsigned)min(bj, c.cloud.nby - 1)) * c.cloud.nbx +
+                               (unsigned)min(bi, c.cloud.nbx - 1);
+            if (__ldg(c.brick_absmax_wide + b) == 0.0f) return 0.0f;
+        }
+        return div_rn_by(column_sample<CL, true>(c, a, z) * c.density_scaling, c.base_scaling, c.rbase);
+    };
+    auto transmittance = [&](int z, float acc) -> float {
+        float tr = 1.0f;
+        if (__any_sync(0xffffffffu, acc != 0.0f) && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
+        return tr;
+    };
+    // element offset of this thread's voxel in chunk 0, and of the bundle's brick 0; a chunk further is one brick row of the volume
+    const unsigned chunk_step = VolAcc<OL>::off_z(c.out, 8);
+    float* const vox0 = const_cast<float*>(c.out.data) + (VolAcc<OL>::off_x(c.out, x) + VolAcc<OL>::off_y(c.out, y) + VolAcc<OL>::off_z(c.out, lz));
+    float* const brick0 = const_cast<float*>(c.out.data) + (VolAcc<OL>::off_x(c.out, bx * 8) + VolAcc<OL>::off_y(c.out, by * 8));
+
+    bool any_acc = false;             // CTA-uniform: some column of the bundle has a non-zero running sum
+    int k = 0;                        // current chunk
+    while (k < nchunks) {
+        // length of the run of empty chunks starting at k (CTA-uniform)
+        int run = 0;
+        {
+            int j = k;
+            while (j < nchunks) {
+                const uint32_t w = s_full[j >> 5] >> (j & 31);
+                if (w != 0u) { j += __ffs(w) - 1; break; }
+                j = (j | 31) + 1;
+            }
+            run = min(j, nchunks) - k;
+        }
+        if (run > 0) {
+            if (!any_acc && whole_bundle) {
+                // all ones: whole bricks, one warp each
+                const int whole = (k + run) * 8 <= N ? run : run - 1;        // the last chunk may be cut by N
+                for (int j = (int)warp; j < whole; j += 16) store_ones_brick(brick0 + (size_t)(k + j) * chunk_step, lane);
+                if (whole < run) {
+                    const int z = (k + whole) * 8 + lz;
+                    if (z < N) __stcs(vox0 + (size_t)(k + whole) * chunk_step, 1.0f);
+                }
+            } else if (!any_acc) {
+                for (int j = 0; j < run; ++j) {
+                    const int z = (k + j) * 8 + lz;
+                    if (inb && z < N) __stcs(vox0 + (size_t)(k + j) * chunk_step, 1.0f);
+                }
+            } else {
+                // the sums stand: exp + store only
+                const float acc = s_acc[col];
+                const bool any = __any_sync(0xffffffffu, acc != 0.0f);
+                for (int j = 0; j < run; ++j) {
+                    const int z = (k + j) * 8 + lz;
+                    float tr = 1.0f;
+                    if (any && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
+                    if (inb && z < N) __stcs(vox0 + (size_t)(k + j) * chunk_step, tr);
+                }
+            }
+            k += run;
+            continue;
+        }
+        // ---- chunk k may add density: gather, serial sums, exp -- with chunk k + 1 in the same barrier pair ----
+        const int z0 = k * 8;
+        const int za = z0 + lz, zb = z0 + 8 + lz;
+        s_add[lz][col] = addend(za);
+        s_add[8 + lz][col] = addend(zb);
+        __syncthreads();
+        bool nz = false;
+        if (t < 64) {
+            float sum = s_acc[t];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                sum = sum + s_add[u][t];          // accumulatedValue after slice z0 + u, the shader's order (:89)
+                s_add[u][t] = sum;
+            }
+            s_acc[t] = sum;
+            nz = sum != 0.0f;
+        }
+        any_acc = __syncthreads_or(nz) != 0 || any_acc;
+        const float tra = transmittance(za, s_add[lz][col]);
+        const float trb = transmittance(zb, s_add[8 + lz][col]);
+        if (inb && za < N) __stcs(vox0 + (size_t)k * chunk_step, tra);
+        if (inb && zb < N) __stcs(vox0 + (size_t)(k + 1) * chunk_step, trb);
+        k += 2;
+    }
+}
+
 template <int CL, int OL>
 void launch_sv(const SVConst& c, int mode, int* launches, cudaStream_t s)
 {
-    if (mode == SV_MODE_FUSED) {
+    if (mode == SV_MODE_FUSED && OL == CRV_LAYOUT_BRICK) {
+        sv_fused_brick_kernel<CL><<<dim3((c.n + 7) / 8, (c.n + 7) / 8, 1), 512, 0, s>>>(c);
+        *launches = 1;
+        return;
+    }
+    if (mode == SV_MODE_FUSED || mode == SV_MODE_FUSED_V1) {
         sv_fused_kernel<CL, OL><<<dim3((c.n + 7) / 8, (c.n + 7) / 8, 1), 512, 0, s>>>(c);
         *launches = 1;
         return;

@@ -116,7 +116,8 @@ def test_shadow_volume_modes_bit_identical(crv, orc, ctx, layout):
     rng = np.random.default_rng(11)
     cases = [((40, 40, 40), None, (1.0, -1.0, 0.0), 70, 50.0), ((40, 40, 40), None, (0.0, 0.0, 1.0), 33, 400.0),
              ((40, 40, 40), None, (-0.3, 0.8, -0.5), 61, 120.0), ((21, 34, 13), "rand", (0.2, -1.0, 0.1), 45, 120.0),
-             ((8, 8, 8), "rand", (0.0, -1.0, 0.0), 129, 30.0)]
+             ((8, 8, 8), "rand", (0.0, -1.0, 0.0), 129, 30.0), ((96, 96, 96), None, (1.0, -1.0, 0.0), 200, 50.0),
+             ((96, 96, 96), None, (0.5, -0.2, 0.9), 203, 200.0)]
     for shape, kind, light, nsv, ds in cases:
         n = shape[0] * shape[1] * shape[2]
         cloud = rng.random(n, dtype=np.float32) if kind == "rand" else orc.fbm_generate(shape[0], 1234)
@@ -127,13 +128,13 @@ def test_shadow_volume_modes_bit_identical(crv, orc, ctx, layout):
         sv = r.shadowVolumeTechnique
         assert sv.last_build_mode() == ("fused" if layout == "brick" else "two_pass")     # what AUTO resolves to
         out = {}
-        for mode in ["generic", "single_pass", "two_pass", "fused"]:
+        for mode in ["generic", "single_pass", "two_pass", "fused", "fused_v1"]:
             sv.SetTuning(mode)
             r.shadowVolumeImage.upload(np.full(nsv ** 3, -7.0, np.float32))     # poison: every voxel must be rewritten
             r.UpdateShadowVolume()
             assert sv.last_build_mode() == mode
             out[mode] = r.shadowVolumeImage.download()
-        for mode in ["single_pass", "two_pass", "fused"]:
+        for mode in ["single_pass", "two_pass", "fused", "fused_v1"]:
             assert np.array_equal(_bits(out[mode]), _bits(out["generic"])), f"{mode} differs from the literal kernel ({shape}, {light}, N={nsv})"
         _sv_check(out["generic"], orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties))
         r.close()

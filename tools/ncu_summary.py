@@ -188,10 +188,54 @@ def traffic(path):
                                              "launch of the default bench.py step"}))
 
 
+def live(path, source_sha, config):
+    """ncu --metrics <dram bytes, duration, issue counters> --csv over a short bench.py run -> profiles/ncu_live.json: per kernel
+    family the LAST profiled launch (the one inside bench.py's timed region), stamped with the hash of the kernel sources"""
+    import json
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    ii, ni, vi, ui, ki = hdr.index("ID"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Kernel Name")
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tms = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    by_id = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        d = by_id.setdefault(int(r[ii]), {"kernel": r[ki], "dram_bytes": 0.0})
+        v = float(r[vi].replace(",", ""))
+        if r[ni].startswith("dram__bytes"):
+            d["dram_bytes"] += v * mult[r[ui]]
+        elif r[ni].startswith("gpu__time_duration"):
+            d["duration_ms"] = v * tms[r[ui]]
+        elif r[ni] == "sm__inst_executed.avg.per_cycle_elapsed":
+            d["warp_inst_per_cycle_per_sm"] = v          # of 4 issue slots per cycle and SM
+        elif r[ni] == "smsp__thread_inst_executed_per_inst_executed.ratio":
+            d["active_lanes_per_warp_inst"] = v          # of 32
+        elif r[ni] == "smsp__issue_active.avg.pct_of_peak_sustained_active":
+            d["issue_active_pct"] = v
+        elif r[ni] == "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed":
+            d["dram_throughput_pct"] = v
+    kernels = {}
+    for fam in ("pt_wavefront_kernel", "sv_fused_kernel", "fold_kernel", "group_reduce_kernel", "group_scale_kernel", "pt_classify_kernel"):
+        ids = [i for i, d in by_id.items() if fam in d["kernel"]]
+        if ids:
+            d = dict(by_id[ids[-1]])
+            d["launch"] = f"profiled launch {len(ids)} of {len(ids)} of this kernel in the run (ncu id {ids[-1]})"
+            kernels[fam] = d
+    print(json.dumps({"source_sha": source_sha, "config": config, "file": path,
+                      "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__inst_executed.avg.per_cycle_elapsed,"
+                             "smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none "
+                             "python bench.py --quick --steps 1 --warmup 3 --no-e2e --no-cpu-baseline (tools/gpu_profile.sh)",
+                      "kernels": kernels}, indent=1))
+
+
 if __name__ == "__main__":
     mode, path = sys.argv[1], sys.argv[2]
     if mode == "traffic":
         traffic(path)
+    elif mode == "live":
+        live(path, sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "c2")
     elif mode == "launches":
         launches(path)
     elif mode == "full":
