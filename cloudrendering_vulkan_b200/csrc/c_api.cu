@@ -23,6 +23,17 @@
 // ---------------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
 
+// CUDA loads a kernel at its first launch by default, and that load may synchronise the device.  A group member whose stream
+// waits for a peer (crv_group_*) must never be synchronised by the host thread that still has to enqueue that peer's work
+// (crv_headless --gpus N, the tests: several members in one process), so the library asks for eager loading -- all of its
+// kernels are loaded when the context first touches the module -- unless the environment already says otherwise.  The
+// variable is read when CUDA initialises, which is after this library has been loaded in every host of this repo.
+namespace {
+struct EagerModuleLoading {
+    EagerModuleLoading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+} g_eager_module_loading;
+}  // namespace
+
 void crv_set_error(const char* fmt, ...)
 {
     va_list ap;

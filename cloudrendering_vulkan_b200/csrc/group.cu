@@ -8,17 +8,20 @@
 //
 // crv_group: one member per GPU (one per process under torchrun, or all in one process for crv_headless --gpus N).  Every
 // member owns one cudaMalloc'd block -- a flag page followed by `nbuf` RGBA32F images, the render targets -- and maps the
-// blocks of its peers (cudaIpc between processes, peer access inside one).  crv_group_all_reduce_sum_scale launches, on every
-// member, one kernel:
-//   start barrier  every member tells every peer "my image is complete" (system-scope release store into the peer's flag page)
-//                  and waits for the same word from everybody;
-//   band reduce    member r owns rows band r (1/N of the image): it loads that band from all N images (peer loads, issued
-//                  together), adds them in rank order, multiplies by `scale` and stores the result into all N images -- a
-//                  reduce-scatter, the scale epilogue and an all-gather in one pass, 2 x 33 MB over NVLink at 1080p;
-//   end barrier    the last CTA to finish tells every peer "my band is in your image" and waits for theirs: when the kernel
-//                  completes, the member's image holds the final picture and no peer touches it before the next call.
+// blocks of its peers (cudaIpc between processes, peer access inside one).  crv_group_all_reduce_sum_scale enqueues, on every
+// member's stream:
+//   start barrier  every member tells every peer "my image is complete" (a 32-bit word with a system-scope fence into the
+//                  peer's flag page) and waits for the same word from everybody.  Signals and waits are stream memory
+//                  operations (cuStreamWriteValue32 / cuStreamWaitValue32): no SM is held while a member waits, and the members'
+//                  kernels need not be co-resident (several members may even share one device, as the tests do);
+//   band reduce    ONE kernel: member r owns rows band r (1/N of the image): it loads that band from all N images (peer loads,
+//                  issued together), adds them in rank order, multiplies by `scale` and stores the result into all N images --
+//                  a reduce-scatter, the scale epilogue and an all-gather in one pass, 2 x 33 MB over NVLink at 1080p;
+//   end barrier    "my band is in your image" to every peer, wait for theirs: past this point of the stream the member's image
+//                  holds the final picture and no peer touches it before the next call.
 // The result is deterministic (fixed summation order, computed once per pixel) and identical on all members.
-// Spins carry a deadline (default 10 s, crv_group_set_timeout_ms): a member whose peer never arrives sets a sticky error that
+// Where the driver lacks stream memory operations the flags are written / polled by one-warp kernels; their spins carry a
+// deadline (default 10 s, crv_group_set_timeout_ms) and a member whose peer never arrives sets a sticky error that
 // crv_group_status reports, instead of hanging the GPU.
 //
 // The NCCL route north_star names is kept beside it for comparison (crv_group_nccl_*: ncclAllReduce in place through the
@@ -26,8 +29,10 @@
 #include <dlfcn.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "crv_internal.h"
@@ -91,60 +96,39 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch, 
     return true;
 }
 
+// band reduce of member `rank`: its rows band of all N images -> sum in rank order -> * scale -> into all N images.
+// The barriers around it are stream operations (flags_write / flags_wait below), so the kernel never waits for anybody and
+// can use the whole GPU: all peers' loads of several elements are in flight before the first add.
 template <int N>
 __global__ void __launch_bounds__(RED_THREADS) group_reduce_kernel(const __grid_constant__ ReduceArgs a)
 {
-    __shared__ int s_ok;
-    GroupFlags* mine = reinterpret_cast<GroupFlags*>(a.peer[a.rank]);
     const int nr = N > 0 ? N : (int)a.nranks;
-
-    // ---- start barrier: everything this GPU rendered into its image precedes this kernel in stream order ----
-    if (threadIdx.x == 0) s_ok = 1;
-    __syncthreads();
-    if (blockIdx.x == 0 && (int)threadIdx.x < nr) {
-        __threadfence_system();
-        st_release_sys(&reinterpret_cast<GroupFlags*>(a.peer[threadIdx.x])->start[a.rank], a.epoch);
-    }
-    if ((int)threadIdx.x < nr) {
-        if (!wait_flag(&mine->start[threadIdx.x], a.epoch, a.timeout_ns)) {
-            atomicExch(&mine->error, 1u);
-            s_ok = 0;
-        }
-    }
-    __syncthreads();
-
-    // ---- band reduce: rows band `rank`, all peers' loads in flight together, fixed summation order ----
-    if (s_ok) {
-        const uint32_t per = (a.n4 + a.nranks - 1u) / a.nranks;
-        const uint32_t lo = min(a.rank * per, a.n4), hi = min(lo + per, a.n4);
-        for (uint32_t i = lo + blockIdx.x * RED_THREADS + threadIdx.x; i < hi; i += gridDim.x * RED_THREADS) {
-            float4 v[N > 0 ? N : GROUP_MAX];
+    const uint32_t per = (a.n4 + a.nranks - 1u) / a.nranks;
+    const uint32_t lo = min(a.rank * per, a.n4), hi = min(lo + per, a.n4);
+    constexpr int U = N > 0 ? (N <= 2 ? 4 : N <= 4 ? 2 : 1) : 1;      // elements per thread and iteration: U * N loads in flight
+    const uint32_t stride = gridDim.x * RED_THREADS;
+    for (uint32_t i0 = lo + blockIdx.x * RED_THREADS + threadIdx.x; i0 < hi; i0 += stride * U) {
+        float4 v[U][N > 0 ? N : GROUP_MAX];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + u * stride;
 #pragma unroll
             for (int p = 0; p < (N > 0 ? N : GROUP_MAX); ++p)
-                if (p < nr) v[p] = __ldcv(reinterpret_cast<const float4*>(a.peer[p] + a.image_offset) + i);
-            float4 s = v[0];
+                if (p < nr && i < hi) v[u][p] = __ldcv(reinterpret_cast<const float4*>(a.peer[p] + a.image_offset) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + u * stride;
+            if (i >= hi) continue;
+            float4 s = v[u][0];
 #pragma unroll
             for (int p = 1; p < (N > 0 ? N : GROUP_MAX); ++p)
-                if (p < nr) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+                if (p < nr) { s.x += v[u][p].x; s.y += v[u][p].y; s.z += v[u][p].z; s.w += v[u][p].w; }
             s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
 #pragma unroll
             for (int p = 0; p < (N > 0 ? N : GROUP_MAX); ++p)
                 if (p < nr) reinterpret_cast<float4*>(a.peer[p] + a.image_offset)[i] = s;
         }
-    }
-
-    // ---- end barrier: the last CTA of this kernel speaks for all of them ----
-    __threadfence_system();
-    __syncthreads();
-    __shared__ int s_last;
-    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->done, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (!s_last) return;
-    if (threadIdx.x == 0) mine->done = 0u;         // re-armed for the next call (nobody else touches it any more)
-    if ((int)threadIdx.x < nr) {
-        __threadfence_system();
-        st_release_sys(&reinterpret_cast<GroupFlags*>(a.peer[threadIdx.x])->end[a.rank], a.epoch);
-        if (!wait_flag(&mine->end[threadIdx.x], a.epoch, a.timeout_ns)) atomicExch(&mine->error, 2u);
     }
 }
 
@@ -243,6 +227,8 @@ struct crv_group {
     void* nccl_comm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    cudaStream_t aux = nullptr;                    // crv_group_status uses it to release a wait whose peer never arrived
+    bool broken = false;                           // a barrier timed out: the group's flags no longer mean anything
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -253,6 +239,9 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
     } while (0)
 
 extern "C" {
+
+static int flags_write(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s);
+static int flags_wait(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s);
 
 int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, uint64_t staging_bytes,
                      crv_group** out)
@@ -276,6 +265,19 @@ int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t widt
     g->block_bytes = g->staging_offset + g->staging_bytes * nbuf;
     probe_stream_memops();
     g->use_memops = g_stream_write32 != nullptr;
+    {
+        // Load the kernels now.  CUDA loads a kernel at its first launch, and that may synchronise the device: behind a stream
+        // that is waiting for a peer served later by the same host thread (several members in one process) it would never return.
+        cudaFuncAttributes fa;
+        (void)cudaFuncGetAttributes(&fa, group_reduce_kernel<0>);
+        (void)cudaFuncGetAttributes(&fa, group_reduce_kernel<2>);
+        (void)cudaFuncGetAttributes(&fa, group_reduce_kernel<4>);
+        (void)cudaFuncGetAttributes(&fa, group_reduce_kernel<8>);
+        (void)cudaFuncGetAttributes(&fa, group_scale_kernel);
+        (void)cudaFuncGetAttributes(&fa, flag_write_kernel);
+        (void)cudaFuncGetAttributes(&fa, flag_wait_kernel);
+        (void)cudaGetLastError();
+    }
     cudaError_t e = cudaMalloc(&g->block, g->block_bytes);
     if (e != cudaSuccess) {
         crv_set_error("crv_group_create: cudaMalloc of %zu bytes failed: %s", g->block_bytes, cudaGetErrorString(e));
@@ -283,6 +285,7 @@ int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t widt
         return CRV_ERR_OOM;
     }
     e = cudaMemset(g->block, 0, g->block_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->aux, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&g->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&g->ev1);
     if (e != cudaSuccess) {
@@ -308,10 +311,26 @@ int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t widt
     return CRV_OK;
 }
 
+// Release every wait this member may be sitting in: its own flags are set to the epochs it is waiting for.  Only after a
+// timeout (the group is unusable afterwards) or at destruction.
+static void group_break_waits(crv_group* g)
+{
+    GroupFlags h{};
+    for (uint32_t p = 0; p < (uint32_t)GROUP_MAX; ++p) {
+        h.start[p] = h.end[p] = g->epoch;
+        for (uint32_t b = 0; b < (uint32_t)GROUP_MAX_BUF; ++b) h.arrived[b][p] = h.released[b][p] = g->stage_epoch[b];
+    }
+    h.error = 4u;
+    cudaMemcpyAsync(g->block, &h, sizeof(h), cudaMemcpyHostToDevice, g->aux);
+    cudaStreamSynchronize(g->aux);
+    g->broken = true;
+}
+
 int crv_group_destroy(crv_group* g)
 {
     if (!g) return CRV_OK;
     cudaSetDevice(g->ctx->device);
+    if (g->nranks > 1 && g->connected) group_break_waits(g);      // a stream still waiting for a peer must not block the teardown
     cudaDeviceSynchronize();
     if (g->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->nccl_comm);
     for (uint32_t p = 0; p < g->nranks; ++p)
@@ -319,6 +338,7 @@ int crv_group_destroy(crv_group* g)
     for (crv_image* i : g->images) crv_image_destroy(i);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->aux) cudaStreamDestroy(g->aux);
     if (g->block) cudaFree(g->block);
     delete g;
     return CRV_OK;
@@ -396,27 +416,39 @@ int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, v
     CRV_REQUIRE(g != nullptr, "crv_group_all_reduce_sum_scale: null group");
     CRV_REQUIRE(buffer < g->nbuf, "crv_group_all_reduce_sum_scale: buffer index out of range");
     CRV_REQUIRE(g->connected, "crv_group_all_reduce_sum_scale: crv_group_connect has not been called");
+    CRV_REQUIRE(!g->broken, "crv_group_all_reduce_sum_scale: a barrier of this group timed out earlier");
     CRV_CUDA(cudaSetDevice(g->ctx->device));
     cudaStream_t s = as_stream(stream);
     const uint32_t n4 = g->width * g->height;
     CRV_CUDA(cudaEventRecord(g->ev0, s));
     if (g->nranks == 1) {
         group_scale_kernel<<<g->ctx->sm_count * 2, 512, 0, s>>>(reinterpret_cast<float4*>(g->block + FLAG_PAGE + buffer * g->image_bytes), n4, scale);
+        g->ctx->launches++;
     } else {
+        const uint32_t epoch = ++g->epoch;
+        GroupFlags* mine = reinterpret_cast<GroupFlags*>(g->block);
+        uint32_t* addrs[GROUP_MAX];
+        uint32_t n = 0;
+        // start barrier: "my image is complete" to everybody (behind the render in stream order, with a system-scope fence),
+        // then wait for the same word from everybody -- stream operations, no SM is held while waiting
+        for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[p])->start[g->rank];
+        CRV_TRY_G(flags_write(g, addrs, n, epoch, s));
+        n = 0;
+        for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->start[p];
+        CRV_TRY_G(flags_wait(g, addrs, n, epoch, s));
         ReduceArgs a{};
         for (uint32_t p = 0; p < g->nranks; ++p) a.peer[p] = g->peer[p];
         a.image_offset = FLAG_PAGE + buffer * g->image_bytes;
         a.n4 = n4;
         a.rank = g->rank;
         a.nranks = g->nranks;
-        a.epoch = ++g->epoch;
+        a.epoch = epoch;
         a.scale = scale;
         a.timeout_ns = g->timeout_ns;
-        // few, fat CTAs: the band is 1/N of the image and every element costs N loads + N stores over NVLink; all members'
-        // kernels have to be resident at the same time (also when several members share one device, as the tests do)
         const uint32_t band = (n4 + g->nranks - 1) / g->nranks;
-        unsigned blocks = (band + RED_THREADS * 4 - 1) / (RED_THREADS * 4);
-        if (blocks > 32u) blocks = 32u;
+        unsigned blocks = (band + RED_THREADS - 1) / RED_THREADS;
+        const unsigned cap = (unsigned)g->ctx->sm_count * 2u;
+        if (blocks > cap) blocks = cap;
         if (blocks < 1u) blocks = 1u;
         switch (g->nranks) {
             case 2: group_reduce_kernel<2><<<blocks, RED_THREADS, 0, s>>>(a); break;
@@ -424,8 +456,17 @@ int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, v
             case 8: group_reduce_kernel<8><<<blocks, RED_THREADS, 0, s>>>(a); break;
             default: group_reduce_kernel<0><<<blocks, RED_THREADS, 0, s>>>(a); break;
         }
+        g->ctx->launches++;
+        CRV_CUDA(cudaGetLastError());
+        // end barrier: "my band is in your image" to everybody, then wait for theirs: when the stream gets past this point
+        // the member's image holds the final picture and no peer touches it before the next call's start barrier
+        n = 0;
+        for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[p])->end[g->rank];
+        CRV_TRY_G(flags_write(g, addrs, n, epoch, s));
+        n = 0;
+        for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->end[p];
+        CRV_TRY_G(flags_wait(g, addrs, n, epoch, s));
     }
-    g->ctx->launches++;
     CRV_CUDA(cudaGetLastError());
     CRV_CUDA(cudaEventRecord(g->ev1, s));
     g->timed = true;
@@ -436,12 +477,33 @@ int crv_group_status(crv_group* g, void* stream)
 {
     CRV_REQUIRE(g != nullptr, "crv_group_status: null group");
     CRV_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = as_stream(stream);
+    // wait for the stream with the group's deadline: a wait for a peer that never arrives is a stream operation that would
+    // block a plain synchronise for ever
+    const auto t0 = std::chrono::steady_clock::now();
+    bool timed_out = false;
+    while (true) {
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) CRV_CUDA(q);
+        (void)cudaGetLastError();
+        const auto waited = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        if ((unsigned long long)waited > g->timeout_ns) { timed_out = true; break; }
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+    if (timed_out) {
+        group_break_waits(g);
+        CRV_CUDA(cudaStreamSynchronize(s));
+        crv_set_error("crv_group: member %u gave up waiting for a peer (timeout %llu ms); the group is unusable now", g->rank,
+                      g->timeout_ns / 1000000ull);
+        return CRV_ERR_CUDA;
+    }
     uint32_t err = 0;
-    CRV_CUDA(cudaMemcpyAsync(&err, g->block + offsetof(GroupFlags, error), sizeof(err), cudaMemcpyDeviceToHost, as_stream(stream)));
-    CRV_CUDA(cudaStreamSynchronize(as_stream(stream)));
-    if (err != 0) {
+    CRV_CUDA(cudaMemcpyAsync(&err, g->block + offsetof(GroupFlags, error), sizeof(err), cudaMemcpyDeviceToHost, s));
+    CRV_CUDA(cudaStreamSynchronize(s));
+    if (err != 0 || g->broken) {
         crv_set_error("crv_group: member %u gave up waiting for a peer at the %s (timeout %llu ms)", g->rank,
-                      err == 1 ? "start barrier" : err == 2 ? "end barrier" : "staging exchange", g->timeout_ns / 1000000ull);
+                      err == 1 ? "start barrier" : err == 2 ? "end barrier" : err == 3 ? "staging exchange" : "barrier", g->timeout_ns / 1000000ull);
         return CRV_ERR_CUDA;
     }
     return CRV_OK;
@@ -505,6 +567,7 @@ int crv_group_staging_all_gather(crv_group* g, uint32_t buffer, const void* host
     CRV_REQUIRE(g && host_src, "crv_group_staging_all_gather: null argument");
     CRV_REQUIRE(buffer < g->nbuf && bytes > 0 && bytes <= g->staging_bytes, "crv_group_staging_all_gather: buffer index or size out of range");
     CRV_REQUIRE(g->connected, "crv_group_staging_all_gather: crv_group_connect has not been called");
+    CRV_REQUIRE(!g->broken, "crv_group_staging_all_gather: a barrier of this group timed out earlier");
     CRV_CUDA(cudaSetDevice(g->ctx->device));
     cudaStream_t s = as_stream(stream);
     const size_t off0 = g->staging_offset + buffer * g->staging_bytes;

@@ -277,12 +277,14 @@ int  crv_image_scale(crv_image* img, float scale, void* stream);
  *     crv_group_image(g, 0, &img); crv_pt_set_frame_references(pt, &img, 1);
  *     per picture, on every member:  crv_image_clear(img) ; crv_pt_render_batch(pt, my_seeds, n, 0, CRV_ACCUM_SUM, ...)
  *                                    crv_group_all_reduce_sum_scale(g, 0, 1.0f / spp_total, stream)
- * crv_group_all_reduce_sum_scale is ONE kernel per member that synchronises with its peers through flags in mapped
- * memory, sums its band of rows from all members' images in rank order, scales it and writes it into all members'
- * images: afterwards every member's image holds the same, final picture (bit-identical on all members, and independent
- * of timing).  All members must call it the same number of times with the same buffer index; each call is asynchronous
- * on the caller's stream.  A member whose peers never arrive gives up after crv_group_set_timeout_ms (default 10 s) and
- * crv_group_status reports it.
+ * crv_group_all_reduce_sum_scale enqueues, per member: a start barrier with its peers, ONE kernel that sums its band of
+ * rows from all members' images in rank order, scales it and writes it into all members' images, and an end barrier:
+ * afterwards every member's image holds the same, final picture (bit-identical on all members, and independent of timing).
+ * The barriers are stream memory operations on flags in mapped memory (no SM is held while waiting).  All members must call
+ * it the same number of times with the same buffer index; each call is asynchronous on the caller's stream.
+ * crv_group_status waits for the stream with the group's deadline (crv_group_set_timeout_ms, default 10 s): if a peer never
+ * arrives it releases the wait, returns an error and the group is unusable from then on -- use it instead of a plain
+ * synchronise wherever a member might be missing.
  * crv_group_nccl_*: the same operation as ncclAllReduce + a scale kernel through the libnccl.so.2 already loaded in the
  * process (rank 0 creates the id, everybody passes it to crv_group_nccl_init). */
 int  crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, uint64_t staging_bytes,
@@ -293,7 +295,7 @@ int  crv_group_connect(crv_group* g, const crv_group_handle* handles, uint32_t c
 int  crv_group_image(crv_group* g, uint32_t buffer, crv_image** out);              /* owned by the group */
 int  crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream);
 int  crv_group_set_timeout_ms(crv_group* g, uint32_t ms);
-int  crv_group_status(crv_group* g, void* stream);                                  /* CRV_OK, or the barrier that timed out */
+int  crv_group_status(crv_group* g, void* stream);                                  /* waits for `stream` (with the deadline); CRV_OK or the time-out */
 int  crv_group_last_reduce_ms(crv_group* g, float* ms);                             /* device time of the last reduce call of this member */
 /* Replicated input from the host (the density grid is the same on every member): with staging_bytes > 0 every member also
  * owns `nbuf` staging buffers.  crv_group_staging_all_gather: member r copies slice r (1/N) of the host array into its
