@@ -587,11 +587,15 @@ int crv_group_staging_all_gather(crv_group* g, uint32_t buffer, const void* host
     CRV_TRY_G(flags_wait(g, addrs, n, epoch - 1u, s));
     if (len > 0) {
         CRV_CUDA(cudaMemcpyAsync(g->block + off0 + lo, static_cast<const unsigned char*>(host_src) + lo, len, cudaMemcpyHostToDevice, s));
-        for (uint32_t p = 0; p < g->nranks; ++p)       // copy engines, NVLink: my slice into every peer's buffer
-            if (p != g->rank) CRV_CUDA(cudaMemcpyAsync(g->peer[p] + off0 + lo, g->block + off0 + lo, len, cudaMemcpyDefault, s));
+        // copy engines, NVLink: my slice into every peer's buffer.  Member r starts with r + 1, r + 2, ...: at any moment the
+        // members write to different destinations (all starting with member 0 made its ingress the bottleneck: 80 GB/s per sender)
+        for (uint32_t k = 1; k < g->nranks; ++k) {
+            const uint32_t p = (g->rank + k) % g->nranks;
+            CRV_CUDA(cudaMemcpyAsync(g->peer[p] + off0 + lo, g->block + off0 + lo, len, cudaMemcpyDefault, s));
+        }
     }
     n = 0;
-    for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[p])->arrived[buffer][g->rank];
+    for (uint32_t k = 1; k < g->nranks; ++k) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[(g->rank + k) % g->nranks])->arrived[buffer][g->rank];
     CRV_TRY_G(flags_write(g, addrs, n, epoch, s));
     n = 0;
     for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->arrived[buffer][p];
