@@ -10,15 +10,15 @@
 // member owns one cudaMalloc'd block -- a flag page followed by `nbuf` RGBA32F images, the render targets -- and maps the
 // blocks of its peers (cudaIpc between processes, peer access inside one).  crv_group_all_reduce_sum_scale enqueues, on every
 // member's stream:
-//   start barrier  every member tells every peer "my image is complete" (a 32-bit word with a system-scope fence into the
-//                  peer's flag page) and waits for the same word from everybody.  Signals and waits are stream memory
-//                  operations (cuStreamWriteValue32 / cuStreamWaitValue32): no SM is held while a member waits, and the members'
-//                  kernels need not be co-resident (several members may even share one device, as the tests do);
+//   start barrier  every member tells every peer "my image is complete" (a one-warp kernel: a 32-bit word with a system-scope
+//                  release into each peer's flag page) and waits for the same word from everybody.  The waits are stream memory
+//                  operations (cuStreamWaitValue32): no SM is held while a member waits, and the members' kernels need not be
+//                  co-resident (several members may even share one device, as the tests do);
 //   band reduce    ONE kernel: member r owns rows band r (1/N of the image): it loads that band from all N images (peer loads,
 //                  issued together), adds them in rank order, multiplies by `scale` and stores the result into all N images --
 //                  a reduce-scatter, the scale epilogue and an all-gather in one pass, 2 x 33 MB over NVLink at 1080p;
-//   end barrier    "my band is in your image" to every peer, wait for theirs: past this point of the stream the member's image
-//                  holds the final picture and no peer touches it before the next call.
+//   end barrier    the kernel's last CTA tells every peer "my band is in your image"; the stream then waits for the peers' words:
+//                  past this point the member's image holds the final picture and no peer touches it before the next call.
 // The result is deterministic (fixed summation order, computed once per pixel) and identical on all members.
 // Where the driver lacks stream memory operations the flags are written / polled by one-warp kernels; their spins carry a
 // deadline (default 10 s, crv_group_set_timeout_ms) and a member whose peer never arrives sets a sticky error that
@@ -130,6 +130,19 @@ __global__ void __launch_bounds__(RED_THREADS) group_reduce_kernel(const __grid_
                 if (p < nr) reinterpret_cast<float4*>(a.peer[p] + a.image_offset)[i] = s;
         }
     }
+    // end barrier, signalling half: the last CTA to finish tells every peer "my band is in your image"
+    __shared__ int s_last;
+    GroupFlags* mine = reinterpret_cast<GroupFlags*>(a.peer[a.rank]);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->done, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) mine->done = 0u;         // re-armed for the next call
+    if ((int)threadIdx.x < nr && threadIdx.x != a.rank) {
+        __threadfence_system();
+        st_release_sys(&reinterpret_cast<GroupFlags*>(a.peer[threadIdx.x])->end[a.rank], a.epoch);
+    }
 }
 
 // fallbacks for cuStreamWriteValue32 / cuStreamWaitValue32 where the driver does not offer them
@@ -240,7 +253,7 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 extern "C" {
 
-static int flags_write(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s);
+static int flags_write(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s, bool prefer_kernel = false);
 static int flags_wait(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s);
 
 int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t width, uint32_t height, uint32_t nbuf, uint64_t staging_bytes,
@@ -432,7 +445,7 @@ int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, v
         // start barrier: "my image is complete" to everybody (behind the render in stream order, with a system-scope fence),
         // then wait for the same word from everybody -- stream operations, no SM is held while waiting
         for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[p])->start[g->rank];
-        CRV_TRY_G(flags_write(g, addrs, n, epoch, s));
+        CRV_TRY_G(flags_write(g, addrs, n, epoch, s, true));
         n = 0;
         for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->start[p];
         CRV_TRY_G(flags_wait(g, addrs, n, epoch, s));
@@ -458,11 +471,8 @@ int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, v
         }
         g->ctx->launches++;
         CRV_CUDA(cudaGetLastError());
-        // end barrier: "my band is in your image" to everybody, then wait for theirs: when the stream gets past this point
-        // the member's image holds the final picture and no peer touches it before the next call's start barrier
-        n = 0;
-        for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &reinterpret_cast<GroupFlags*>(g->peer[p])->end[g->rank];
-        CRV_TRY_G(flags_write(g, addrs, n, epoch, s));
+        // end barrier: the kernel's last CTA has told everybody "my band is in your image"; wait for theirs: when the stream gets
+        // past this point the member's image holds the final picture and no peer touches it before the next call's start barrier
         n = 0;
         for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->end[p];
         CRV_TRY_G(flags_wait(g, addrs, n, epoch, s));
@@ -520,9 +530,11 @@ int crv_group_last_reduce_ms(crv_group* g, float* ms)
 }
 
 // ---- staging all-gather: a replicated input (the density grid) crosses PCIe once per job, 1/N on every member's link ----------
-static int flags_write(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s)
+static int flags_write(crv_group* g, uint32_t* const* addrs, uint32_t n, uint32_t value, cudaStream_t s, bool prefer_kernel)
 {
-    if (g->use_memops) {
+    // one-warp kernel: all peers' words in parallel, one launch (a few microseconds); stream memory operations: one driver call
+    // and a few microseconds per word, but no SM -- the staging exchange, which must run beside a kernel that holds every SM
+    if (g->use_memops && !prefer_kernel) {
         bool ok = true;
         for (uint32_t i = 0; i < n && ok; ++i) ok = g_stream_write32(s, (unsigned long long)(uintptr_t)addrs[i], value, 0u) == 0;
         if (ok) return CRV_OK;
