@@ -132,6 +132,7 @@ SIGNATURES = {
     "crv_volume_dims": (C.c_int, [_vp, _P(_u32), _P(_u32), _P(_u32), _P(C.c_int)]),
     "crv_volume_majorant": (C.c_int, [_vp, _P(C.c_float), _vp]),
     "crv_volume_device_ptr": (C.c_int, [_vp, _P(_vp)]),
+    "crv_volume_mark_dirty": (C.c_int, [_vp]),
     "crv_image_create": (C.c_int, [_vp, _u32, _u32, _P(_vp)]),
     "crv_image_wrap": (C.c_int, [_vp, _vp, _u32, _u32, _P(_vp)]),
     "crv_image_destroy": (C.c_int, [_vp]),

@@ -6,6 +6,7 @@
 // All host arithmetic that feeds the kernels is fp32 in the shader's evaluation order (compiled with
 // -ffp-contract=off), because the kernels take these values as if the shader had computed them.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cmath>
 #include <cstdarg>
@@ -162,24 +163,24 @@ struct crv_pt {
     uint32_t nhit_known = 0;
 };
 
-// volumes carry an upload generation so cached q-tables notice re-uploads
-static uint64_t g_generation = 1;
-struct VolGen { const crv_volume* v; uint64_t gen; };
-static std::vector<VolGen> g_gens;
-static uint64_t vol_generation(const crv_volume* v)
-{
-    for (auto& g : g_gens) if (g.v == v) return g.gen;
-    return 0;
-}
-static void vol_touch(const crv_volume* v)
-{
-    for (auto& g : g_gens) if (g.v == v) { g.gen = ++g_generation; return; }
-    g_gens.push_back({v, ++g_generation});
-}
-static void vol_forget(const crv_volume* v)
-{
-    for (size_t i = 0; i < g_gens.size(); ++i) if (g_gens[i].v == v) { g_gens.erase(g_gens.begin() + i); return; }
-}
+// volumes carry a contents generation so cached q-tables / classifications notice re-uploads.  The numbers come from one
+// process-wide atomic counter (a technique may be re-bound to another volume object that happens to live at the same address),
+// the generation itself lives in the volume: no shared registry, contexts on different host threads do not meet here.
+static std::atomic<uint64_t> g_generation{1};
+static uint64_t vol_generation(const crv_volume* v) { return v->generation; }
+static void vol_touch(crv_volume* v) { v->generation = g_generation.fetch_add(1, std::memory_order_relaxed) + 1; }
+
+// stream-ordered scratch that is released on every path out of the scope, error returns included
+struct AsyncScratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    explicit AsyncScratch(cudaStream_t stream) : s(stream) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, s); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    ~AsyncScratch() { if (p) cudaFreeAsync(p, s); }
+    AsyncScratch(const AsyncScratch&) = delete;
+    AsyncScratch& operator=(const AsyncScratch&) = delete;
+};
 
 extern "C" {
 
@@ -339,7 +340,6 @@ int crv_volume_destroy(crv_volume* v)
     if (v->brick_max) cudaFree(v->brick_max);
     if (v->brick_absmax) cudaFree(v->brick_absmax);
     if (v->brick_absmax_wide) cudaFree(v->brick_absmax_wide);
-    vol_forget(v);
     delete v;
     return CRV_OK;
 }
@@ -356,11 +356,9 @@ int crv_volume_upload(crv_volume* v, const float* data, int is_device, void* str
     bool tables_done = false;
     if (v->layout == CRV_LAYOUT_LINEAR) {
         CRV_CUDA(cudaMemcpyAsync(v->data, data, n * sizeof(float), kind, s));
-        float* scratch = nullptr;
-        CRV_CUDA(cudaMallocAsync(&scratch, scratch_bytes, s));
-        const int rc = crv_launch_retile_tables(v->ctx, v->data, v, false, scratch, s);
-        CRV_CUDA(cudaFreeAsync(scratch, s));
-        if (rc != CRV_OK) return rc;
+        AsyncScratch scratch(s);
+        CRV_CUDA(scratch.alloc(scratch_bytes));
+        CRV_TRY(crv_launch_retile_tables(v->ctx, v->data, v, false, scratch.as<float>(), s));
         tables_done = true;
     } else if (v->layout == CRV_LAYOUT_TEX3D) {
         cudaMemcpy3DParms p{};
@@ -370,20 +368,15 @@ int crv_volume_upload(crv_volume* v, const float* data, int is_device, void* str
         p.kind = kind;
         CRV_CUDA(cudaMemcpy3DAsync(&p, s));
     } else {
-        float* scratch = nullptr;
-        CRV_CUDA(cudaMallocAsync(&scratch, scratch_bytes, s));
-        int rc;
+        AsyncScratch scratch(s), tmp(s);
+        CRV_CUDA(scratch.alloc(scratch_bytes));
         if (is_device) {
-            rc = crv_launch_retile_tables(v->ctx, data, v, true, scratch, s);
+            CRV_TRY(crv_launch_retile_tables(v->ctx, data, v, true, scratch.as<float>(), s));
         } else {
-            float* tmp = nullptr;
-            CRV_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
-            CRV_CUDA(cudaMemcpyAsync(tmp, data, n * sizeof(float), cudaMemcpyHostToDevice, s));
-            rc = crv_launch_retile_tables(v->ctx, tmp, v, true, scratch, s);
-            CRV_CUDA(cudaFreeAsync(tmp, s));
+            CRV_CUDA(tmp.alloc(n * sizeof(float)));
+            CRV_CUDA(cudaMemcpyAsync(tmp.p, data, n * sizeof(float), cudaMemcpyHostToDevice, s));
+            CRV_TRY(crv_launch_retile_tables(v->ctx, tmp.as<float>(), v, true, scratch.as<float>(), s));
         }
-        CRV_CUDA(cudaFreeAsync(scratch, s));
-        if (rc != CRV_OK) return rc;
         tables_done = true;
     }
     v->brick_max_valid = tables_done;
@@ -401,12 +394,10 @@ int crv_volume_download(crv_volume* v, float* host_out, void* stream)
     if (v->layout == CRV_LAYOUT_LINEAR) {
         CRV_CUDA(cudaMemcpyAsync(host_out, v->data, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     } else {
-        float* tmp = nullptr;
-        CRV_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
-        const int rc = crv_launch_untile(v->ctx, v, tmp, s);
-        if (rc == CRV_OK) CRV_CUDA(cudaMemcpyAsync(host_out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CRV_CUDA(cudaFreeAsync(tmp, s));
-        if (rc != CRV_OK) return rc;
+        AsyncScratch tmp(s);
+        CRV_CUDA(tmp.alloc(n * sizeof(float)));
+        CRV_TRY(crv_launch_untile(v->ctx, v, tmp.as<float>(), s));
+        CRV_CUDA(cudaMemcpyAsync(host_out, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     CRV_CUDA(cudaStreamSynchronize(s));
     return CRV_OK;
@@ -438,6 +429,15 @@ int crv_volume_device_ptr(crv_volume* v, float** out)
     return CRV_OK;
 }
 
+int crv_volume_mark_dirty(crv_volume* v)
+{
+    CRV_REQUIRE(v != nullptr, "crv_volume_mark_dirty: null volume");
+    v->brick_max_valid = false;
+    v->majorant_valid = false;
+    vol_touch(v);
+    return CRV_OK;
+}
+
 int crv_fbm_generate(crv_volume* v, uint32_t seed, void* stream)
 {
     CRV_REQUIRE(v != nullptr, "crv_fbm_generate: null volume");
@@ -451,13 +451,11 @@ int crv_fbm_generate(crv_volume* v, uint32_t seed, void* stream)
         vol_touch(v);
         return CRV_OK;
     }
-    float* tmp = nullptr;
     const size_t n = (size_t)v->nx * v->ny * v->nz;
-    CRV_CUDA(cudaMallocAsync(&tmp, n * sizeof(float), s));
-    int rc = crv_launch_fbm(v->ctx, tmp, v->nx, seed, s);
-    if (rc == CRV_OK) rc = crv_volume_upload(v, tmp, 1, stream);
-    CRV_CUDA(cudaFreeAsync(tmp, s));
-    return rc;
+    AsyncScratch tmp(s);
+    CRV_CUDA(tmp.alloc(n * sizeof(float)));
+    CRV_TRY(crv_launch_fbm(v->ctx, tmp.as<float>(), v->nx, seed, s));
+    return crv_volume_upload(v, tmp.as<float>(), 1, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -840,14 +838,21 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
     pt->ctor_cam = cam;
     pt->pc = pc;
     pt->sets.resize(1);
-    CRV_CUDA(cudaMalloc(&pt->job_counter, sizeof(unsigned int)));
-    CRV_CUDA(cudaMalloc(&pt->nhit, 2 * sizeof(uint32_t)));      // [0] hits, [1] misses
-    CRV_CUDA(cudaMallocHost(&pt->counts_host, 2 * sizeof(uint32_t)));
-    CRV_CUDA(cudaEventCreateWithFlags(&pt->counts_ev, cudaEventDisableTiming));
-    CRV_CUDA(cudaMalloc(&pt->occ_ext, 6 * sizeof(int)));
-    CRV_CUDA(cudaMalloc(&pt->occ_aabb, 6 * sizeof(float)));
-    CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
-    CRV_CUDA(cudaMemset(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT));
+    const int rc = [&]() -> int {
+        CRV_CUDA(cudaMalloc(&pt->job_counter, sizeof(unsigned int)));
+        CRV_CUDA(cudaMalloc(&pt->nhit, 2 * sizeof(uint32_t)));      // [0] hits, [1] misses
+        CRV_CUDA(cudaMallocHost(&pt->counts_host, 2 * sizeof(uint32_t)));
+        CRV_CUDA(cudaEventCreateWithFlags(&pt->counts_ev, cudaEventDisableTiming));
+        CRV_CUDA(cudaMalloc(&pt->occ_ext, 6 * sizeof(int)));
+        CRV_CUDA(cudaMalloc(&pt->occ_aabb, 6 * sizeof(float)));
+        CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
+        CRV_CUDA(cudaMemset(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT));
+        return CRV_OK;
+    }();
+    if (rc != CRV_OK) {
+        crv_pt_destroy(pt);           // releases whatever was allocated before the failure
+        return rc;
+    }
     *out = pt;
     return CRV_OK;
 }

@@ -236,6 +236,7 @@ struct crv_volume {
     bool brick_max_valid = false;
     float majorant = 0.0f;
     bool majorant_valid = false;
+    uint64_t generation = 0;               // contents version: every upload / build / mark_dirty draws a new process-wide number
     VolView view() const;
 };
 

@@ -136,20 +136,23 @@ int crv_grid_save_zfastest(const char* path, const uint32_t counts[3], const dou
 
 
 // ---- PNG: 8-bit RGBA, filter 0 on every row, zlib stream of stored deflate blocks (no compression library needed) ----
-static uint32_t png_crc(uint32_t crc, const unsigned char* p, size_t n)
-{
-    static uint32_t table[256];
-    static bool ready = false;
-    if (!ready) {
+struct CrcTable {
+    uint32_t v[256];
+    constexpr CrcTable() : v{}
+    {
         for (uint32_t i = 0; i < 256; ++i) {
             uint32_t c = i;
             for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            table[i] = c;
+            v[i] = c;
         }
-        ready = true;
     }
+};
+static constexpr CrcTable kCrcTable{};          // built by the compiler: nothing to initialise (or race on) at run time
+
+static uint32_t png_crc(uint32_t crc, const unsigned char* p, size_t n)
+{
     crc = ~crc;
-    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    for (size_t i = 0; i < n; ++i) crc = kCrcTable.v[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
     return ~crc;
 }
 

@@ -125,6 +125,10 @@ class Volume:
         check(lib.crv_volume_device_ptr(self.handle, C.byref(p)))
         return p.value or 0
 
+    def mark_dirty(self):
+        """after writing through device_ptr: majorant, brick maxima and everything cached from them are stale"""
+        check(lib.crv_volume_mark_dirty(self.handle))
+
     def close(self):
         if self.handle:
             lib.crv_volume_destroy(self.handle)

@@ -235,8 +235,11 @@ int  crv_volume_download(crv_volume* vol, float* host_out, void* stream);
 int  crv_volume_dims(const crv_volume* vol, uint32_t* nx, uint32_t* ny, uint32_t* nz, int* layout);
 /* Grid3D<float>::GetMajorant (Grid3D.h:181-192) as a device reduction */
 int  crv_volume_majorant(crv_volume* vol, float* out, void* stream);
-/* raw device pointer of a LINEAR volume (NULL otherwise); for zero-copy interop */
+/* raw device pointer of a LINEAR volume (NULL otherwise); for zero-copy interop.  After WRITING through it call
+ * crv_volume_mark_dirty: the majorant, the brick maxima and everything the techniques cache from them (skip tables, occupied
+ * spans, pixel classification) belong to the old contents, and the skips are proofs -- stale tables give wrong pictures. */
 int  crv_volume_device_ptr(crv_volume* vol, float** out);
+int  crv_volume_mark_dirty(crv_volume* vol);
 
 /* ---- result image: VulkanImage(R32G32B32A32_SFLOAT, 2D, STORAGE) (main.cpp:405-414) ------ */
 int  crv_image_create(crv_ctx* ctx, uint32_t width, uint32_t height, crv_image** out);
