@@ -449,8 +449,12 @@ def run_ours(args, wl):
         o_ms = timed(make_step(o_seeds), max(3, args.steps), 2)
         scaling_other = {"scaling": other, "spp_total": o_total, "ms_per_step": o_ms, "value": W * H * o_total / (o_ms * 1e-3) / 1e6,
                          "unit": "Mpath-samples/s"}
-    reduce_cmp = {"peer_kernel_ms": reduce_ms}
+    reduce_cmp = {"peer_kernel_ms": reduce_ms,
+                  "note": "peer_kernel: crv_group_all_reduce_lists_sum_scale, start / end barriers included (only the tracked pixels cross "
+                          "NVLink); peer_dense: whole images through the same kernel; nccl: ncclAllReduce of the whole image + scale kernel"}
     if world > 1 and not args.quick:
+        timed(make_step(all_seeds, "peer_dense"), 3, 2)
+        reduce_cmp["peer_dense_kernel_ms"] = split.group.last_reduce_ms()
         try:
             init_group_nccl(split.group)
             timed(make_step(all_seeds, "nccl"), 3, 2)
@@ -612,7 +616,10 @@ def run_ours(args, wl):
             p.r.UpdateCloudData(p.s)                                                           # descriptor updates + shadow-volume rebuild
             p.img.clear(p.s)
             p.r.pathTracingTechnique.RenderBatch(my, 0, crv.ACCUM_SUM, p.s, 0)
-            split.group.all_reduce_sum_scale(1.0 / spp_total, p.s, p.k)
+            if len(my) * world == spp_total:          # even split: only the tracked pixels cross between the GPUs
+                split.group.all_reduce_lists_sum_scale(1.0 / spp_total, 1.0 / len(my), p.r.pathTracingTechnique.PixelLists(), p.s, p.k)
+            else:
+                split.group.all_reduce_sum_scale(1.0 / spp_total, p.s, p.k)
 
         def e2e_finish(p):
             p.img.download(p.s, out=p.hi)                                                      # D2H: the picture (synchronises p.s)

@@ -1807,6 +1807,18 @@ int crv_pt_get_stats(crv_pt* pt, crv_pt_stats* out, void* stream)
     return CRV_OK;
 }
 
+int crv_pt_pixel_lists(crv_pt* pt, crv_pixel_lists* out)
+{
+    CRV_REQUIRE(pt && out, "crv_pt_pixel_lists: null argument");
+    CRV_REQUIRE(pt->geom_valid && pt->hitlist && pt->misslist, "crv_pt_pixel_lists: nothing rendered yet");
+    out->tracked_xy = pt->hitlist;
+    out->other_pixels = pt->misslist;
+    out->counts = pt->nhit;
+    out->width = (uint32_t)(pt->ctor_cam->halfWidth * 2);
+    out->reserved = 0;
+    return CRV_OK;
+}
+
 int crv_pt_last_render_ms(crv_pt* pt, float* tracker_ms, unsigned* tracker_launches)
 {
     CRV_REQUIRE(pt && tracker_ms, "crv_pt_last_render_ms: null argument");

@@ -65,6 +65,12 @@ struct ReduceArgs {
     uint32_t epoch;
     float scale;
     unsigned long long timeout_ns;
+    // pixel-list variant (crv_group_all_reduce_lists_sum_scale): only the listed pixels travel
+    const uint32_t* tracked_xy;                    // x | y << 16, counts[0] entries (this member's own copy of the list)
+    const uint32_t* other_pixels;                  // pixel indices, counts[1] entries
+    const uint32_t* counts;
+    uint32_t width;
+    float others_scale;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
@@ -142,6 +148,68 @@ __global__ void __launch_bounds__(RED_THREADS) group_reduce_kernel(const __grid_
     if ((int)threadIdx.x < nr && threadIdx.x != a.rank) {
         __threadfence_system();
         st_release_sys(&reinterpret_cast<GroupFlags*>(a.peer[threadIdx.x])->end[a.rank], a.epoch);
+    }
+}
+
+// The same with pixel lists: every member holds the same SET of listed pixels (its tracker's hit list; the order of the list
+// may differ from member to member, so ownership goes by pixel index: member r combines the listed pixels with index % N == r)
+// and only those cross NVLink; every other pixel is finished locally (value * others_scale).
+template <int N>
+__global__ void __launch_bounds__(RED_THREADS) group_reduce_lists_kernel(const __grid_constant__ ReduceArgs a)
+{
+    const int nr = N > 0 ? N : (int)a.nranks;
+    const uint32_t ntracked = a.counts[0], nothers = a.counts[1];
+    const uint32_t stride = gridDim.x * RED_THREADS, t0 = blockIdx.x * RED_THREADS + threadIdx.x;
+    for (uint32_t j = t0; j < ntracked; j += stride) {
+        const uint32_t xy = __ldg(a.tracked_xy + j);
+        const uint32_t i = (xy >> 16) * a.width + (xy & 0xffffu);
+        if (i % a.nranks != a.rank) continue;
+        float4 v[N > 0 ? N : GROUP_MAX];
+#pragma unroll
+        for (int p = 0; p < (N > 0 ? N : GROUP_MAX); ++p)
+            if (p < nr) v[p] = __ldcv(reinterpret_cast<const float4*>(a.peer[p] + a.image_offset) + i);
+        float4 s = v[0];
+#pragma unroll
+        for (int p = 1; p < (N > 0 ? N : GROUP_MAX); ++p)
+            if (p < nr) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+        s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
+#pragma unroll
+        for (int p = 0; p < (N > 0 ? N : GROUP_MAX); ++p)
+            if (p < nr) reinterpret_cast<float4*>(a.peer[p] + a.image_offset)[i] = s;
+    }
+    float4* img = reinterpret_cast<float4*>(a.peer[a.rank] + a.image_offset);
+    for (uint32_t j = t0; j < nothers; j += stride) {
+        const uint32_t i = __ldg(a.other_pixels + j);
+        float4 v = img[i];
+        v.x *= a.others_scale; v.y *= a.others_scale; v.z *= a.others_scale; v.w *= a.others_scale;
+        img[i] = v;
+    }
+    __shared__ int s_last;
+    GroupFlags* mine = reinterpret_cast<GroupFlags*>(a.peer[a.rank]);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->done, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) mine->done = 0u;
+    if ((int)threadIdx.x < nr && threadIdx.x != a.rank) {
+        __threadfence_system();
+        st_release_sys(&reinterpret_cast<GroupFlags*>(a.peer[threadIdx.x])->end[a.rank], a.epoch);
+    }
+}
+
+__global__ void group_scale_lists_kernel(float4* __restrict__ img, const uint32_t* __restrict__ tracked_xy, const uint32_t* __restrict__ other_pixels,
+                                         const uint32_t* __restrict__ counts, uint32_t width, float scale, float others_scale)
+{
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t j = t0; j < counts[0]; j += stride) {
+        const uint32_t xy = tracked_xy[j];
+        float4& v = img[(xy >> 16) * width + (xy & 0xffffu)];
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    }
+    for (uint32_t j = t0; j < counts[1]; j += stride) {
+        float4& v = img[other_pixels[j]];
+        v.x *= others_scale; v.y *= others_scale; v.z *= others_scale; v.w *= others_scale;
     }
 }
 
@@ -287,6 +355,11 @@ int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t widt
         (void)cudaFuncGetAttributes(&fa, group_reduce_kernel<4>);
         (void)cudaFuncGetAttributes(&fa, group_reduce_kernel<8>);
         (void)cudaFuncGetAttributes(&fa, group_scale_kernel);
+        (void)cudaFuncGetAttributes(&fa, group_reduce_lists_kernel<0>);
+        (void)cudaFuncGetAttributes(&fa, group_reduce_lists_kernel<2>);
+        (void)cudaFuncGetAttributes(&fa, group_reduce_lists_kernel<4>);
+        (void)cudaFuncGetAttributes(&fa, group_reduce_lists_kernel<8>);
+        (void)cudaFuncGetAttributes(&fa, group_scale_lists_kernel);
         (void)cudaFuncGetAttributes(&fa, flag_write_kernel);
         (void)cudaFuncGetAttributes(&fa, flag_wait_kernel);
         (void)cudaGetLastError();
@@ -424,7 +497,7 @@ int crv_group_set_timeout_ms(crv_group* g, uint32_t ms)
     return CRV_OK;
 }
 
-int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream)
+static int group_all_reduce(crv_group* g, uint32_t buffer, float scale, const crv_pixel_lists* lists, float others_scale, void* stream)
 {
     CRV_REQUIRE(g != nullptr, "crv_group_all_reduce_sum_scale: null group");
     CRV_REQUIRE(buffer < g->nbuf, "crv_group_all_reduce_sum_scale: buffer index out of range");
@@ -435,7 +508,9 @@ int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, v
     const uint32_t n4 = g->width * g->height;
     CRV_CUDA(cudaEventRecord(g->ev0, s));
     if (g->nranks == 1) {
-        group_scale_kernel<<<g->ctx->sm_count * 2, 512, 0, s>>>(reinterpret_cast<float4*>(g->block + FLAG_PAGE + buffer * g->image_bytes), n4, scale);
+        float4* img = reinterpret_cast<float4*>(g->block + FLAG_PAGE + buffer * g->image_bytes);
+        if (lists) group_scale_lists_kernel<<<g->ctx->sm_count * 2, 512, 0, s>>>(img, lists->tracked_xy, lists->other_pixels, lists->counts, lists->width, scale, others_scale);
+        else group_scale_kernel<<<g->ctx->sm_count * 2, 512, 0, s>>>(img, n4, scale);
         g->ctx->launches++;
     } else {
         const uint32_t epoch = ++g->epoch;
@@ -458,16 +533,32 @@ int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, v
         a.epoch = epoch;
         a.scale = scale;
         a.timeout_ns = g->timeout_ns;
-        const uint32_t band = (n4 + g->nranks - 1) / g->nranks;
+        if (lists) {
+            a.tracked_xy = lists->tracked_xy;
+            a.other_pixels = lists->other_pixels;
+            a.counts = lists->counts;
+            a.width = lists->width;
+            a.others_scale = others_scale;
+        }
+        const uint32_t band = lists ? n4 : (n4 + g->nranks - 1) / g->nranks;
         unsigned blocks = (band + RED_THREADS - 1) / RED_THREADS;
         const unsigned cap = (unsigned)g->ctx->sm_count * 2u;
         if (blocks > cap) blocks = cap;
         if (blocks < 1u) blocks = 1u;
-        switch (g->nranks) {
-            case 2: group_reduce_kernel<2><<<blocks, RED_THREADS, 0, s>>>(a); break;
-            case 4: group_reduce_kernel<4><<<blocks, RED_THREADS, 0, s>>>(a); break;
-            case 8: group_reduce_kernel<8><<<blocks, RED_THREADS, 0, s>>>(a); break;
-            default: group_reduce_kernel<0><<<blocks, RED_THREADS, 0, s>>>(a); break;
+        if (lists) {
+            switch (g->nranks) {
+                case 2: group_reduce_lists_kernel<2><<<blocks, RED_THREADS, 0, s>>>(a); break;
+                case 4: group_reduce_lists_kernel<4><<<blocks, RED_THREADS, 0, s>>>(a); break;
+                case 8: group_reduce_lists_kernel<8><<<blocks, RED_THREADS, 0, s>>>(a); break;
+                default: group_reduce_lists_kernel<0><<<blocks, RED_THREADS, 0, s>>>(a); break;
+            }
+        } else {
+            switch (g->nranks) {
+                case 2: group_reduce_kernel<2><<<blocks, RED_THREADS, 0, s>>>(a); break;
+                case 4: group_reduce_kernel<4><<<blocks, RED_THREADS, 0, s>>>(a); break;
+                case 8: group_reduce_kernel<8><<<blocks, RED_THREADS, 0, s>>>(a); break;
+                default: group_reduce_kernel<0><<<blocks, RED_THREADS, 0, s>>>(a); break;
+            }
         }
         g->ctx->launches++;
         CRV_CUDA(cudaGetLastError());
@@ -481,6 +572,19 @@ int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, v
     CRV_CUDA(cudaEventRecord(g->ev1, s));
     g->timed = true;
     return CRV_OK;
+}
+
+int crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, void* stream)
+{
+    return group_all_reduce(g, buffer, scale, nullptr, 0.0f, stream);
+}
+
+int crv_group_all_reduce_lists_sum_scale(crv_group* g, uint32_t buffer, float scale, float others_scale, const crv_pixel_lists* lists, void* stream)
+{
+    CRV_REQUIRE(lists && lists->tracked_xy && lists->other_pixels && lists->counts && lists->width > 0,
+                "crv_group_all_reduce_lists_sum_scale: incomplete pixel lists");
+    CRV_REQUIRE(g == nullptr || lists->width == g->width, "crv_group_all_reduce_lists_sum_scale: the lists belong to another image width");
+    return group_all_reduce(g, buffer, scale, lists, others_scale, stream);
 }
 
 int crv_group_status(crv_group* g, void* stream)

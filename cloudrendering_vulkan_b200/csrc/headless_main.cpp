@@ -248,7 +248,15 @@ int main(int argc, char** argv)
                     a.resultImage->Clear(a.stream->Get());
                     if (!mine.empty()) a.pathTracingTechnique->RenderBatch(mine.data(), (unsigned)mine.size(), 0, CRV_ACCUM_SUM, a.stream->Get(), 0);
                 }
-                for (auto& a : apps) a->group->AllReduceSumScale(1.0f / (float)o.spp, a->stream->Get());
+                // frames split evenly: every member holds the same number of samples of every pixel and only the tracked pixels
+                // have to cross between the GPUs; otherwise the whole images are combined
+                for (unsigned m = 0; m < o.gpus; ++m) {
+                    App& a = *apps[m];
+                    if (o.spp % o.gpus == 0)
+                        a.group->AllReduceListsSumScale(1.0f / (float)o.spp, 1.0f / (float)(o.spp / o.gpus), a.pathTracingTechnique->GetPixelLists(), a.stream->Get());
+                    else
+                        a.group->AllReduceSumScale(1.0f / (float)o.spp, a.stream->Get());
+                }
                 for (auto& a : apps) a->device->WaitIdle(a->stream->Get());
                 for (auto& a : apps) a->group->CheckStatus(a->stream->Get());
                 app.pushConstants.frameCount += o.spp;

@@ -88,16 +88,22 @@ class SampleSplit:
         return frames_for_rank(all_seeds, self.rank, self.world)
 
     def render_picture(self, all_seeds, stream=0, backend: str = "peer"):
-        """clear, this member's frames as a plain sum, combine + divide by len(all_seeds): every member ends with the mean"""
+        """clear, this member's frames as a plain sum, combine + divide by len(all_seeds): every member ends with the mean.
+        backend: "peer" (the group's combine kernel; only the tracked pixels travel when the frames split evenly),
+        "peer_dense" (whole images), "nccl" (ncclAllReduce + scale, for comparison)"""
         seeds = self.my_seeds(all_seeds)
         self.image.clear(stream)
         if len(seeds):
             self.r.pathTracingTechnique.RenderBatch(seeds, 0, capi.ACCUM_SUM, stream, 0)
-        self.reduce(len(all_seeds), stream, backend)
+        self.reduce(len(all_seeds), stream, backend, n_mine=len(seeds))
 
-    def reduce(self, spp_total: int, stream=0, backend: str = "peer"):
+    def reduce(self, spp_total: int, stream=0, backend: str = "peer", n_mine: int = 0):
         scale = 1.0 / float(spp_total)
-        if backend == "peer":
+        if backend == "peer" and n_mine > 0 and n_mine * self.world == spp_total:
+            # replicas of one scene: the same pixel lists everywhere, and every member holds n_mine samples of every pixel
+            lists = self.r.pathTracingTechnique.PixelLists()
+            self.group.all_reduce_lists_sum_scale(scale, 1.0 / float(n_mine), lists, stream, self.buffer)
+        elif backend in ("peer", "peer_dense"):
             self.group.all_reduce_sum_scale(scale, stream, self.buffer)
         elif backend == "nccl":
             self.group.nccl_all_reduce_sum_scale(scale, stream, self.buffer)

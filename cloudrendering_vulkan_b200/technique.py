@@ -257,6 +257,10 @@ class Group:
     def staging_release(self, buffer: int = 0, stream=0):
         check(lib.crv_group_staging_release(self.handle, buffer, _stream(stream)))
 
+    def all_reduce_lists_sum_scale(self, scale: float, others_scale: float, lists, stream=0, buffer: int = 0):
+        """lists: RenderTechniquePT.PixelLists() of this member's technique; only the tracked pixels cross NVLink"""
+        check(lib.crv_group_all_reduce_lists_sum_scale(self.handle, buffer, C.c_float(scale), C.c_float(others_scale), C.byref(lists), _stream(stream)))
+
     def set_timeout_ms(self, ms: int):
         check(lib.crv_group_set_timeout_ms(self.handle, int(ms)))
 
@@ -504,6 +508,12 @@ class RenderTechniquePT(RenderTechnique):
     def SetScheduler(self, scheduler="pool"):
         """which persistent-thread scheduler runs the tracker; both produce the same bits"""
         check(lib.crv_pt_set_scheduler(self.handle, self.SCHEDULERS[scheduler] if isinstance(scheduler, str) else int(scheduler)))
+
+    def PixelLists(self) -> capi.PixelLists:
+        """device-side lists of the tracked / other pixels of the last render call (crv_pt_pixel_lists)"""
+        out = capi.PixelLists()
+        check(lib.crv_pt_pixel_lists(self.handle, C.byref(out)))
+        return out
 
     def SetCoarseShift(self, min_shift: int = -1):
         """at least this cell size (8 << shift voxels) for the tracker's coarse threshold table; -1 = automatic"""

@@ -183,6 +183,11 @@ public:
         return Image(img, m_width, m_height);
     }
     void AllReduceSumScale(float scale, CommandStream stream = nullptr, uint32_t buffer = 0) { Check(crv_group_all_reduce_sum_scale(m_group, buffer, scale, stream)); }
+    // members that hold replicas of one scene: only the tracked pixels travel (lists = this member's RenderTechniquePT::GetPixelLists())
+    void AllReduceListsSumScale(float scale, float othersScale, const crv_pixel_lists& lists, CommandStream stream = nullptr, uint32_t buffer = 0)
+    {
+        Check(crv_group_all_reduce_lists_sum_scale(m_group, buffer, scale, othersScale, &lists, stream));
+    }
     void CheckStatus(CommandStream stream = nullptr) { Check(crv_group_status(m_group, stream)); }
     float LastReduceMs()
     {
@@ -374,6 +379,13 @@ public:
     void SetScheduler(int scheduler) { Check(crv_pt_set_scheduler(m_pt, scheduler)); }
     // 1 (default): ray sections that provably cannot collide are not tracked; 0: every step of the reference is executed
     void SetSkipLevel(int level) { Check(crv_pt_set_skip_level(m_pt, level)); }
+    // which pixels of the last render call were tracked / are the same background sample in every frame (device-side lists)
+    crv_pixel_lists GetPixelLists()
+    {
+        crv_pixel_lists l{};
+        Check(crv_pt_pixel_lists(m_pt, &l));
+        return l;
+    }
     // minimum cell size (8 << shift voxels) of the tracker's coarse threshold table; -1 = automatic
     void SetCoarseShift(int minShift) { Check(crv_pt_set_coarse_shift(m_pt, minShift)); }
     float LastRenderMs(unsigned* launches = nullptr)

@@ -57,13 +57,13 @@ def test_cpp_driver_matches_the_python_host_bitwise(crv, ctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gpus,same_device", [(2, True), (3, True), (2, False)])
-def test_cpp_driver_sample_split(crv, gpus, same_device):
+@pytest.mark.parametrize("gpus,same_device,spp", [(2, True, 7), (3, True, 7), (2, True, 8), (2, False, 7), (4, False, 8)])
+def test_cpp_driver_sample_split(crv, gpus, same_device, spp):
     """crv_headless --gpus N: crv::DeviceGroup (crv_group_*) from C++ -- one replica per member, frames f mod N, one combine
     kernel per member.  Every member must hold the same picture, equal to the 1-GPU picture within summation order (1e-6)."""
     if not same_device and crv.capi.lib.crv_device_count() < gpus:
         pytest.skip(f"needs {gpus} GPUs")
-    n, w, h, nsv, spp = 40, 96, 64, 56, 7
+    n, w, h, nsv = 40, 96, 64, 56          # spp 7: ragged split, whole images combined; spp 8: even split, tracked pixels only
     args = ["--fbm", n, "--width", w, "--height", h, "--nsv", nsv, "--spp", spp, "--g", 0.85, "--absorption", 0.1]
     import tempfile
     with tempfile.TemporaryDirectory() as d:
