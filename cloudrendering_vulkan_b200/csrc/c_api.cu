@@ -118,7 +118,6 @@ struct crv_pt {
     // ... and, through the occupied spans, on the cloud image's contents and the skip level
     bool geom_valid = false;
     unsigned char geom_key[68 + 32 + 4 + 8 + 8 + 4 + 4] = {};
-    int* occ_ext = nullptr;            // brick-index extremes of the occupied bricks (6 ints)
     float* occ_aabb = nullptr;         // world-space box around them (6 floats), PTConst::occ_aabb
     int skip_level = 1;                // crv_pt_set_skip_level
     // q-table cache
@@ -319,6 +318,7 @@ int crv_volume_create(crv_ctx* ctx, uint32_t nx, uint32_t ny, uint32_t nz, int l
             if (e == cudaSuccess) e = cudaCreateSurfaceObject(&v->surf, &rd);
         }
     }
+    if (e == cudaSuccess) e = cudaMalloc(&v->occ_ext, 6 * sizeof(int));
     if (e != cudaSuccess) {
         crv_set_error("crv_volume_create(%u,%u,%u,layout %d): %s", nx, ny, nz, layout, cudaGetErrorString(e));
         crv_volume_destroy(v);
@@ -340,6 +340,7 @@ int crv_volume_destroy(crv_volume* v)
     if (v->brick_max) cudaFree(v->brick_max);
     if (v->brick_absmax) cudaFree(v->brick_absmax);
     if (v->brick_absmax_wide) cudaFree(v->brick_absmax_wide);
+    if (v->occ_ext) cudaFree(v->occ_ext);
     delete v;
     return CRV_OK;
 }
@@ -756,6 +757,7 @@ int crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned /*image_index
     for (int i = 0; i < 3; ++i) c.rcext[i] = 1.0f / c.cext[i];
     c.rbase = 1.0f / c.base_scaling;
     c.brick_absmax = sv->cloud_vol->brick_absmax;
+    c.occ_ext = sv->cloud_vol->occ_ext;
     {   // fused build's approximate brick coordinate (doubles here, one rounding to fp32 each)
         bool ok = true;
         for (int i = 0; i < 3; ++i) {
@@ -843,7 +845,6 @@ int crv_pt_create(crv_ctx* ctx, const crv_camera_properties* cam, const crv_push
         CRV_CUDA(cudaMalloc(&pt->nhit, 2 * sizeof(uint32_t)));      // [0] hits, [1] misses
         CRV_CUDA(cudaMallocHost(&pt->counts_host, 2 * sizeof(uint32_t)));
         CRV_CUDA(cudaEventCreateWithFlags(&pt->counts_ev, cudaEventDisableTiming));
-        CRV_CUDA(cudaMalloc(&pt->occ_ext, 6 * sizeof(int)));
         CRV_CUDA(cudaMalloc(&pt->occ_aabb, 6 * sizeof(float)));
         CRV_CUDA(cudaMalloc(&pt->stats, sizeof(unsigned long long) * PT_STAT_COUNT));
         CRV_CUDA(cudaMemset(pt->stats, 0, sizeof(unsigned long long) * PT_STAT_COUNT));
@@ -1302,7 +1303,6 @@ int crv_pt_destroy(crv_pt* pt)
     if (pt->nhit) cudaFree(pt->nhit);
     if (pt->counts_host) cudaFreeHost(pt->counts_host);
     if (pt->counts_ev) cudaEventDestroy(pt->counts_ev);
-    if (pt->occ_ext) cudaFree(pt->occ_ext);
     if (pt->occ_aabb) cudaFree(pt->occ_aabb);
     if (pt->misslist) cudaFree(pt->misslist);
     if (pt->missdy) cudaFree(pt->missdy);
@@ -1709,8 +1709,7 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
             CRV_CUDA(cudaMemsetAsync(pt->nhit, 0, 2 * sizeof(uint32_t), s));
             CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
             if (c.occ_wide)
-                CRV_TRY(crv_launch_occ_aabb(pt->ctx, c.occ_wide, c.cloud.nbx, c.cloud.nby, c.cloud.nbz, pt->occ_ext, pt->occ_aabb, c.cb0, c.cext,
-                                            c.cloud.nx, c.cloud.ny, c.cloud.nz, s));
+                CRV_TRY(crv_launch_occ_aabb(pt->ctx, b.cloud_vol->occ_ext, pt->occ_aabb, c.cb0, c.cext, c.cloud.nx, c.cloud.ny, c.cloud.nz, s));
             CRV_TRY(crv_launch_classify(pt->ctx, c, pt->hitlist, pt->start, pt->nhit, pt->misslist, pt->missdy, s));
             pt->launches++;
             std::memcpy(pt->geom_key, key, sizeof(key));

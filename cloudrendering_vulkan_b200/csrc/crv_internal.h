@@ -233,6 +233,8 @@ struct crv_volume {
     float* brick_max = nullptr;            // nbx*nby*nbz: max(v, 0) over each brick's dilated voxel set
     float* brick_absmax = nullptr;         // nbx*nby*nbz: max |v| over the same set (feeds the q-table)
     float* brick_absmax_wide = nullptr;    // nbx*nby*nbz: max |v| over voxels [8b-1, 8b+9]^3 (approximate brick test)
+    int* occ_ext = nullptr;                // 6 ints, device: min / max brick index per axis over the bricks with brick_absmax_wide != 0
+                                           // ("occupied"); min = INT_MAX, max = -1 when there is none.  Valid with the brick tables.
     bool brick_max_valid = false;
     float majorant = 0.0f;
     bool majorant_valid = false;

@@ -122,8 +122,7 @@ struct FoldConst {
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
 int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t* hitlist, float* start, uint32_t* counts, uint32_t* misslist, float* missdy, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
-int crv_launch_occ_aabb(crv_ctx* ctx, const float* wide, int nbx, int nby, int nbz, int* ext6, float* aabb6, const float* b0, const float* extent,
-                        int nx, int ny, int nz, cudaStream_t s);
+int crv_launch_occ_aabb(crv_ctx* ctx, const int* ext6, float* aabb6, const float* b0, const float* extent, int nx, int ny, int nz, cudaStream_t s);
 int crv_launch_rcp_frames(crv_ctx* ctx, float* rcp, uint32_t first_frame_count, uint32_t n, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);
 int crv_launch_qcoarse(crv_ctx* ctx, const float* absmax_wide, uint8_t* qc, int nbx, int nby, int nbz, int shift, float max_ext, cudaStream_t s);

@@ -623,7 +623,8 @@ __global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_con
     __shared__ int s_lo, s_hi;
     __shared__ int s_search[6][64];
     __shared__ int s_zin[64], s_zend[64];
-    __shared__ float s_add[16][64];     // two chunks' addends, then the running sums after each slice
+    constexpr int G = 4;                // chunks per gather / serial-sum / exp iteration (G * 8 slices between two barriers)
+    __shared__ float s_add[8 * G][64];  // G chunks' addends, then the running sums after each slice
     __shared__ float s_acc[64];         // running sum of every column after the previous chunk
     __shared__ uint32_t s_full[MAX_CHUNK_WORDS];      // bit k: chunk k may add density
     const int N = c.n;
@@ -632,38 +633,47 @@ __global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_con
     const int bx = centre_out(blockIdx.x, gridDim.x), by = centre_out(blockIdx.y, gridDim.y);
     const int nchunks = (N + 7) >> 3;
 
-    // ---- [z_in, z_end) of the bundle's 64 columns: 6 bisections per column spread over 384 threads ----
+    // ---- which chunks of this bundle can meet density at all?  Its samples' brick coordinates are affine in z: per axis the
+    //      z range in which the bundle's 8 x 8 columns can touch the box of occupied bricks (crv_volume::occ_ext) is closed
+    //      form; outside the intersection of the three ranges every chunk is empty.  Most bundles have no such range. ----
+    __shared__ int s_clo, s_chi;
     if (t == 0) { s_lo = N; s_hi = 0; }
     if (t < MAX_CHUNK_WORDS) s_full[t] = 0u;
-    if (t < 384) {
-        const int col = t & 63, search = t >> 6;
-        const int cx = bx * 8 + (col & 7), cy = by * 8 + (col >> 3);
-        const int ax = search >> 1;
-        const float a_ax = (float)cx * c.right[ax] + (float)cy * c.up[ax];
-        s_search[search][col] = range_seek(c, a_ax, ax, (search & 1) != 0);
-    }
-    __syncthreads();
-    if (t < 64) {
-        const int cx = bx * 8 + (t & 7), cy = by * 8 + (t >> 3);
-        int z_in = max(max(s_search[0][t], s_search[2][t]), s_search[4][t]);
-        int z_end = min(min(s_search[1][t], s_search[3][t]), s_search[5][t]);
-        if (z_end < z_in) z_end = z_in;
-        if (cx >= N || cy >= N) z_in = z_end = 0;
-        s_zin[t] = z_in;
-        s_zend[t] = z_end;
-        s_acc[t] = 0.0f;
-        if (z_in < z_end) {
-            atomicMin(&s_lo, z_in);
-            atomicMax(&s_hi, z_end);
-        }
-    }
-    __syncthreads();
-    const int hi = s_hi;
-    const int lo = hi > 0 ? (s_lo & ~7) : N;      // bundle never enters the cloud: every chunk is "before"
-
-    // ---- classification of the chunks in [lo, hi): one warp per chunk, lanes over the cloud bricks its samples can touch ----
     const bool pre = c.brick_absmax_wide != nullptr;
-    for (int k = (lo >> 3) + (int)warp; k * 8 < hi; k += 16) {
+    if (t == 0) {
+        float zlo = 0.0f, zhi = (float)N;
+        if (pre) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int nb = a == 0 ? c.cloud.nbx : a == 1 ? c.cloud.nby : c.cloud.nbz;
+                const int e0 = __ldg(c.occ_ext + a), e1 = __ldg(c.occ_ext + 3 + a);
+                if (e1 < e0) { zlo = 1.0f; zhi = 0.0f; break; }                   // nothing occupied anywhere
+                const float base = c.pre_c[a] + (float)(bx * 8) * c.pre_r[a] + (float)(by * 8) * c.pre_u[a];
+                const float er = 7.0f * c.pre_r[a], eu = 7.0f * c.pre_u[a];
+                const float mn = base + fminf(er, 0.0f) + fminf(eu, 0.0f) - 0.25f, mx = base + fmaxf(er, 0.0f) + fmaxf(eu, 0.0f) + 0.25f;
+                // coordinates beyond the volume clamp to its boundary bricks: an occupied boundary brick extends to infinity
+                const float lo_b = e0 == 0 ? -3.0e38f : (float)e0, hi_b = e1 == nb - 1 ? 3.0e38f : (float)(e1 + 1);
+                const float l = c.pre_l[a];
+                // need  mx + z*l >= lo_b  and  mn + z*l < hi_b
+                if (l > 0.0f) {
+                    zlo = fmaxf(zlo, (lo_b - mx) / l);
+                    zhi = fminf(zhi, (hi_b - mn) / l);
+                } else if (l < 0.0f) {
+                    zlo = fmaxf(zlo, (hi_b - mn) / l);
+                    zhi = fminf(zhi, (lo_b - mx) / l);
+                } else if (mx < lo_b || mn >= hi_b) {
+                    zlo = 1.0f; zhi = 0.0f;
+                }
+            }
+        }
+        // one chunk of slack on either side covers the rounding of the divisions above
+        const bool none = !(zlo <= zhi);
+        s_clo = none ? N : max((int)floorf(fmaxf(zlo, 0.0f)) - 8, 0) & ~7;
+        s_chi = none ? 0 : min((int)ceilf(fminf(zhi, (float)N)) + 8, N);
+    }
+    __syncthreads();
+    // ---- classification of the chunks in that range: one warp per chunk, lanes over the cloud bricks its samples can touch ----
+    for (int k = (s_clo >> 3) + (int)warp; k * 8 < s_chi; k += 16) {
         bool occupied = !pre;
         if (pre) {
             // approximate brick coordinate of the chunk's corner voxel and its extent over the chunk (affine in x, y, z)
@@ -693,6 +703,48 @@ __global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_con
         if (occupied && lane == 0) atomicOr(&s_full[k >> 5], 1u << (k & 31));
     }
     __syncthreads();
+    bool any_full = false;
+#pragma unroll
+    for (int w = 0; w < MAX_CHUNK_WORDS; ++w) any_full = any_full || s_full[w] != 0u;
+
+    // ---- [z_in, z_end) of the bundle's 64 columns -- only a bundle with such chunks needs them: 6 searches per column spread
+    //      over 384 threads; chunks outside every column's interval are empty after all ----
+    if (any_full) {
+        if (t < 384) {
+            const int col = t & 63, search = t >> 6;
+            const int cx = bx * 8 + (col & 7), cy = by * 8 + (col >> 3);
+            const int ax = search >> 1;
+            const float a_ax = (float)cx * c.right[ax] + (float)cy * c.up[ax];
+            s_search[search][col] = range_seek(c, a_ax, ax, (search & 1) != 0);
+        }
+        __syncthreads();
+        if (t < 64) {
+            const int cx = bx * 8 + (t & 7), cy = by * 8 + (t >> 3);
+            int z_in = max(max(s_search[0][t], s_search[2][t]), s_search[4][t]);
+            int z_end = min(min(s_search[1][t], s_search[3][t]), s_search[5][t]);
+            if (z_end < z_in) z_end = z_in;
+            if (cx >= N || cy >= N) z_in = z_end = 0;
+            s_zin[t] = z_in;
+            s_zend[t] = z_end;
+            if (z_in < z_end) {
+                atomicMin(&s_lo, z_in);
+                atomicMax(&s_hi, z_end);
+            }
+        }
+        __syncthreads();
+        const int hi = s_hi, lo = hi > 0 ? (s_lo & ~7) : N;
+        if (t < MAX_CHUNK_WORDS) {              // keep the chunks [lo / 8, ceil(hi / 8))
+            const int first = lo >> 3, last = (hi + 7) >> 3, w0 = t * 32;
+            uint32_t keep = 0u;
+            for (int bit = 0; bit < 32; ++bit) if (w0 + bit >= first && w0 + bit < last) keep |= 1u << bit;
+            s_full[t] &= keep;
+        }
+    }
+    if (t < 64) {
+        s_acc[t] = 0.0f;
+        if (!any_full) { s_zin[t] = 0; s_zend[t] = 0; }
+    }
+    __syncthreads();
 
     const int col = t & 63, lz = t >> 6;
     const int x = bx * 8 + (t & 7), y = by * 8 + ((t >> 3) & 7);
@@ -704,19 +756,6 @@ __global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_con
     const float pa[3] = {__fmaf_rn(fy, c.pre_u[0], __fmaf_rn(fx, c.pre_r[0], c.pre_c[0])),
                          __fmaf_rn(fy, c.pre_u[1], __fmaf_rn(fx, c.pre_r[1], c.pre_c[1])),
                          __fmaf_rn(fy, c.pre_u[2], __fmaf_rn(fx, c.pre_r[2], c.pre_c[2]))};
-    auto addend = [&](int z) -> float {
-        if (!(z >= z_in && z < z_end)) return 0.0f;       // + 0 outside the interval leaves the sum unchanged (it is never -0)
-        if (pre) {
-            const float fz = (float)z;
-            const int bi = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[0], pa[0]), 8388608.0f)) - 0x4B000000, 0);
-            const int bj = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[1], pa[1]), 8388608.0f)) - 0x4B000000, 0);
-            const int bk = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[2], pa[2]), 8388608.0f)) - 0x4B000000, 0);
-            const unsigned b = ((unsigned)min(bk, c.cloud.nbz - 1) * c.cloud.nby + (unsigned)min(bj, c.cloud.nby - 1)) * c.cloud.nbx +
-                               (unsigned)min(bi, c.cloud.nbx - 1);
-            if (__ldg(c.brick_absmax_wide + b) == 0.0f) return 0.0f;
-        }
-        return div_rn_by(column_sample<CL, true>(c, a, z) * c.density_scaling, c.base_scaling, c.rbase);
-    };
     auto transmittance = [&](int z, float acc) -> float {
         float tr = 1.0f;
         if (__any_sync(0xffffffffu, acc != 0.0f) && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
@@ -769,17 +808,41 @@ __global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_con
             k += run;
             continue;
         }
-        // ---- chunk k may add density: gather, serial sums, exp -- with chunk k + 1 in the same barrier pair ----
+        // ---- chunk k may add density: gather, serial sums, exp for chunks k .. k + G - 1 between one pair of barriers.  The G
+        //      brick look-ups of a thread are issued together, then the samples of those that are not proven empty: a bundle
+        //      inside the cloud is a chain of such iterations, and their latency is what the build waits for at the end ----
         const int z0 = k * 8;
-        const int za = z0 + lz, zb = z0 + 8 + lz;
-        s_add[lz][col] = addend(za);
-        s_add[8 + lz][col] = addend(zb);
+        float addv[G];
+        bool need[G];
+        float wide[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const int z = z0 + 8 * u + lz;
+            need[u] = z >= z_in && z < z_end;
+            wide[u] = 1.0f;
+            if (need[u] && pre) {
+                const float fz = (float)z;
+                const int bi = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[0], pa[0]), 8388608.0f)) - 0x4B000000, 0);
+                const int bj = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[1], pa[1]), 8388608.0f)) - 0x4B000000, 0);
+                const int bk = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[2], pa[2]), 8388608.0f)) - 0x4B000000, 0);
+                const unsigned b = ((unsigned)min(bk, c.cloud.nbz - 1) * c.cloud.nby + (unsigned)min(bj, c.cloud.nby - 1)) * c.cloud.nbx +
+                                   (unsigned)min(bi, c.cloud.nbx - 1);
+                wide[u] = __ldg(c.brick_absmax_wide + b);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            addv[u] = 0.0f;       // + 0 outside the interval / in empty bricks leaves the sum unchanged (it is never -0)
+            if (need[u] && !(wide[u] == 0.0f))
+                addv[u] = div_rn_by(column_sample<CL, true>(c, a, z0 + 8 * u + lz) * c.density_scaling, c.base_scaling, c.rbase);
+            s_add[8 * u + lz][col] = addv[u];
+        }
         __syncthreads();
         bool nz = false;
         if (t < 64) {
             float sum = s_acc[t];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < 8 * G; ++u) {
                 sum = sum + s_add[u][t];          // accumulatedValue after slice z0 + u, the shader's order (:89)
                 s_add[u][t] = sum;
             }
@@ -787,11 +850,13 @@ __global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_con
             nz = sum != 0.0f;
         }
         any_acc = __syncthreads_or(nz) != 0 || any_acc;
-        const float tra = transmittance(za, s_add[lz][col]);
-        const float trb = transmittance(zb, s_add[8 + lz][col]);
-        if (inb && za < N) __stcs(vox0 + (size_t)k * chunk_step, tra);
-        if (inb && zb < N) __stcs(vox0 + (size_t)(k + 1) * chunk_step, trb);
-        k += 2;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const int z = z0 + 8 * u + lz;
+            const float tr = transmittance(z, s_add[8 * u + lz][col]);
+            if (inb && z < N) __stcs(vox0 + (size_t)(k + u) * chunk_step, tr);
+        }
+        k += G;
     }
 }
 

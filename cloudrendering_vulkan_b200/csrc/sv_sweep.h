@@ -24,6 +24,7 @@ struct SVConst {
     // (~ ((s*size - 0.5) / 8) per axis), against the wide-dilated brick table; null when the error bound does not hold
     const float* brick_absmax_wide;
     float pre_c[3], pre_r[3], pre_u[3], pre_l[3];
+    const int* occ_ext;         // crv_volume::occ_ext of the cloud: brick-index extremes of its occupied bricks (device, 6 ints)
 };
 
 constexpr int SV_MAX_FAST_N = 4096;   // entries of the constant reciprocal table (4096^3 floats = 275 GB: beyond HBM anyway)

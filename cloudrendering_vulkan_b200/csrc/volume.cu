@@ -255,6 +255,46 @@ int crv_launch_retile(crv_ctx* ctx, const float* linear_src, crv_volume* dst, cu
     return CRV_OK;
 }
 
+// Occupancy extent: min / max brick index per axis over the bricks whose wide maximum is not zero (crv_volume::occ_ext).  The
+// path tracer turns it into a world-space box (segments end where they leave it), the shadow-volume build into the range of
+// chunks of a column bundle that can meet density at all.
+__global__ void occ_init_kernel(int* __restrict__ ext)
+{
+    if (threadIdx.x < 6) ext[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : -1;
+}
+__global__ void occ_extent_kernel(const float* __restrict__ wide, int nbx, int nby, int nbz, int* __restrict__ ext)
+{
+    const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y, bz = blockIdx.z;
+    bool occ = false;
+    if (bx < nbx && by < nby) occ = wide[((size_t)bz * nby + by) * nbx + bx] != 0.0f;
+    // one atomic per warp and bound: the warp's lanes share bz and span a few (bx, by)
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    if (m == 0u) return;
+    int lox = occ ? bx : 0x7fffffff, hix = occ ? bx : -1, loy = occ ? by : 0x7fffffff, hiy = occ ? by : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lox = min(lox, __shfl_xor_sync(0xffffffffu, lox, o));
+        hix = max(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = min(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+        hiy = max(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+    }
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31u) == 0u) {
+        atomicMin(ext + 0, lox); atomicMin(ext + 1, loy); atomicMin(ext + 2, bz);
+        atomicMax(ext + 3, hix); atomicMax(ext + 4, hiy); atomicMax(ext + 5, bz);
+    }
+}
+
+static int launch_occ_extent(crv_ctx* ctx, crv_volume* vol, cudaStream_t s)
+{
+    if (!vol->occ_ext) CRV_CUDA(cudaMalloc(&vol->occ_ext, 6 * sizeof(int)));
+    occ_init_kernel<<<1, 32, 0, s>>>(vol->occ_ext);
+    const dim3 block(32, 8, 1), grid((vol->nbx + 31) / 32, (vol->nby + 7) / 8, vol->nbz);
+    occ_extent_kernel<<<grid, block, 0, s>>>(vol->brick_absmax_wide, (int)vol->nbx, (int)vol->nby, (int)vol->nbz, vol->occ_ext);
+    ctx->launches += 2;
+    CRV_CUDA(cudaGetLastError());
+    return CRV_OK;
+}
+
 // Upload path: layout conversion (when `store`) + all three brick tables in two passes over a linear x-fastest source.
 // `scratch` holds the pass-X arrays: 3 * nbx * ny * nz floats.
 int crv_launch_retile_tables(crv_ctx* ctx, const float* linear_src, crv_volume* dst, bool store, float* scratch, cudaStream_t s)
@@ -283,6 +323,10 @@ int crv_launch_retile_tables(crv_ctx* ctx, const float* linear_src, crv_volume* 
                                             dst->brick_absmax, dst->brick_max, dst->brick_absmax_wide);
     ctx->launches += 2;
     CRV_CUDA(cudaGetLastError());
+    {
+        const int rc = launch_occ_extent(ctx, dst, s);
+        if (rc != CRV_OK) return rc;
+    }
     dst->brick_max_valid = true;
     return CRV_OK;
 }
@@ -326,6 +370,10 @@ int crv_launch_brick_max(crv_ctx* ctx, crv_volume* vol, cudaStream_t s)
         brick_absmax_wide_kernel<CRV_LAYOUT_LINEAR><<<blocks, threads, 0, s>>>(v, vol->brick_absmax_wide);
     ctx->launches += 2;
     CRV_CUDA(cudaGetLastError());
+    {
+        const int rc = launch_occ_extent(ctx, vol, s);
+        if (rc != CRV_OK) return rc;
+    }
     vol->brick_max_valid = true;
     return CRV_OK;
 }

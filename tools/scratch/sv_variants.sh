@@ -1,0 +1,7 @@
+#!/bin/bash
+cp cloudrendering_vulkan_b200/libcrv_b200.so /tmp/base.so
+for v in base "$@"; do
+  if [ "$v" = base ]; then cp /tmp/base.so cloudrendering_vulkan_b200/libcrv_b200.so; else cp build_variants/$v/libcrv_b200.so cloudrendering_vulkan_b200/libcrv_b200.so; fi
+  python tools/sv_bench.py --layout brick --mode fused --cases 512:512,1024:1024 | python -c "import sys,json; [print('$v', d['n_sv'], round(d['ms_median'],4)) for d in map(json.loads, sys.stdin)]"
+done
+cp /tmp/base.so cloudrendering_vulkan_b200/libcrv_b200.so

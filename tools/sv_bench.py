@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "generic", "single_pass", "two_pass", "fused", "fused_v1"])
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--light", default="1,-1,0")
+    ap.add_argument("--zero", action="store_true", help="an empty cloud: the build degenerates to storing ones (its floor)")
     args = ap.parse_args()
     try:
         peak = float(json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"])
@@ -35,7 +36,10 @@ def main():
         wl = crv.Workload("svbench", nc, 64, 64, 1, nsv, 50.0, 0.0, 0.85, light)
         r = crv.make_renderer(ctx, wl, cloud_layout=args.layout)
         r.shadowVolumeTechnique.SetTuning(args.mode)
-        r.set_cloud_synthetic(nc, 1234, 0)
+        if args.zero:
+            r.set_cloud_host(np.zeros(nc ** 3, np.float32), (nc,) * 3, (1.0 / nc,) * 3)
+        else:
+            r.set_cloud_synthetic(nc, 1234, 0)
         ts = []
         for i in range(args.reps + 3):
             r.UpdateShadowVolume(0)
