@@ -144,7 +144,7 @@ def _workload_text(wl, spp_total, world):
 
 def _config_dict(wl, args, world, spp_total, layout, math):
     return {"workload": _workload_text(wl, spp_total, world), "spp_total": spp_total,
-            "parallelism": f"frames f mod {world} per GPU, grid + shadow volume replicated, one peer-memory combine kernel per GPU"
+            "parallelism": f"frames f mod {world} per GPU, grid + shadow volume replicated, the fold pushes the tracked sums into every member over NVLink, then one wait + one local kernel per GPU"
                            if world > 1 else "one GPU",
             "layout": layout, "math": math,
             "l2": "inputs larger than L2 (grid + shadow volume >= 1 GB vs 126 MB)" if wl.n_cloud >= 512 else
@@ -351,7 +351,8 @@ def run_ours(args, wl):
 
     step_no = [0]
 
-    def make_step(all_seeds, backend="peer"):
+    def make_step(all_seeds, backend=None):
+        backend = backend or args.combine
         def step():
             if animated:
                 r.lightDirection = light_of(step_no[0])
@@ -449,10 +450,15 @@ def run_ours(args, wl):
         o_ms = timed(make_step(o_seeds), max(3, args.steps), 2)
         scaling_other = {"scaling": other, "spp_total": o_total, "ms_per_step": o_ms, "value": W * H * o_total / (o_ms * 1e-3) / 1e6,
                          "unit": "Mpath-samples/s"}
-    reduce_cmp = {"peer_kernel_ms": reduce_ms,
-                  "note": "peer_kernel: crv_group_all_reduce_lists_sum_scale, start / end barriers included (only the tracked pixels cross "
-                          "NVLink); peer_dense: whole images through the same kernel; nccl: ncclAllReduce of the whole image + scale kernel"}
+    reduce_cmp = {"timed_path": args.combine, "push_ms" if args.combine == "push" else "timed_ms": reduce_ms,
+                  "note": "device time of the combine on rank 0, waiting for the slowest member included.  push (the timed path): "
+                          "crv_group_push_finish -- the fold has already stored the tracked sums into every member's inbox; one wait, one "
+                          "local kernel; peer_kernel: crv_group_all_reduce_lists_sum_scale, two barriers around a band reduce over peer "
+                          "memory (tracked pixels only); peer_dense: whole images through the same kernel; nccl: ncclAllReduce of the "
+                          "whole image + scale kernel"}
     if world > 1 and not args.quick:
+        reduce_cmp["peer_ms_per_step"] = timed(make_step(all_seeds, "peer"), 3, 2)
+        reduce_cmp["peer_kernel_ms"] = split.group.last_reduce_ms()
         timed(make_step(all_seeds, "peer_dense"), 3, 2)
         reduce_cmp["peer_dense_kernel_ms"] = split.group.last_reduce_ms()
         try:
@@ -614,12 +620,17 @@ def run_ours(args, wl):
                 p.r.cloudImage.upload(hg, p.s, wait=False)                                     # H2D: the density grid
             p.r.SetCloudProperties((wl.n_cloud,) * 3, (1.0 / wl.n_cloud,) * 3, p.r.cloudImage.majorant(p.s))
             p.r.UpdateCloudData(p.s)                                                           # descriptor updates + shadow-volume rebuild
-            p.img.clear(p.s)
-            p.r.pathTracingTechnique.RenderBatch(my, 0, crv.ACCUM_SUM, p.s, 0)
-            if len(my) * world == spp_total:          # even split: only the tracked pixels cross between the GPUs
-                split.group.all_reduce_lists_sum_scale(1.0 / spp_total, 1.0 / len(my), p.r.pathTracingTechnique.PixelLists(), p.s, p.k)
+            if len(my) * world == spp_total and args.combine == "push":      # even split: only the tracked pixels cross between the GPUs, pushed by the fold
+                targets = split.group.push_begin(p.k)
+                p.r.pathTracingTechnique.RenderBatchPush(my, targets, 1.0 / len(my), p.s, 0)
+                split.group.push_finish(1.0 / spp_total, p.r.pathTracingTechnique.PixelLists(), p.s, p.k)
             else:
-                split.group.all_reduce_sum_scale(1.0 / spp_total, p.s, p.k)
+                p.img.clear(p.s)
+                p.r.pathTracingTechnique.RenderBatch(my, 0, crv.ACCUM_SUM, p.s, 0)
+                if len(my) * world == spp_total:
+                    split.group.all_reduce_lists_sum_scale(1.0 / spp_total, 1.0 / len(my), p.r.pathTracingTechnique.PixelLists(), p.s, p.k)
+                else:
+                    split.group.all_reduce_sum_scale(1.0 / spp_total, p.s, p.k)
 
         def e2e_finish(p):
             p.img.download(p.s, out=p.hi)                                                      # D2H: the picture (synchronises p.s)
@@ -780,6 +791,8 @@ def main():
                          "(crv_c_api.h: crv_pt_math_mode); the other mode's figure is reported under math_modes")
     ap.add_argument("--scheduler", default="pool", choices=["pool", "lanes"])
     ap.add_argument("--skip-level", type=int, default=1, choices=[0, 1])
+    ap.add_argument("--combine", default="push", choices=["push", "peer", "peer_dense"],
+                    help="how the members' sums are combined in the timed region (A/B; see `combine` in the output line)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="only the timed region (no census / other modes): for profiler passes")

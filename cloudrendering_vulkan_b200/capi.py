@@ -83,6 +83,11 @@ class PixelLists(C.Structure):
     _fields_ = [("tracked_xy", C.c_void_p), ("other_pixels", C.c_void_p), ("counts", C.c_void_p), ("width", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class PushTargets(C.Structure):
+    _fields_ = [("inbox", C.c_void_p * 16), ("flag", C.c_void_p * 16), ("done", C.c_void_p), ("nranks", C.c_uint32), ("rank", C.c_uint32),
+                ("epoch", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class GroupHandle(C.Structure):
     _fields_ = [("pid", C.c_uint64), ("device", C.c_int32), ("rank", C.c_uint32), ("base", C.c_uint64), ("bytes", C.c_uint64),
                 ("ipc", C.c_ubyte * 64)]
@@ -126,6 +131,9 @@ SIGNATURES = {
     "crv_group_set_timeout_ms": (C.c_int, [_vp, _u32]),
     "crv_group_all_reduce_lists_sum_scale": (C.c_int, [_vp, _u32, C.c_float, C.c_float, _P(PixelLists), _vp]),
     "crv_pt_pixel_lists": (C.c_int, [_vp, _P(PixelLists)]),
+    "crv_group_push_begin": (C.c_int, [_vp, _u32, _P(PushTargets)]),
+    "crv_group_push_finish": (C.c_int, [_vp, _u32, C.c_float, _P(PixelLists), _vp]),
+    "crv_pt_render_batch_push": (C.c_int, [_vp, _P(_i32), C.c_uint, _P(PushTargets), C.c_float, _vp, C.c_uint]),
     "crv_group_status": (C.c_int, [_vp, _vp]),
     "crv_group_last_reduce_ms": (C.c_int, [_vp, _P(C.c_float)]),
     "crv_group_nccl_unique_id": (C.c_int, [_vp]),

@@ -1628,7 +1628,8 @@ static int pt_timed_launch(crv_pt* pt, const PTConst& c, const PTBindings& b, cu
     return CRV_OK;
 }
 
-static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t first_fc, int mode, cudaStream_t s, unsigned idx)
+static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t first_fc, int mode, cudaStream_t s, unsigned idx,
+                     const crv_push_targets* push = nullptr, float others_scale = 0.0f)
 {
     CRV_REQUIRE(n > 0 && seeds, "RenderTechniquePT: no frames to render");
     CRV_REQUIRE(mode == CRV_ACCUM_RUNNING_MEAN || mode == CRV_ACCUM_SUM, "RenderTechniquePT: unknown accumulation mode");
@@ -1688,11 +1689,12 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         CRV_CUDA(cudaMalloc(&pt->rcp_fc1, sizeof(float) * cap));
         pt->rcp_elems = cap;
     }
-    if (n > 1) {                      // a single frame computes its one reciprocal in the fold kernel (same IEEE division)
+    const bool rcp_table = n > 1 && mode == CRV_ACCUM_RUNNING_MEAN;      // a plain sum divides by nothing
+    if (rcp_table) {                  // a single frame computes its one reciprocal in the fold kernel (same IEEE division)
         CRV_TRY(crv_launch_rcp_frames(pt->ctx, pt->rcp_fc1, first_fc, n, s));
         pt->launches++;
     }
-    c.rcp_fc1 = n > 1 ? pt->rcp_fc1 : nullptr;
+    c.rcp_fc1 = rcp_table ? pt->rcp_fc1 : nullptr;
     {
         unsigned char key[sizeof(pt->geom_key)];
         std::memcpy(key, &b.cam, 68);
@@ -1768,7 +1770,23 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         fc.missdy = pt->missdy;
         fc.job_counter = pt->job_counter;
         fc.stats = pt->stats;
-        CRV_TRY(crv_launch_fold(pt->ctx, fc, s));
+        if (push) {
+            fc.fresh = f0 == 0;
+            fc.last_round = f0 + nf >= n;
+            fc.frames_total = n;
+            fc.others_scale = others_scale;
+            fc.push_n = push->nranks;
+            fc.push_rank = push->rank;
+            fc.push_epoch = push->epoch;
+            for (uint32_t p = 0; p < push->nranks; ++p) {
+                fc.push_inbox[p] = reinterpret_cast<float4*>(push->inbox[p]);
+                fc.push_flag[p] = push->flag[p];
+            }
+            fc.push_done = push->done;
+            CRV_TRY(crv_launch_fold_push(pt->ctx, fc, s));
+        } else {
+            CRV_TRY(crv_launch_fold(pt->ctx, fc, s));
+        }
         pt->launches += 2;
     }
     return CRV_OK;
@@ -1788,6 +1806,18 @@ int crv_pt_render_batch(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t f
     CRV_REQUIRE(pt != nullptr, "crv_pt_render_batch: null technique");
     CRV_ENTER(pt->ctx);
     return pt_render(pt, seeds, n, first_frame_count, accum_mode, as_stream(stream), image_index);
+}
+
+int crv_pt_render_batch_push(crv_pt* pt, const int32_t* seeds, unsigned n, const crv_push_targets* targets, float others_scale,
+                             void* stream, unsigned image_index)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_render_batch_push: null technique");
+    CRV_REQUIRE(targets && targets->nranks >= 1 && targets->nranks <= 16 && targets->rank < targets->nranks && targets->done,
+                "crv_pt_render_batch_push: incomplete push targets (crv_group_push_begin fills them)");
+    for (uint32_t p = 0; p < targets->nranks; ++p)
+        CRV_REQUIRE(targets->inbox[p] && targets->flag[p], "crv_pt_render_batch_push: incomplete push targets (crv_group_push_begin fills them)");
+    CRV_ENTER(pt->ctx);
+    return pt_render(pt, seeds, n, 0, CRV_ACCUM_SUM, as_stream(stream), image_index, targets, others_scale);
 }
 
 int crv_pt_get_stats(crv_pt* pt, crv_pt_stats* out, void* stream)

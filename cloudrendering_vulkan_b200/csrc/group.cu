@@ -54,6 +54,10 @@ struct GroupFlags {
     // released[b][p] = last epoch of ITS staging buffer b that member p has finished reading
     uint32_t arrived[GROUP_MAX_BUF][GROUP_MAX];
     uint32_t released[GROUP_MAX_BUF][GROUP_MAX];
+    // push combine: pushed[b][p] = epoch of the last picture of buffer b whose sums member p has stored into MY inboxes;
+    // push_done[b] = CTA counter of my own fold of buffer b (zero between launches)
+    uint32_t pushed[GROUP_MAX_BUF][GROUP_MAX];
+    uint32_t push_done[GROUP_MAX_BUF];
 };
 static_assert(sizeof(GroupFlags) <= FLAG_PAGE, "flag page");
 
@@ -213,6 +217,40 @@ __global__ void group_scale_lists_kernel(float4* __restrict__ img, const uint32_
     }
 }
 
+// Second half of the push combine (crv_group_push_finish): every member's fold has stored its tracked sums into the inbox
+// this member keeps for it and the flags have been waited for, so everything is local: tracked pixel = (inbox[0] + inbox[1]
+// + ...) * scale in rank order -- the arithmetic of group_reduce_lists_kernel, so the same bits, on every member.
+struct FinishArgs {
+    const float4* inbox0;                          // inbox of member 0; member p's follows at p * stride4
+    size_t stride4;
+    float4* image;
+    const uint32_t* tracked_xy;
+    const uint32_t* counts;
+    uint32_t width, nranks;
+    float scale;
+};
+template <int N>
+__global__ void __launch_bounds__(RED_THREADS) group_push_finish_kernel(const __grid_constant__ FinishArgs a)
+{
+    const int nr = N > 0 ? N : (int)a.nranks;
+    const uint32_t ntracked = a.counts[0];
+    const uint32_t stride = gridDim.x * RED_THREADS;
+    for (uint32_t j = blockIdx.x * RED_THREADS + threadIdx.x; j < ntracked; j += stride) {
+        const uint32_t xy = __ldg(a.tracked_xy + j);
+        const uint32_t i = (xy >> 16) * a.width + (xy & 0xffffu);
+        float4 v[N > 0 ? N : GROUP_MAX];
+#pragma unroll
+        for (int p = 0; p < (N > 0 ? N : GROUP_MAX); ++p)
+            if (p < nr) v[p] = __ldcv(a.inbox0 + p * a.stride4 + i);
+        float4 s = v[0];
+#pragma unroll
+        for (int p = 1; p < (N > 0 ? N : GROUP_MAX); ++p)
+            if (p < nr) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+        s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
+        a.image[i] = s;
+    }
+}
+
 // fallbacks for cuStreamWriteValue32 / cuStreamWaitValue32 where the driver does not offer them
 struct FlagList {
     uint32_t* addr[GROUP_MAX];
@@ -297,6 +335,8 @@ struct crv_group {
     size_t image_bytes = 0, block_bytes = 0;
     size_t staging_bytes = 0, staging_offset = 0;  // per-buffer size (256-aligned) and offset of staging buffer 0 in the block
     uint32_t stage_epoch[GROUP_MAX_BUF] = {};
+    size_t inbox_offset = 0;                       // inbox of (buffer b, slot s, source member r) at inbox_offset + ((b * 2 + s) * nranks + r) * image_bytes
+    uint32_t push_epoch[GROUP_MAX_BUF] = {};
     bool use_memops = false;
     unsigned char* block = nullptr;                // own allocation
     unsigned char* peer[GROUP_MAX] = {};           // mapped peers (own block at [rank])
@@ -343,7 +383,8 @@ int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t widt
     g->image_bytes = ((size_t)width * height * 16 + 255) / 256 * 256;
     g->staging_bytes = ((size_t)staging_bytes + 255) / 256 * 256;
     g->staging_offset = FLAG_PAGE + g->image_bytes * nbuf;
-    g->block_bytes = g->staging_offset + g->staging_bytes * nbuf;
+    g->inbox_offset = g->staging_offset + g->staging_bytes * nbuf;
+    g->block_bytes = g->inbox_offset + g->image_bytes * 2 * nranks * nbuf;
     probe_stream_memops();
     g->use_memops = g_stream_write32 != nullptr;
     {
@@ -360,6 +401,11 @@ int crv_group_create(crv_ctx* ctx, uint32_t rank, uint32_t nranks, uint32_t widt
         (void)cudaFuncGetAttributes(&fa, group_reduce_lists_kernel<4>);
         (void)cudaFuncGetAttributes(&fa, group_reduce_lists_kernel<8>);
         (void)cudaFuncGetAttributes(&fa, group_scale_lists_kernel);
+        (void)cudaFuncGetAttributes(&fa, group_push_finish_kernel<0>);
+        (void)cudaFuncGetAttributes(&fa, group_push_finish_kernel<1>);
+        (void)cudaFuncGetAttributes(&fa, group_push_finish_kernel<2>);
+        (void)cudaFuncGetAttributes(&fa, group_push_finish_kernel<4>);
+        (void)cudaFuncGetAttributes(&fa, group_push_finish_kernel<8>);
         (void)cudaFuncGetAttributes(&fa, flag_write_kernel);
         (void)cudaFuncGetAttributes(&fa, flag_wait_kernel);
         (void)cudaGetLastError();
@@ -404,7 +450,10 @@ static void group_break_waits(crv_group* g)
     GroupFlags h{};
     for (uint32_t p = 0; p < (uint32_t)GROUP_MAX; ++p) {
         h.start[p] = h.end[p] = g->epoch;
-        for (uint32_t b = 0; b < (uint32_t)GROUP_MAX_BUF; ++b) h.arrived[b][p] = h.released[b][p] = g->stage_epoch[b];
+        for (uint32_t b = 0; b < (uint32_t)GROUP_MAX_BUF; ++b) {
+            h.arrived[b][p] = h.released[b][p] = g->stage_epoch[b];
+            h.pushed[b][p] = g->push_epoch[b];
+        }
     }
     h.error = 4u;
     cudaMemcpyAsync(g->block, &h, sizeof(h), cudaMemcpyHostToDevice, g->aux);
@@ -585,6 +634,68 @@ int crv_group_all_reduce_lists_sum_scale(crv_group* g, uint32_t buffer, float sc
                 "crv_group_all_reduce_lists_sum_scale: incomplete pixel lists");
     CRV_REQUIRE(g == nullptr || lists->width == g->width, "crv_group_all_reduce_lists_sum_scale: the lists belong to another image width");
     return group_all_reduce(g, buffer, scale, lists, others_scale, stream);
+}
+
+int crv_group_push_begin(crv_group* g, uint32_t buffer, crv_push_targets* out)
+{
+    CRV_REQUIRE(g && out, "crv_group_push_begin: null argument");
+    CRV_REQUIRE(buffer < g->nbuf, "crv_group_push_begin: buffer index out of range");
+    CRV_REQUIRE(g->connected, "crv_group_push_begin: crv_group_connect has not been called");
+    CRV_REQUIRE(!g->broken, "crv_group_push_begin: a barrier of this group timed out earlier");
+    std::memset(out, 0, sizeof(*out));
+    const uint32_t epoch = ++g->push_epoch[buffer];
+    const size_t slot = g->inbox_offset + ((size_t)(buffer * 2u + (epoch & 1u)) * g->nranks + g->rank) * g->image_bytes;
+    for (uint32_t p = 0; p < g->nranks; ++p) {
+        out->inbox[p] = reinterpret_cast<float*>(g->peer[p] + slot);
+        out->flag[p] = &reinterpret_cast<GroupFlags*>(g->peer[p])->pushed[buffer][g->rank];
+    }
+    out->done = &reinterpret_cast<GroupFlags*>(g->block)->push_done[buffer];
+    out->nranks = g->nranks;
+    out->rank = g->rank;
+    out->epoch = epoch;
+    return CRV_OK;
+}
+
+int crv_group_push_finish(crv_group* g, uint32_t buffer, float scale, const crv_pixel_lists* lists, void* stream)
+{
+    CRV_REQUIRE(g != nullptr, "crv_group_push_finish: null group");
+    CRV_REQUIRE(buffer < g->nbuf, "crv_group_push_finish: buffer index out of range");
+    CRV_REQUIRE(lists && lists->tracked_xy && lists->counts && lists->width == g->width, "crv_group_push_finish: pixel lists missing or of another image width");
+    CRV_REQUIRE(g->push_epoch[buffer] > 0, "crv_group_push_finish: crv_group_push_begin has not been called for this buffer");
+    CRV_REQUIRE(!g->broken, "crv_group_push_finish: a barrier of this group timed out earlier");
+    CRV_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = as_stream(stream);
+    const uint32_t epoch = g->push_epoch[buffer];
+    CRV_CUDA(cudaEventRecord(g->ev0, s));
+    if (g->nranks > 1) {
+        GroupFlags* mine = reinterpret_cast<GroupFlags*>(g->block);
+        uint32_t* addrs[GROUP_MAX];
+        uint32_t n = 0;
+        for (uint32_t p = 0; p < g->nranks; ++p) if (p != g->rank) addrs[n++] = &mine->pushed[buffer][p];
+        CRV_TRY_G(flags_wait(g, addrs, n, epoch, s));
+    }
+    FinishArgs a{};
+    a.inbox0 = reinterpret_cast<const float4*>(g->block + g->inbox_offset + (size_t)(buffer * 2u + (epoch & 1u)) * g->nranks * g->image_bytes);
+    a.stride4 = g->image_bytes / 16;
+    a.image = reinterpret_cast<float4*>(g->block + FLAG_PAGE + buffer * g->image_bytes);
+    a.tracked_xy = lists->tracked_xy;
+    a.counts = lists->counts;
+    a.width = g->width;
+    a.nranks = g->nranks;
+    a.scale = scale;
+    const unsigned blocks = (unsigned)g->ctx->sm_count * 2u;
+    switch (g->nranks) {
+        case 1: group_push_finish_kernel<1><<<blocks, RED_THREADS, 0, s>>>(a); break;
+        case 2: group_push_finish_kernel<2><<<blocks, RED_THREADS, 0, s>>>(a); break;
+        case 4: group_push_finish_kernel<4><<<blocks, RED_THREADS, 0, s>>>(a); break;
+        case 8: group_push_finish_kernel<8><<<blocks, RED_THREADS, 0, s>>>(a); break;
+        default: group_push_finish_kernel<0><<<blocks, RED_THREADS, 0, s>>>(a); break;
+    }
+    g->ctx->launches++;
+    CRV_CUDA(cudaGetLastError());
+    CRV_CUDA(cudaEventRecord(g->ev1, s));
+    g->timed = true;
+    return CRV_OK;
 }
 
 int crv_group_status(crv_group* g, void* stream)

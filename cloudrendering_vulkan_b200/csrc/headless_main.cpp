@@ -241,19 +241,26 @@ int main(int argc, char** argv)
             if (o.gpus > 1) {
                 // frame f -> member f mod N; every member sums its frames, one kernel per member combines and divides.
                 // All renders are enqueued before the first combine: a member's combine kernel waits for its peers' on the device.
+                // Frames split evenly: every member holds the same number of samples of every pixel, so only the tracked pixels
+                // have to cross between the GPUs -- each member's fold stores their sums into every member's inbox and one wait +
+                // one local kernel finish the picture (DeviceGroup::PushBegin / PushFinish).  Otherwise whole images are combined.
+                const bool even = o.spp % o.gpus == 0;
                 for (unsigned m = 0; m < o.gpus; ++m) {
                     App& a = *apps[m];
                     std::vector<int32_t> mine;
                     for (unsigned f = m; f < o.spp; f += o.gpus) mine.push_back(seeds[f]);
-                    a.resultImage->Clear(a.stream->Get());
-                    if (!mine.empty()) a.pathTracingTechnique->RenderBatch(mine.data(), (unsigned)mine.size(), 0, CRV_ACCUM_SUM, a.stream->Get(), 0);
+                    if (even) {
+                        const crv_push_targets targets = a.group->PushBegin();
+                        a.pathTracingTechnique->RenderBatchPush(mine.data(), (unsigned)mine.size(), targets, 1.0f / (float)mine.size(), a.stream->Get(), 0);
+                    } else {
+                        a.resultImage->Clear(a.stream->Get());
+                        if (!mine.empty()) a.pathTracingTechnique->RenderBatch(mine.data(), (unsigned)mine.size(), 0, CRV_ACCUM_SUM, a.stream->Get(), 0);
+                    }
                 }
-                // frames split evenly: every member holds the same number of samples of every pixel and only the tracked pixels
-                // have to cross between the GPUs; otherwise the whole images are combined
                 for (unsigned m = 0; m < o.gpus; ++m) {
                     App& a = *apps[m];
-                    if (o.spp % o.gpus == 0)
-                        a.group->AllReduceListsSumScale(1.0f / (float)o.spp, 1.0f / (float)(o.spp / o.gpus), a.pathTracingTechnique->GetPixelLists(), a.stream->Get());
+                    if (even)
+                        a.group->PushFinish(1.0f / (float)o.spp, a.pathTracingTechnique->GetPixelLists(), a.stream->Get());
                     else
                         a.group->AllReduceSumScale(1.0f / (float)o.spp, a.stream->Get());
                 }

@@ -116,12 +116,22 @@ struct FoldConst {
     const float* missdy;               // and dir.y of that ray
     unsigned int* job_counter;         // reset for the next tracker launch
     unsigned long long* stats;         // PT_STAT_PATHS += the miss pixels' paths (may be null)
+    // ---- push mode (crv_pt_render_batch_push, fold_push_kernel): CRV_ACCUM_SUM whose result leaves for the group members ----
+    int fresh;                         // the image holds nothing yet: this launch's sums replace its contents (no clear needed)
+    int last_round;                    // last launch of the render call: tracked sums go to the inboxes, the other pixels are finished
+    uint32_t frames_total;             // frames of the whole render call (the other pixels hold frames_total identical samples)
+    float others_scale;                // their final value: (frames_total * sampleBackground) * others_scale
+    uint32_t push_n, push_rank, push_epoch;
+    float4* push_inbox[16];            // member p's inbox image for this member's sums (own inbox included)
+    uint32_t* push_flag[16];           // word in member p's flag page: "the sums of member push_rank, epoch push_epoch, have arrived"
+    uint32_t* push_done;               // CTA counter in this member's flag page, zero between launches
 };
 
 
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
 int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t* hitlist, float* start, uint32_t* counts, uint32_t* misslist, float* missdy, cudaStream_t s);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
+int crv_launch_fold_push(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_occ_aabb(crv_ctx* ctx, const int* ext6, float* aabb6, const float* b0, const float* extent, int nx, int ny, int nz, cudaStream_t s);
 int crv_launch_rcp_frames(crv_ctx* ctx, float* rcp, uint32_t first_frame_count, uint32_t n, cudaStream_t s);
 int crv_launch_qtable(crv_ctx* ctx, const float* brick_max, float* qtable, long long n, float max_ext, cudaStream_t s);

@@ -89,9 +89,19 @@ class SampleSplit:
 
     def render_picture(self, all_seeds, stream=0, backend: str = "peer"):
         """clear, this member's frames as a plain sum, combine + divide by len(all_seeds): every member ends with the mean.
-        backend: "peer" (the group's combine kernel; only the tracked pixels travel when the frames split evenly),
+        backend: "push" (one-barrier combine: the fold stores the tracked sums into the members' inboxes; needs an even split,
+        otherwise "peer"), "peer" (the group's combine kernel; only the tracked pixels travel when the frames split evenly),
         "peer_dense" (whole images), "nccl" (ncclAllReduce + scale, for comparison)"""
         seeds = self.my_seeds(all_seeds)
+        if backend == "push" and len(seeds) > 0 and len(seeds) * self.world == len(all_seeds):
+            # replicas of one scene, even split: tracker, fold that pushes the tracked sums to every member, one wait, one local kernel
+            pt = self.r.pathTracingTechnique
+            targets = self.group.push_begin(self.buffer)
+            pt.RenderBatchPush(seeds, targets, 1.0 / float(len(seeds)), stream, 0)
+            self.group.push_finish(1.0 / float(len(all_seeds)), pt.PixelLists(), stream, self.buffer)
+            return
+        if backend == "push":
+            backend = "peer"
         self.image.clear(stream)
         if len(seeds):
             self.r.pathTracingTechnique.RenderBatch(seeds, 0, capi.ACCUM_SUM, stream, 0)

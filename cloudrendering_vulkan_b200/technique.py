@@ -261,6 +261,17 @@ class Group:
         """lists: RenderTechniquePT.PixelLists() of this member's technique; only the tracked pixels cross NVLink"""
         check(lib.crv_group_all_reduce_lists_sum_scale(self.handle, buffer, C.c_float(scale), C.c_float(others_scale), C.byref(lists), _stream(stream)))
 
+    # ---- one-barrier combine: the fold pushes the tracked sums into the members' inboxes ----
+    def push_begin(self, buffer: int = 0) -> "capi.PushTargets":
+        """next picture of `buffer`: where this member's sums go (for RenderTechniquePT.RenderBatchPush)"""
+        t = capi.PushTargets()
+        check(lib.crv_group_push_begin(self.handle, buffer, C.byref(t)))
+        return t
+
+    def push_finish(self, scale: float, lists, stream=0, buffer: int = 0):
+        """waits for the members' sums of the picture begun with push_begin and finishes the tracked pixels locally"""
+        check(lib.crv_group_push_finish(self.handle, buffer, C.c_float(scale), C.byref(lists), _stream(stream)))
+
     def set_timeout_ms(self, ms: int):
         check(lib.crv_group_set_timeout_ms(self.handle, int(ms)))
 
@@ -473,6 +484,13 @@ class RenderTechniquePT(RenderTechnique):
         s = np.ascontiguousarray(seeds, dtype=np.int32)
         check(lib.crv_pt_render_batch(self.handle, s.ctypes.data_as(C.POINTER(C.c_int32)), s.size,
                                       C.c_uint32(first_frame_count), int(accum_mode), _stream(commandBuffer), int(imageIndex)))
+
+    def RenderBatchPush(self, seeds, targets, others_scale: float, commandBuffer=0, imageIndex=0):
+        """CRV_ACCUM_SUM render of a group member whose fold sends the tracked sums to the members' inboxes
+        (targets = Group.push_begin(); the image needs no clear; follow with Group.push_finish)"""
+        s = np.ascontiguousarray(seeds, dtype=np.int32)
+        check(lib.crv_pt_render_batch_push(self.handle, s.ctypes.data_as(C.POINTER(C.c_int32)), s.size, C.byref(targets),
+                                           C.c_float(others_scale), _stream(commandBuffer), int(imageIndex)))
 
     def GetStats(self, stream=0) -> capi.PTStats:
         st = capi.PTStats()

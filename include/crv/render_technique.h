@@ -188,6 +188,17 @@ public:
     {
         Check(crv_group_all_reduce_lists_sum_scale(m_group, buffer, scale, othersScale, &lists, stream));
     }
+    // one-barrier combine: PushBegin() -> RenderTechniquePT::RenderBatchPush(seeds, n, targets, othersScale) -> PushFinish()
+    crv_push_targets PushBegin(uint32_t buffer = 0)
+    {
+        crv_push_targets t{};
+        Check(crv_group_push_begin(m_group, buffer, &t));
+        return t;
+    }
+    void PushFinish(float scale, const crv_pixel_lists& lists, CommandStream stream = nullptr, uint32_t buffer = 0)
+    {
+        Check(crv_group_push_finish(m_group, buffer, scale, &lists, stream));
+    }
     void CheckStatus(CommandStream stream = nullptr) { Check(crv_group_status(m_group, stream)); }
     float LastReduceMs()
     {
@@ -367,6 +378,13 @@ public:
                      unsigned int imageIndex)
     {
         Check(crv_pt_render_batch(m_pt, seeds, n, firstFrameCount, mode, stream, imageIndex));
+    }
+    // the same as a plain sum for a member of a DeviceGroup: the fold sends the tracked pixels' sums to every member's inbox
+    // (targets = DeviceGroup::PushBegin()) and finishes the other pixels; the image needs no clear
+    void RenderBatchPush(const int32_t* seeds, unsigned n, const crv_push_targets& targets, float othersScale, CommandStream stream,
+                         unsigned int imageIndex)
+    {
+        Check(crv_pt_render_batch_push(m_pt, seeds, n, &targets, othersScale, stream, imageIndex));
     }
     crv_pt_stats GetStats(CommandStream stream = nullptr)
     {

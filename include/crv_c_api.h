@@ -200,6 +200,16 @@ typedef struct crv_pixel_lists {
     uint32_t reserved;
 } crv_pixel_lists;
 
+/* Where a group member's sums of one picture go (crv_group_push_begin fills it, crv_pt_render_batch_push consumes it): one
+ * inbox image per member -- inbox[p] lies in member p's memory, mapped into this device's address space -- the word in every
+ * member's flag page that announces this member's sums, and this member's CTA counter. */
+typedef struct crv_push_targets {
+    float*    inbox[16];
+    uint32_t* flag[16];
+    uint32_t* done;
+    uint32_t  nranks, rank, epoch, reserved;
+} crv_push_targets;
+
 typedef struct crv_group_handle {
     uint64_t pid;            /* exporting process: members of one process use `base` directly            */
     int32_t  device;         /* CUDA device ordinal of the member                                        */
@@ -314,6 +324,19 @@ int  crv_group_all_reduce_sum_scale(crv_group* g, uint32_t buffer, float scale, 
  * pixel holds n_mine identical samples and is finished locally as value x others_scale (= scale x n_total / n_mine).  At 1080p
  * the c2 scene moves 2 MB instead of 33 MB per member.  `lists` = crv_pt_pixel_lists of this member's own technique. */
 int  crv_group_all_reduce_lists_sum_scale(crv_group* g, uint32_t buffer, float scale, float others_scale, const crv_pixel_lists* lists, void* stream);
+/* One-barrier combine for replicas of one scene (the fast path of the split; the calls above are the general ones).
+ *     crv_group_push_begin(g, b, &targets)                                        next picture of buffer b: inbox slots + flags
+ *     crv_pt_render_batch_push(pt, my_seeds, n, &targets, others_scale, stream)   tracker + fold: no clear, no private sum image
+ *     crv_group_push_finish(g, b, scale, &lists, stream)                          wait for the members' flags, then one local kernel
+ * The fold stores every tracked pixel's sum into the inbox each member keeps for this member (peer stores over NVLink, under
+ * the kernel) and its last CTA raises this member's flag at every peer; every other pixel is finished by the fold itself in
+ * the group image ((n * sampleBackground) * others_scale).  crv_group_push_finish waits for the peers' flags (stream memory
+ * operations) and runs one kernel on local memory only: tracked pixel = (inbox[0] + inbox[1] + ...) * scale, rank order --
+ * the same bits as crv_group_all_reduce_lists_sum_scale, on every member.  One barrier instead of two, no all-gather, and the
+ * transfer is hidden behind the fold.  Inboxes are double-buffered per image buffer (a member may run one picture ahead of
+ * its peers); all calls concerning one buffer must be ordered on one stream.  Memory: 2 * nranks images per buffer. */
+int  crv_group_push_begin(crv_group* g, uint32_t buffer, crv_push_targets* out);
+int  crv_group_push_finish(crv_group* g, uint32_t buffer, float scale, const crv_pixel_lists* lists, void* stream);
 int  crv_group_set_timeout_ms(crv_group* g, uint32_t ms);
 int  crv_group_status(crv_group* g, void* stream);                                  /* waits for `stream` (with the deadline); CRV_OK or the time-out */
 int  crv_group_last_reduce_ms(crv_group* g, float* ms);                             /* device time of the last reduce call of this member */
@@ -380,6 +403,11 @@ int  crv_pt_render_batch(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t 
                          int accum_mode, void* stream, unsigned image_index);
 /* enable per-path counters (steps/collisions/fetches); costs a few atomics per CTA */
 int  crv_pt_get_stats(crv_pt* pt, crv_pt_stats* out, void* stream);
+/* crv_pt_render_batch in CRV_ACCUM_SUM mode for a group member (see crv_group_push_begin): the image needs no clear; after
+ * the call (in stream order) it holds the final value of every pixel that was not tracked, the tracked pixels' sums are on
+ * their way to the members' inboxes. */
+int  crv_pt_render_batch_push(crv_pt* pt, const int32_t* seeds, unsigned n, const crv_push_targets* targets, float others_scale,
+                              void* stream, unsigned image_index);
 /* the pixel lists of the last render call (see crv_pixel_lists) */
 int  crv_pt_pixel_lists(crv_pt* pt, crv_pixel_lists* out);
 int  crv_pt_reset_stats(crv_pt* pt, void* stream);

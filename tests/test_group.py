@@ -133,6 +133,55 @@ def test_epochs_and_double_buffering(crv):
     _close(ms)
 
 
+@pytest.mark.parametrize("n,distinct", [(1, False), (2, False), (3, False), (4, False), (2, True), (4, True), (8, True)])
+def test_push_combine_equals_lists_combine_bitwise(crv, n, distinct):
+    """crv_group_push_begin / crv_pt_render_batch_push / crv_group_push_finish (one barrier, the fold stores the tracked sums
+    into the members' inboxes, no clear) against crv_group_all_reduce_lists_sum_scale (two barriers around a band reduce): the
+    same arithmetic in the same order, so the same bits, on every member; then pictures back to back without host
+    synchronisation (inbox slots alternate per picture), and a render call that needs several tracker launches."""
+    spp = 16 if n == 8 else 12
+    seeds = crv.msvc_rand_sequence(spp)
+    ms = _members(crv, n, distinct)
+    for ctx, r, split, stream in ms:
+        split.render_picture(seeds, int(stream), "peer")
+    lists_pic = []
+    for ctx, r, split, stream in ms:
+        lists_pic.append(split.image.download(int(stream)).copy())
+        split.group.status(int(stream))
+    for ctx, r, split, stream in ms:
+        split.image.upload(np.full((64, 96, 4), np.nan, np.float32), int(stream))      # the push path must not read the image
+        split.render_picture(seeds, int(stream), "push")
+    for k, (ctx, r, split, stream) in enumerate(ms):
+        got = split.image.download(int(stream)).copy()
+        split.group.status(int(stream))
+        assert np.array_equal(_bits(got), _bits(lists_pic[0])), f"member {k}: push combine differs from the lists combine"
+    ref = _single_gpu_picture(crv, seeds, crv.ACCUM_SUM)
+    err = np.abs(lists_pic[0] - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert err.max() <= 1e-6
+    # five more pictures with different seeds, nobody waits in between; the last one is checked
+    more = crv.msvc_rand_sequence(spp * 6)
+    for k in range(1, 6):
+        for ctx, r, split, stream in ms:
+            split.render_picture(more[spp * k:spp * (k + 1)], int(stream), "push")
+    last = []
+    for ctx, r, split, stream in ms:
+        last.append(split.image.download(int(stream)).copy())
+        split.group.status(int(stream))
+    ref = _single_gpu_picture(crv, more[spp * 5:spp * 6], crv.ACCUM_SUM)
+    for got in last:
+        assert np.array_equal(_bits(got), _bits(last[0]))
+        assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)).max() <= 1e-6
+    # a sample buffer that holds one frame: every render call is spp / n tracker launches, the sums stay in the image until the last
+    for ctx, r, split, stream in ms:
+        r.pathTracingTechnique.SetTuning(sample_buffer_bytes=1)
+        split.render_picture(seeds, int(stream), "push")
+    for ctx, r, split, stream in ms:
+        got = split.image.download(int(stream)).copy()
+        split.group.status(int(stream))
+        assert (np.abs(got - lists_pic[0]) / np.maximum(np.abs(lists_pic[0]), 1e-3)).max() <= 1e-6
+    _close(ms)
+
+
 @pytest.mark.parametrize("n,distinct", [(2, False), (3, False), (1, False), (2, True), (4, True)])
 def test_staging_all_gather(crv, n, distinct):
     """a replicated host array: every member uploads 1/N and pushes it to its peers on the copy engines; two rounds into the
