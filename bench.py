@@ -282,7 +282,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config_dict(wl, args, max(1, args.gpus), wl.spp * (max(1, args.gpus) if args.scaling == "weak" else 1), "cpu", "libm"),
+        "config": _config_dict(wl, args, max(1, args.gpus), wl.spp * (max(1, args.gpus) if args.scaling == "weak" else 1), args.layout, args.math),
+        "reference_arm": {"runs_on": "host cores", "math": "libm, no FMA contraction", "note": "`config` is the product arm's, key for key: the same workload, picture and sample budget"},
         "cpu_baseline": {"value": value, "unit": "Mpath-samples/s", "cores": orc.max_threads(), "kind": kind,
                          "sample": sample, "sv_build_s": sv_s, "reference_shader_value": shader_value, "note": _cpu_note(kind, wl)},
         "e2e": {"value": value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
