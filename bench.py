@@ -327,6 +327,7 @@ def run_ours(args, wl):
     own_image.close()
     img = split.image
     pt = r.pathTracingTechnique
+    pt.SetJobOrder(args.job_order)
     if args.track_threshold or args.ctas_per_sm or args.steps_per_decision or args.sample_buffer_mib:
         pt.SetTuning(ctas_per_sm=args.ctas_per_sm, track_threshold=args.track_threshold,
                      steps_per_decision=args.steps_per_decision, sample_buffer_bytes=args.sample_buffer_mib << 20)
@@ -601,6 +602,7 @@ def run_ours(args, wl):
                 p.r.resultImage.close()
                 p.r.pathTracingTechnique.SetScheduler(args.scheduler)
                 p.r.pathTracingTechnique.SetSkipLevel(args.skip_level)
+                p.r.pathTracingTechnique.SetJobOrder(args.job_order)
             p.img = split.group.image(k)
             p.r.resultImage = p.img
             p.r.pathTracingTechnique.SetFrameReferences([p.img])
@@ -796,6 +798,8 @@ def main():
                     help="how the members' sums are combined in the timed region (A/B; see `combine` in the output line)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--job-order", type=int, default=-1, choices=[-1, 0, 1],
+                    help="crv_pt_set_job_order: 0 frame-major, 1 pixel-major over the sorted hit list, -1 automatic (identical pictures)")
     ap.add_argument("--quick", action="store_true", help="only the timed region (no census / other modes): for profiler passes")
     ap.add_argument("--print-source-sha", action="store_true")
     args = ap.parse_args()

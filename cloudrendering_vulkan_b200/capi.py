@@ -195,6 +195,7 @@ SIGNATURES = {
     "crv_pt_set_scheduler": (C.c_int, [_vp, C.c_int]),
     "crv_pt_set_skip_level": (C.c_int, [_vp, C.c_int]),
     "crv_pt_set_coarse_shift": (C.c_int, [_vp, C.c_int]),
+    "crv_pt_set_job_order": (C.c_int, [_vp, C.c_int]),
     "crv_pt_get_coarse_shift": (C.c_int, [_vp, _P(C.c_int)]),
     "crv_ppm_create": (C.c_int, [_vp, _P(PhotonMapPropertiesPOD), _P(PushConstantsPOD), C.c_float, _P(_vp)]),
     "crv_ppm_set_frame_references": (C.c_int, [_vp, _P(_vp), C.c_uint]),

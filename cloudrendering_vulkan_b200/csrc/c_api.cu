@@ -114,6 +114,14 @@ struct crv_pt {
     size_t hitlist_elems = 0;
     uint32_t* misslist = nullptr;      // pixels whose camera ray misses the box
     float* missdy = nullptr;           // dir.y of those rays
+    // the same list sorted by descending expected work (crv_pt_set_job_order): built on demand, once per classification
+    float* hit_keys = nullptr;
+    uint32_t* hitlist_sorted = nullptr;
+    float* start_sorted = nullptr;
+    uint32_t* sorted_from = nullptr;
+    uint32_t* sort_scratch = nullptr;
+    bool sorted_valid = false;
+    int job_order = -1;                // -1 automatic, 0 frame-major, 1 pixel-major over the sorted list
     // the classification depends on the camera and the cloud box only: kept across render calls while those bytes stand
     // ... and, through the occupied spans, on the cloud image's contents and the skip level
     bool geom_valid = false;
@@ -1306,6 +1314,11 @@ int crv_pt_destroy(crv_pt* pt)
     if (pt->occ_aabb) cudaFree(pt->occ_aabb);
     if (pt->misslist) cudaFree(pt->misslist);
     if (pt->missdy) cudaFree(pt->missdy);
+    if (pt->hit_keys) cudaFree(pt->hit_keys);
+    if (pt->hitlist_sorted) cudaFree(pt->hitlist_sorted);
+    if (pt->start_sorted) cudaFree(pt->start_sorted);
+    if (pt->sorted_from) cudaFree(pt->sorted_from);
+    if (pt->sort_scratch) cudaFree(pt->sort_scratch);
     if (pt->samples) cudaFree(pt->samples);
     if (pt->job_counter) cudaFree(pt->job_counter);
     if (pt->stats) cudaFree(pt->stats);
@@ -1429,6 +1442,14 @@ int crv_pt_set_coarse_shift(crv_pt* pt, int min_shift)
     CRV_REQUIRE(pt != nullptr, "crv_pt_set_coarse_shift: null technique");
     CRV_REQUIRE(min_shift >= -1 && min_shift <= 6, "crv_pt_set_coarse_shift: shift must be -1 (automatic) or 0..6");
     pt->forced_shift = min_shift;
+    return CRV_OK;
+}
+
+int crv_pt_set_job_order(crv_pt* pt, int order)
+{
+    CRV_REQUIRE(pt != nullptr, "crv_pt_set_job_order: null technique");
+    CRV_REQUIRE(order >= -1 && order <= 1, "crv_pt_set_job_order: order must be -1 (automatic), 0 (frame-major) or 1 (pixel-major, sorted)");
+    pt->job_order = order;
     return CRV_OK;
 }
 
@@ -1665,16 +1686,30 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         if (pt->start) CRV_CUDA(cudaFree(pt->start));
         if (pt->misslist) CRV_CUDA(cudaFree(pt->misslist));
         if (pt->missdy) CRV_CUDA(cudaFree(pt->missdy));
+        if (pt->hit_keys) CRV_CUDA(cudaFree(pt->hit_keys));
+        if (pt->hitlist_sorted) CRV_CUDA(cudaFree(pt->hitlist_sorted));
+        if (pt->start_sorted) CRV_CUDA(cudaFree(pt->start_sorted));
+        if (pt->sorted_from) CRV_CUDA(cudaFree(pt->sorted_from));
         pt->hitlist = nullptr;
         pt->start = nullptr;
         pt->misslist = nullptr;
         pt->missdy = nullptr;
+        pt->hit_keys = nullptr;
+        pt->hitlist_sorted = nullptr;
+        pt->start_sorted = nullptr;
+        pt->sorted_from = nullptr;
         pt->hitlist_elems = 0;
         pt->geom_valid = false;
+        pt->sorted_valid = false;
         CRV_CUDA(cudaMalloc(&pt->hitlist, sizeof(uint32_t) * c.npix));
         CRV_CUDA(cudaMalloc(&pt->start, sizeof(float) * 8 * (size_t)c.npix));
         CRV_CUDA(cudaMalloc(&pt->misslist, sizeof(uint32_t) * c.npix));
         CRV_CUDA(cudaMalloc(&pt->missdy, sizeof(float) * c.npix));
+        CRV_CUDA(cudaMalloc(&pt->hit_keys, sizeof(float) * c.npix));
+        CRV_CUDA(cudaMalloc(&pt->hitlist_sorted, sizeof(uint32_t) * c.npix));
+        CRV_CUDA(cudaMalloc(&pt->start_sorted, sizeof(float) * 8 * (size_t)c.npix));
+        CRV_CUDA(cudaMalloc(&pt->sorted_from, sizeof(uint32_t) * c.npix));
+        if (!pt->sort_scratch) CRV_CUDA(cudaMalloc(&pt->sort_scratch, sizeof(uint32_t) * (PT_SORT_BUCKETS + 1)));
         pt->hitlist_elems = c.npix;
     }
     c.hitlist = pt->hitlist;
@@ -1712,8 +1747,9 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
             CRV_CUDA(cudaMemsetAsync(pt->job_counter, 0, sizeof(unsigned int), s));
             if (c.occ_wide)
                 CRV_TRY(crv_launch_occ_aabb(pt->ctx, b.cloud_vol->occ_ext, pt->occ_aabb, c.cb0, c.cext, c.cloud.nx, c.cloud.ny, c.cloud.nz, s));
-            CRV_TRY(crv_launch_classify(pt->ctx, c, pt->hitlist, pt->start, pt->nhit, pt->misslist, pt->missdy, s));
+            CRV_TRY(crv_launch_classify(pt->ctx, c, pt->hitlist, pt->start, pt->nhit, pt->misslist, pt->missdy, pt->hit_keys, s));
             pt->launches++;
+            pt->sorted_valid = false;
             std::memcpy(pt->geom_key, key, sizeof(key));
             pt->geom_valid = true;
             // the counts travel to the host behind the classification; a later render call picks them up if they have arrived
@@ -1749,9 +1785,27 @@ static int pt_render(crv_pt* pt, const int32_t* seeds, unsigned n, uint32_t firs
         pt->samples_bytes = need;
     }
     c.samples = pt->samples;
+    // Job order: with several frames per launch the jobs run pixel-major over the hit list sorted by descending expected
+    // work, so the paths still in flight when the job queue runs dry are the short ones (the tail of the persistent kernel
+    // is what a member of a sample split with few frames per GPU pays for).  Identical samples either way.
+    const bool sorted_jobs = pt->job_order == 1 || (pt->job_order < 0 && per_round >= 4);
+    if (sorted_jobs && !pt->sorted_valid) {
+        const float diag = std::sqrt((c.cext[0] * c.cext[0] + c.cext[1] * c.cext[1]) + c.cext[2] * c.cext[2]);
+        CRV_TRY(crv_launch_sort_hits(pt->ctx, pt->nhit, pt->hit_keys, c.sigma * 3.0f * diag, pt->hitlist, pt->start, pt->hitlist_sorted,
+                                     pt->start_sorted, pt->sorted_from, pt->sort_scratch, s));
+        pt->launches += 3;
+        pt->sorted_valid = true;
+    }
+    c.job_order = sorted_jobs ? 1 : 0;
+    c.hitlist_sorted = pt->hitlist_sorted;
+    c.start_sorted = pt->start_sorted;
+    c.sorted_from = pt->sorted_from;
     for (unsigned f0 = 0; f0 < n; f0 += (unsigned)per_round) {
         const unsigned nf = (n - f0 < per_round) ? (n - f0) : (unsigned)per_round;
         c.nframes = nf;
+        const U32Div dv = make_u32_div(nf);
+        c.div_magic = dv.magic;
+        c.div_shift = dv.shift;
         std::memcpy(c.seeds, seeds + f0, sizeof(int32_t) * nf);
         c.first_frame_count = first_fc + f0;
         CRV_TRY(pt_timed_launch(pt, c, b, s));        // the job counter is zero: reset by the previous fold (or by the classification)

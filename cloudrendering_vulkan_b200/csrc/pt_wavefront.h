@@ -87,6 +87,14 @@ struct PTConst {
     // ---- job description ----
     uint32_t npix;                     // width*height
     uint32_t nframes;                  // frames in this launch
+    // Job order (crv_pt_set_job_order).  0: frame-major, job = frame * nhit + k (the hit list as the classification left it).
+    // 1 (default): pixel-major, job = k * nframes + frame, over a hit list sorted by descending expected path length: all
+    // frames of the longest pixels start first, so what is still in flight when the queue runs dry are short paths.
+    int job_order;
+    uint32_t div_magic, div_shift;             // job / nframes without a division (U32Div below; host: make_u32_div)
+    const uint32_t* hitlist_sorted;            // the sorted copy of hitlist / start (crv_launch_sort_hits) and, per entry, its
+    const float* start_sorted;                 // index in the unsorted list: sample records stay indexed frame * nhit + that,
+    const uint32_t* sorted_from;               // so the fold does not depend on the job order
     int32_t seeds[PT_MAX_FRAMES_PER_LAUNCH];   // pushConstants.seed of every frame of this launch (by value: no staging copy)
     uint32_t first_frame_count;        // pushConstants.frameCount of frame 0 of this launch
     const float* rcp_fc1;              // rcp_fc1[f] = RN(1 / float(first_frame_count + f + 1)) for the frames of this render CALL
@@ -129,7 +137,17 @@ struct FoldConst {
 
 
 int crv_launch_pt(crv_ctx* ctx, const PTConst& c, int cloud_layout, int sv_layout, int ctas_per_sm, cudaStream_t s);
-int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t* hitlist, float* start, uint32_t* counts, uint32_t* misslist, float* missdy, cudaStream_t s);
+int crv_launch_classify(crv_ctx* ctx, const PTConst& c, uint32_t* hitlist, float* start, uint32_t* counts, uint32_t* misslist, float* missdy, float* keys, cudaStream_t s);
+// hit list + start records sorted by descending key (a counting sort over PT_SORT_BUCKETS key ranges; the order inside a
+// range is arbitrary) into (hitlist_out, start_out), from_out[j] = index of entry j in the unsorted list;
+// scratch = PT_SORT_BUCKETS + 1 u32, key_max = an upper bound of the keys
+constexpr int PT_SORT_BUCKETS = 4096;
+int crv_launch_sort_hits(crv_ctx* ctx, const uint32_t* counts, const float* keys, float key_max, const uint32_t* hitlist, const float* start,
+                         uint32_t* hitlist_out, float* start_out, uint32_t* from_out, uint32_t* scratch, cudaStream_t s);
+// unsigned 32-bit division by a launch-uniform divisor d >= 1: magic == 0 (d a power of two): n >> shift; otherwise
+// q = umulhi(n, magic), n / d = (((n - q) >> 1) + q) >> shift  (Granlund-Montgomery, the round-up form that needs no 33rd bit)
+struct U32Div { uint32_t magic, shift; };
+U32Div make_u32_div(uint32_t d);
 int crv_launch_fold(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_fold_push(crv_ctx* ctx, const FoldConst& c, cudaStream_t s);
 int crv_launch_occ_aabb(crv_ctx* ctx, const int* ext6, float* aabb6, const float* b0, const float* extent, int nx, int ny, int nz, cudaStream_t s);

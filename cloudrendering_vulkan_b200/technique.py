@@ -537,6 +537,10 @@ class RenderTechniquePT(RenderTechnique):
         """at least this cell size (8 << shift voxels) for the tracker's coarse threshold table; -1 = automatic"""
         check(lib.crv_pt_set_coarse_shift(self.handle, int(min_shift)))
 
+    def SetJobOrder(self, order: int = -1):
+        """0 frame-major, 1 pixel-major over the hit list sorted by expected work per path, -1 automatic; identical samples"""
+        check(lib.crv_pt_set_job_order(self.handle, int(order)))
+
     def GetCoarseShift(self) -> int:
         v = C.c_int()
         check(lib.crv_pt_get_coarse_shift(self.handle, C.byref(v)))

@@ -406,6 +406,8 @@ public:
     }
     // minimum cell size (8 << shift voxels) of the tracker's coarse threshold table; -1 = automatic
     void SetCoarseShift(int minShift) { Check(crv_pt_set_coarse_shift(m_pt, minShift)); }
+    // job order of a launch: 0 frame-major, 1 pixel-major over the hit list sorted by expected work, -1 automatic; identical results
+    void SetJobOrder(int order) { Check(crv_pt_set_job_order(m_pt, order)); }
     float LastRenderMs(unsigned* launches = nullptr)
     {
         float ms = 0.0f;

@@ -444,6 +444,14 @@ int  crv_pt_set_skip_level(crv_pt* pt, int level);
  * crv_pt_get_coarse_shift: the shift of the tables built by the last render call. */
 int  crv_pt_set_coarse_shift(crv_pt* pt, int min_shift);
 int  crv_pt_get_coarse_shift(crv_pt* pt, int* shift);
+/* In which order the (pixel, frame) jobs of a launch are handed to the tracker (identical samples, bit for bit):
+ *   0  frame-major over the hit list as the classification left it (neighbouring lanes start on neighbouring pixels)
+ *   1  pixel-major over the hit list sorted by descending expected work per path (span length and optical depth of the
+ *      pixel's first segment): all frames of the longest pixels start first, so the paths still in flight when the job
+ *      queue runs dry are short -- the tail of the launch shrinks, which is what a member of a sample split with few
+ *      frames per GPU pays for
+ *  -1  automatic (default): 1 for launches of at least 4 frames, else 0 */
+int  crv_pt_set_job_order(crv_pt* pt, int order);
 /* which persistent-thread scheduler runs the tracker (identical results, bit for bit):
  *   0 = pool  (default) every warp owns 128 paths in shared memory and runs one kind of work at a time on 32 of them
  *   1 = lanes every lane owns one path plus one in reserve (kept for A/B measurements) */

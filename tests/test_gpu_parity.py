@@ -281,6 +281,37 @@ def test_schedulers_are_bit_identical(crv, orc, ctx):
             assert st == stats[0], f"scheduler changed the counters: {st} vs {stats[0]}"
 
 
+@pytest.mark.parametrize("frames", [1, 5, 32, 37])
+def test_job_orders_are_bit_identical(crv, orc, ctx, frames):
+    """crv_pt_set_job_order: frame-major over the classification's hit list, pixel-major over the list sorted by expected
+    work (job / nframes by multiply-shift: a power of two, odd counts, one frame), and the automatic choice -- the order
+    only decides which lane starts which path when: identical image bits and counters, in both accumulation modes and
+    both schedulers"""
+    cloud = orc.fbm_generate(40, 99)
+    ref = {}
+    for sched in ["pool", "lanes"]:
+        for order in [0, 1, -1]:
+            r, _ = make_scene(crv, orc, ctx, layout="brick", g=0.85, absorption=0.05, cloud=cloud, density_scaling=120.0)
+            pt = r.pathTracingTechnique
+            pt.SetScheduler(sched)
+            pt.SetJobOrder(order)
+            pt.ResetStats()
+            r.render(frames)                                   # running mean, one batch
+            mean = r.resultImage.download().copy()
+            st = pt.GetStats()
+            r.resultImage.clear()
+            pt.RenderBatch(crv.msvc_rand_sequence(frames, 0), 0, crv.ACCUM_SUM)
+            total = r.resultImage.download().copy()
+            r.close()
+            got = (_bits(mean), _bits(total), (st.paths, st.tracking_steps, st.collisions))
+            if not ref:
+                ref = got
+                continue
+            assert np.array_equal(ref[0], got[0]), f"job order {order} / {sched} changed the running-mean image"
+            assert np.array_equal(ref[1], got[1]), f"job order {order} / {sched} changed the sum image"
+            assert ref[2] == got[2], f"job order {order} / {sched} changed the counters: {got[2]} vs {ref[2]}"
+
+
 @pytest.mark.parametrize("g,absorption,ds", [(None, 0.0, 50.0), (0.85, 0.1, 50.0), (0.85, 0.01, 200.0)])
 def test_driver_math_mode_parity(crv, orc, ctx, g, absorption, ds):
     """CRV_PT_MATH_DRIVER (lg2 on the SFU, reciprocal multiply, contracted add for t += -log(zeta)/sigma): the same bars as
