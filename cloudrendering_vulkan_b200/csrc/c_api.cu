@@ -787,13 +787,14 @@ int crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned /*image_index
     c.search_iters = 1;
     while ((1u << c.search_iters) < n + 1u) c.search_iters++;
     c.zrange = sv->zrange;
-    // AUTO: the fused build stores whole 8^3 blocks, which is one contiguous brick of the BRICK layout (0.19 ms vs 0.26 ms
-    // two-pass at 512^3, 1.41 vs 1.81 ms at 1024^3); in the other layouts the two-pass build's row stores do as well or better
-    int mode = sv->mode != CRV_SV_MODE_AUTO ? sv->mode : (sv->out->layout == CRV_LAYOUT_BRICK ? CRV_SV_MODE_FUSED : CRV_SV_MODE_TWO_PASS);
+    // AUTO: the fused builds store whole 8^3 blocks, which is one contiguous brick of the BRICK layout -- warp-owned rows:
+    // 0.124 ms at 512^3, 0.86 ms at 1024^3 (CTA-wide chunks 0.135 / 0.92, two-pass 0.26 / 1.81); in the other layouts the
+    // two-pass build's row stores do as well or better
+    int mode = sv->mode != CRV_SV_MODE_AUTO ? sv->mode : (sv->out->layout == CRV_LAYOUT_BRICK ? CRV_SV_MODE_FUSED_ROWS : CRV_SV_MODE_TWO_PASS);
     if (!crv_sv_fast_path_ok(c)) mode = CRV_SV_MODE_GENERIC;       // preconditions of the fast kernels not met
     sv->last_mode = mode;
     CRV_CUDA(cudaEventRecord(sv->ev0, s));
-    if ((mode == CRV_SV_MODE_FUSED || mode == CRV_SV_MODE_FUSED_V1) && sv->dist_for_vs != c.voxel_size) {       // inside the timed region when it is needed
+    if ((mode == CRV_SV_MODE_FUSED || mode == CRV_SV_MODE_FUSED_V1 || mode == CRV_SV_MODE_FUSED_ROWS) && sv->dist_for_vs != c.voxel_size) {       // inside the timed region when it is needed
         CRV_TRY(crv_launch_sv_dist(sv->ctx, sv->dist_z, c.n, c.voxel_size, s));
         sv->dist_for_vs = c.voxel_size;
     } else if (mode == CRV_SV_MODE_TWO_PASS) {
@@ -811,7 +812,7 @@ int crv_sv_record_draw_commands(crv_sv* sv, void* stream, unsigned /*image_index
 int crv_sv_set_tuning(crv_sv* sv, int mode)
 {
     CRV_REQUIRE(sv != nullptr, "crv_sv_set_tuning: null technique");
-    CRV_REQUIRE(mode >= CRV_SV_MODE_AUTO && mode <= CRV_SV_MODE_FUSED_V1, "crv_sv_set_tuning: unknown mode");
+    CRV_REQUIRE(mode >= CRV_SV_MODE_AUTO && mode <= CRV_SV_MODE_FUSED_ROWS, "crv_sv_set_tuning: unknown mode");
     sv->mode = mode;
     return CRV_OK;
 }

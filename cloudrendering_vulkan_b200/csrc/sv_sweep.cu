@@ -860,6 +860,327 @@ __global__ void __launch_bounds__(512, 3) sv_fused_brick_kernel(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Fused build, brick output, warp-owned rows (SV_MODE_FUSED_ROWS): the chunk classification of sv_fused_brick_kernel with a
+// walk that needs no CTA barrier.  One CTA of 8 warps per bundle; warp w owns the bundle's row y = w (8 columns) and walks it
+// from the bundle's first chunk that may add density to z = N on its own: lane = x + 8 * zz holds the voxel (x, y, 4 h + zz) of
+// half-chunk h, so a warp's store covers four whole 32-byte sectors of the brick, and the running sums of its 8 columns live in
+// registers (the 4 lanes of a column hold the same value).  The shader's serial order is kept by fetching the column's four
+// addends with shuffles and adding them one after the other in every lane of the column.  The chunks in front of the first
+// occupied one are ones for every column of the bundle: whole bricks, one warp each, before the walk.
+// ------------------------------------------------------------------------------------------------------
+#ifndef CRV_SV_ROWS_GROUP
+#define CRV_SV_ROWS_GROUP 4
+#endif
+#ifndef CRV_SV_ROWS_BATCH
+#define CRV_SV_ROWS_BATCH 2        // samples whose texel loads are issued together (0: sample by sample, with the second emptiness proof)
+#endif
+#ifndef CRV_SV_ROWS_CTAS
+#define CRV_SV_ROWS_CTAS 4
+#endif
+template <int CL>
+__global__ void __launch_bounds__(256, CRV_SV_ROWS_CTAS) sv_fused_rows_kernel(const __grid_constant__ SVConst c)
+{
+    constexpr int OL = CRV_LAYOUT_BRICK;
+    constexpr int NW = 8;               // warps per CTA = rows of the bundle
+    constexpr int MAX_CHUNK_WORDS = SV_MAX_FAST_N / 8 / 32;
+    __shared__ int s_lo, s_hi;
+    __shared__ int s_search[6][64];
+    __shared__ int s_zin[64], s_zend[64];
+    __shared__ uint32_t s_full[MAX_CHUNK_WORDS];      // bit k: chunk k may add density
+    __shared__ int s_clo, s_chi;
+    const int N = c.n;
+    const int t = threadIdx.x;
+    const unsigned lane = t & 31u, warp = t >> 5;
+    const int bx = centre_out(blockIdx.x, gridDim.x), by = centre_out(blockIdx.y, gridDim.y);
+    const int nchunks = (N + 7) >> 3;
+
+    // ---- the z range in which the bundle can touch the box of occupied bricks (as in sv_fused_brick_kernel) ----
+    if (t == 0) { s_lo = N; s_hi = 0; }
+    if (t < MAX_CHUNK_WORDS) s_full[t] = 0u;
+    const bool pre = c.brick_absmax_wide != nullptr;
+    if (t == 0) {
+        float zlo = 0.0f, zhi = (float)N;
+        if (pre) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int nb = a == 0 ? c.cloud.nbx : a == 1 ? c.cloud.nby : c.cloud.nbz;
+                const int e0 = __ldg(c.occ_ext + a), e1 = __ldg(c.occ_ext + 3 + a);
+                if (e1 < e0) { zlo = 1.0f; zhi = 0.0f; break; }                   // nothing occupied anywhere
+                const float base = c.pre_c[a] + (float)(bx * 8) * c.pre_r[a] + (float)(by * 8) * c.pre_u[a];
+                const float er = 7.0f * c.pre_r[a], eu = 7.0f * c.pre_u[a];
+                const float mn = base + fminf(er, 0.0f) + fminf(eu, 0.0f) - 0.25f, mx = base + fmaxf(er, 0.0f) + fmaxf(eu, 0.0f) + 0.25f;
+                const float lo_b = e0 == 0 ? -3.0e38f : (float)e0, hi_b = e1 == nb - 1 ? 3.0e38f : (float)(e1 + 1);
+                const float l = c.pre_l[a];
+                if (l > 0.0f) {
+                    zlo = fmaxf(zlo, (lo_b - mx) / l);
+                    zhi = fminf(zhi, (hi_b - mn) / l);
+                } else if (l < 0.0f) {
+                    zlo = fmaxf(zlo, (hi_b - mn) / l);
+                    zhi = fminf(zhi, (lo_b - mx) / l);
+                } else if (mx < lo_b || mn >= hi_b) {
+                    zlo = 1.0f; zhi = 0.0f;
+                }
+            }
+        }
+        const bool none = !(zlo <= zhi);
+        s_clo = none ? N : max((int)floorf(fmaxf(zlo, 0.0f)) - 8, 0) & ~7;
+        s_chi = none ? 0 : min((int)ceilf(fminf(zhi, (float)N)) + 8, N);
+    }
+    __syncthreads();
+    // ---- classification of the chunks in that range: one warp per chunk ----
+    for (int k = (s_clo >> 3) + (int)warp; k * 8 < s_chi; k += NW) {
+        bool occupied = !pre;
+        if (pre) {
+            int b0i[3], cnt[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v0 = c.pre_c[a] + (float)(bx * 8) * c.pre_r[a] + (float)(by * 8) * c.pre_u[a] + (float)(k * 8) * c.pre_l[a];
+                const float er = 7.0f * c.pre_r[a], eu = 7.0f * c.pre_u[a], el = 7.0f * c.pre_l[a];
+                const float vmin = v0 + fminf(er, 0.0f) + fminf(eu, 0.0f) + fminf(el, 0.0f) - 0.01f;
+                const float vmax = v0 + fmaxf(er, 0.0f) + fmaxf(eu, 0.0f) + fmaxf(el, 0.0f) + 0.01f;
+                const int nb = a == 0 ? c.cloud.nbx : a == 1 ? c.cloud.nby : c.cloud.nbz;
+                const int i0 = min(max(__float2int_rd(vmin), 0), nb - 1), i1 = min(max(__float2int_rd(vmax), 0), nb - 1);
+                b0i[a] = i0;
+                cnt[a] = i1 - i0 + 1;
+            }
+            const int ix = (int)(lane & 3u), iy = (int)((lane >> 2) & 3u);
+            bool mine = false;
+            if (ix < cnt[0] && iy < cnt[1]) {
+                const unsigned row = (unsigned)(b0i[1] + iy) * c.cloud.nbx + (unsigned)(b0i[0] + ix);
+                const unsigned slab = (unsigned)c.cloud.nby * c.cloud.nbx;
+                for (int iz = (int)(lane >> 4); iz < cnt[2]; iz += 2)
+                    mine = mine || !(__ldg(c.brick_absmax_wide + ((unsigned)(b0i[2] + iz) * slab + row)) == 0.0f);
+            }
+            occupied = __any_sync(0xffffffffu, mine) || cnt[0] > 4 || cnt[1] > 4;
+        }
+        if (occupied && lane == 0) atomicOr(&s_full[k >> 5], 1u << (k & 31));
+    }
+    __syncthreads();
+    bool any_full = false;
+#pragma unroll
+    for (int w = 0; w < MAX_CHUNK_WORDS; ++w) any_full = any_full || s_full[w] != 0u;
+
+    // ---- [z_in, z_end) of the bundle's 64 columns (6 searches per column) ----
+    if (any_full) {
+        for (int i = t; i < 384; i += 256) {
+            const int col = i & 63, search = i >> 6;
+            const int cx = bx * 8 + (col & 7), cy = by * 8 + (col >> 3);
+            const int ax = search >> 1;
+            const float a_ax = (float)cx * c.right[ax] + (float)cy * c.up[ax];
+            s_search[search][col] = range_seek(c, a_ax, ax, (search & 1) != 0);
+        }
+        __syncthreads();
+        if (t < 64) {
+            const int cx = bx * 8 + (t & 7), cy = by * 8 + (t >> 3);
+            int z_in = max(max(s_search[0][t], s_search[2][t]), s_search[4][t]);
+            int z_end = min(min(s_search[1][t], s_search[3][t]), s_search[5][t]);
+            if (z_end < z_in) z_end = z_in;
+            if (cx >= N || cy >= N) z_in = z_end = 0;
+            s_zin[t] = z_in;
+            s_zend[t] = z_end;
+            if (z_in < z_end) {
+                atomicMin(&s_lo, z_in);
+                atomicMax(&s_hi, z_end);
+            }
+        }
+        __syncthreads();
+        const int hi = s_hi, lo = hi > 0 ? (s_lo & ~7) : N;
+        if (t < MAX_CHUNK_WORDS) {              // keep the chunks [lo / 8, ceil(hi / 8))
+            const int first = lo >> 3, last = (hi + 7) >> 3, w0 = t * 32;
+            uint32_t keep = 0u;
+            for (int bit = 0; bit < 32; ++bit) if (w0 + bit >= first && w0 + bit < last) keep |= 1u << bit;
+            s_full[t] &= keep;
+        }
+    } else if (t < 64) {
+        s_zin[t] = 0;
+        s_zend[t] = 0;
+    }
+    __syncthreads();
+
+    // ---- the chunks in front of the first one that may add density: ones in every column ----
+    int first_full = nchunks;
+#pragma unroll
+    for (int w = MAX_CHUNK_WORDS - 1; w >= 0; --w)
+        if (s_full[w] != 0u) first_full = w * 32 + __ffs(s_full[w]) - 1;
+    first_full = min(first_full, nchunks);
+    const int lx = (int)(lane & 7u), zz = (int)(lane >> 3);
+    const int x = bx * 8 + lx, y = by * 8 + (int)warp;
+    const bool inb = x < N && y < N;
+    const bool whole_bundle = bx * 8 + 8 <= N && by * 8 + 8 <= N;
+    const unsigned chunk_step = VolAcc<OL>::off_z(c.out, 8);
+    // this lane's voxel of half-chunk 0 of chunk 0; half-chunk 1 lies 4 slices (4 * 64 elements of the brick) further
+    float* const vox0 = const_cast<float*>(c.out.data) + (VolAcc<OL>::off_x(c.out, x) + VolAcc<OL>::off_y(c.out, y) + VolAcc<OL>::off_z(c.out, zz));
+    float* const brick0 = const_cast<float*>(c.out.data) + (VolAcc<OL>::off_x(c.out, bx * 8) + VolAcc<OL>::off_y(c.out, by * 8));
+    constexpr unsigned HALF = 4u * 64u;
+    if (whole_bundle) {
+        const int whole = first_full * 8 <= N ? first_full : first_full - 1;            // the last chunk may be cut by N
+        for (int j = (int)warp; j < whole; j += NW) store_ones_brick(brick0 + (size_t)j * chunk_step, lane);
+        if (whole < first_full) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (whole * 8 + 4 * h + zz < N) __stcs(vox0 + (size_t)whole * chunk_step + h * HALF, 1.0f);
+        }
+    } else {
+        for (int j = 0; j < first_full; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (inb && j * 8 + 4 * h + zz < N) __stcs(vox0 + (size_t)j * chunk_step + h * HALF, 1.0f);
+        }
+    }
+    if (first_full >= nchunks) return;
+
+    // ---- the walk of this warp's row ----
+    const int col = lx + 8 * (int)warp;
+    const int z_in = s_zin[col], z_end = s_zend[col];
+    const float fx = (float)x, fy = (float)y;
+    const float a[3] = {fx * c.right[0] + fy * c.up[0], fx * c.right[1] + fy * c.up[1], fx * c.right[2] + fy * c.up[2]};
+    const float pa[3] = {__fmaf_rn(fy, c.pre_u[0], __fmaf_rn(fx, c.pre_r[0], c.pre_c[0])),
+                         __fmaf_rn(fy, c.pre_u[1], __fmaf_rn(fx, c.pre_r[1], c.pre_c[1])),
+                         __fmaf_rn(fy, c.pre_u[2], __fmaf_rn(fx, c.pre_r[2], c.pre_c[2]))};
+    float acc = 0.0f;                 // accumulatedValue of this lane's column after the previous chunk
+    bool row_any = false;             // warp-uniform: some column of the row has a non-zero sum
+    constexpr int G = CRV_SV_ROWS_GROUP;          // chunks that may add density handled per iteration: 2 G samples per lane in flight
+    // first proof of emptiness for the 2 G samples of a group starting at slice zb0: approximate brick coordinate against the
+    // wide table (one L2 load per sample, all issued together)
+    auto lookup = [&](int zb0, bool (&need)[2 * G], float (&wide)[2 * G]) {
+#pragma unroll
+        for (int u = 0; u < 2 * G; ++u) {
+            const int z = zb0 + 4 * u;
+            need[u] = z >= z_in && z < z_end;
+            wide[u] = 1.0f;
+            if (need[u] && pre) {
+                const float fz = (float)z;
+                const int bi = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[0], pa[0]), 8388608.0f)) - 0x4B000000, 0);
+                const int bj = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[1], pa[1]), 8388608.0f)) - 0x4B000000, 0);
+                const int bk = max(__float_as_int(__fadd_rd(__fmaf_rn(fz, c.pre_l[2], pa[2]), 8388608.0f)) - 0x4B000000, 0);
+                const unsigned b = ((unsigned)min(bk, c.cloud.nbz - 1) * c.cloud.nby + (unsigned)min(bj, c.cloud.nby - 1)) * c.cloud.nbx +
+                                   (unsigned)min(bi, c.cloud.nbx - 1);
+                wide[u] = __ldg(c.brick_absmax_wide + b);
+            }
+        }
+    };
+    int k = first_full;
+    while (k < nchunks) {
+        const bool full = ((s_full[k >> 5] >> (k & 31)) & 1u) != 0u;
+        float* const dst = vox0 + (size_t)k * chunk_step;
+        const int zb = k * 8 + zz;                                   // this lane's slice in half-chunk 0
+        if (!full) {
+            if (!row_any) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (inb && zb + 4 * h < N) __stcs(dst + h * HALF, 1.0f);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int z = zb + 4 * h;
+                    if (z < N) {
+                        const float tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * acc, (float)(z + 1), c_rcp_z[z]));
+                        if (inb) __stcs(dst + h * HALF, tr);
+                    }
+                }
+            }
+            ++k;
+            continue;
+        }
+        // chunks k .. k + G - 1 (an empty one among them just adds zeros): all look-ups, then the samples, then the serial sums
+        float addv[2 * G], wide[2 * G];
+        bool need[2 * G];
+        lookup(zb, need, wide);
+#if CRV_SV_ROWS_BATCH > 0
+        if constexpr (CL != CRV_LAYOUT_TEX3D) {
+            // B samples at a time in three steps -- footprints, all 8 B texel loads, lerps: a lane waits for DRAM once per batch.
+            // The second proof of emptiness (exact footprint against the dilated brick maxima) is left out: the voxels it
+            // would spare after the wide table has passed them read eight zeros and add +-0, the same bits.
+            using A = VolAcc<CL>;
+            constexpr int B = CRV_SV_ROWS_BATCH;
+            static_assert((2 * G) % B == 0, "batches tile the group");
+#pragma unroll
+            for (int h = 0; h < 2 * G; h += B) {
+                unsigned x0[B], x1[B], r00[B], r10[B], r01[B], r11[B];
+                float wa[B], wb[B], wc[B];
+                bool live[B];
+#pragma unroll
+                for (int v = 0; v < B; ++v) {
+                    const int u = h + v;
+                    live[v] = need[u] && !(wide[u] == 0.0f);
+                    x0[v] = x1[v] = r00[v] = r10[v] = r01[v] = r11[v] = 0u;
+                    wa[v] = wb[v] = wc[v] = 0.0f;
+                    if (live[v]) {
+                        const float fz = (float)(zb + 4 * u);
+                        const float px = c.b0[0] + ((a[0] + fz * c.light[0]) * c.voxel_size);
+                        const float py = c.b0[1] + ((a[1] + fz * c.light[1]) * c.voxel_size);
+                        const float pz = c.b0[2] + ((a[2] + fz * c.light[2]) * c.voxel_size);
+                        const float sx = div_rn_by(px - c.cb0[0], c.cext[0], c.rcext[0]);
+                        const float sy = div_rn_by(py - c.cb0[1], c.cext[1], c.rcext[1]);
+                        const float sz = div_rn_by(pz - c.cb0[2], c.cext[2], c.rcext[2]);
+                        const Footprint f = make_footprint<true>(c.cloud, sx, sy, sz);
+                        x0[v] = A::off_x(c.cloud, f.i0);
+                        x1[v] = A::off_x(c.cloud, f.i1);
+                        const unsigned y0 = A::off_y(c.cloud, f.j0), y1 = A::off_y(c.cloud, f.j1);
+                        const unsigned q0 = A::off_z(c.cloud, f.k0), q1 = A::off_z(c.cloud, f.k1);
+                        r00[v] = y0 + q0; r10[v] = y1 + q0; r01[v] = y0 + q1; r11[v] = y1 + q1;
+                        wa[v] = f.a; wb[v] = f.b; wc[v] = f.c;
+                    }
+                }
+                float tx[B][8];
+#pragma unroll
+                for (int v = 0; v < B; ++v) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) tx[v][j] = 0.0f;
+                    if (live[v]) {
+                        const float* d = c.cloud.data;
+                        tx[v][0] = __ldg(d + (r00[v] + x0[v])); tx[v][1] = __ldg(d + (r00[v] + x1[v]));
+                        tx[v][2] = __ldg(d + (r10[v] + x0[v])); tx[v][3] = __ldg(d + (r10[v] + x1[v]));
+                        tx[v][4] = __ldg(d + (r01[v] + x0[v])); tx[v][5] = __ldg(d + (r01[v] + x1[v]));
+                        tx[v][6] = __ldg(d + (r11[v] + x0[v])); tx[v][7] = __ldg(d + (r11[v] + x1[v]));
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < B; ++v) {
+                    const int u = h + v;
+                    addv[u] = 0.0f;
+                    if (live[v]) {
+                        Footprint f;
+                        f.a = wa[v]; f.b = wb[v]; f.c = wc[v];
+                        const float val = trilerp(f, tx[v][0], tx[v][1], tx[v][2], tx[v][3], tx[v][4], tx[v][5], tx[v][6], tx[v][7]);
+                        addv[u] = div_rn_by(val * c.density_scaling, c.base_scaling, c.rbase);
+                    }
+                }
+            }
+        } else
+#endif
+        {
+#pragma unroll
+            for (int u = 0; u < 2 * G; ++u) {
+                addv[u] = 0.0f;       // + 0 outside the interval / in empty bricks leaves the sum unchanged (it is never -0)
+                if (need[u] && !(wide[u] == 0.0f))
+                    addv[u] = div_rn_by(column_sample<CL, true>(c, a, zb + 4 * u) * c.density_scaling, c.base_scaling, c.rbase);
+            }
+        }
+        // accumulatedValue after each slice, in the shader's order (:89): the addend of slice 4 u + j of this lane's column sits
+        // in lane lx + 8 j
+        float mine[2 * G];
+#pragma unroll
+        for (int u = 0; u < 2 * G; ++u) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc = acc + __shfl_sync(0xffffffffu, addv[u], lx + 8 * j);
+                if (j == zz) mine[u] = acc;
+            }
+        }
+        row_any = row_any || __any_sync(0xffffffffu, acc != 0.0f);
+#pragma unroll
+        for (int u = 0; u < 2 * G; ++u) {
+            const int z = zb + 4 * u;
+            float tr = 1.0f;
+            if (row_any && z < N) tr = expf(div_rn_by((-__ldg(c.dist_z + z)) * mine[u], (float)(z + 1), c_rcp_z[z]));
+            if (inb && z < N) __stcs(dst + (size_t)(u >> 1) * chunk_step + (u & 1) * HALF, tr);
+        }
+        k += G;
+    }
+}
+
 template <int CL, int OL>
 void launch_sv(const SVConst& c, int mode, int* launches, cudaStream_t s)
 {
@@ -868,7 +1189,12 @@ void launch_sv(const SVConst& c, int mode, int* launches, cudaStream_t s)
         *launches = 1;
         return;
     }
-    if (mode == SV_MODE_FUSED || mode == SV_MODE_FUSED_V1) {
+    if (mode == SV_MODE_FUSED_ROWS && OL == CRV_LAYOUT_BRICK) {
+        sv_fused_rows_kernel<CL><<<dim3((c.n + 7) / 8, (c.n + 7) / 8, 1), 256, 0, s>>>(c);
+        *launches = 1;
+        return;
+    }
+    if (mode == SV_MODE_FUSED || mode == SV_MODE_FUSED_V1 || mode == SV_MODE_FUSED_ROWS) {
         sv_fused_kernel<CL, OL><<<dim3((c.n + 7) / 8, (c.n + 7) / 8, 1), 512, 0, s>>>(c);
         *launches = 1;
         return;

@@ -36,7 +36,7 @@ int crv_sv_init_tables(crv_ctx* ctx);
 bool crv_sv_fast_path_ok(const SVConst& c);
 
 // crv_sv_mode of crv_c_api.h (AUTO is resolved by the caller)
-enum { SV_MODE_GENERIC = 1, SV_MODE_SINGLE_PASS = 2, SV_MODE_TWO_PASS = 3, SV_MODE_FUSED = 4, SV_MODE_FUSED_V1 = 5 };
+enum { SV_MODE_GENERIC = 1, SV_MODE_SINGLE_PASS = 2, SV_MODE_TWO_PASS = 3, SV_MODE_FUSED = 4, SV_MODE_FUSED_V1 = 5, SV_MODE_FUSED_ROWS = 6 };
 // dist_z[z] = accumulatedDistance after slice z (the shader's repeated fp32 addition), for the fused build
 int crv_launch_sv_dist(crv_ctx* ctx, float* dist_z, int n, float voxel_size, cudaStream_t s);
 int crv_launch_sv_sweep(crv_ctx* ctx, const SVConst& c, int cloud_layout, int out_layout, int mode, cudaStream_t s);

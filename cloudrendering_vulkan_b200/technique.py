@@ -402,7 +402,7 @@ class RenderTechniqueSV(RenderTechnique):
         check(lib.crv_sv_last_build_ms(self.handle, C.byref(ms)))
         return ms.value
 
-    SV_MODES = {"auto": 0, "generic": 1, "single_pass": 2, "two_pass": 3, "fused": 4, "fused_v1": 5}
+    SV_MODES = {"auto": 0, "generic": 1, "single_pass": 2, "two_pass": 3, "fused": 4, "fused_v1": 5, "fused_rows": 6}
 
     def SetTuning(self, mode="auto"):
         """which kernels build the volume (crv_sv_mode); every mode produces the same bits"""

@@ -173,9 +173,11 @@ typedef enum crv_sv_mode {
     CRV_SV_MODE_GENERIC     = 1,   /* one thread per column, AABB test + sample per voxel: ShadowVolume.comp literally */
     CRV_SV_MODE_SINGLE_PASS = 2,   /* per-column z-interval by bisection + exact FMA division, still one kernel        */
     CRV_SV_MODE_TWO_PASS    = 3,   /* parallel gather of the in-AABB addends, then a streaming per-column scan         */
-    CRV_SV_MODE_FUSED       = 4,   /* default: one CTA per 8x8 column bundle; brick output: chunks classified against the cloud's
-                                      brick maxima, all-ones bricks stored whole, gather + serial sums + exp only where density is */
-    CRV_SV_MODE_FUSED_V1    = 5    /* the fused build without the chunk classification (per-voxel pre-test), kept for A/B       */
+    CRV_SV_MODE_FUSED       = 4,   /* one CTA per 8x8 column bundle; brick output: chunks classified against the cloud's brick maxima,
+                                      all-ones bricks stored whole, gather + serial sums (shared memory, two barriers) + exp where density is */
+    CRV_SV_MODE_FUSED_V1    = 5,   /* the fused build without the chunk classification (per-voxel pre-test), kept for A/B       */
+    CRV_SV_MODE_FUSED_ROWS  = 6    /* default for brick output: the same classification, every warp walks one row of the bundle on its
+                                      own -- serial sums through shuffles, no CTA barrier, texel loads of two samples issued together */
 } crv_sv_mode;
 
 typedef struct crv_ctx    crv_ctx;      /* one per GPU  (~ VulkanDevice)                       */

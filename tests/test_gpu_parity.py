@@ -126,15 +126,15 @@ def test_shadow_volume_modes_bit_identical(crv, orc, ctx, layout):
         vs = (0.01, 0.02, 0.03) if kind == "rand" else (1.0 / shape[0],) * 3
         r.set_cloud_host(cloud, shape, vs)
         sv = r.shadowVolumeTechnique
-        assert sv.last_build_mode() == ("fused" if layout == "brick" else "two_pass")     # what AUTO resolves to
+        assert sv.last_build_mode() == ("fused_rows" if layout == "brick" else "two_pass")     # what AUTO resolves to
         out = {}
-        for mode in ["generic", "single_pass", "two_pass", "fused", "fused_v1"]:
+        for mode in ["generic", "single_pass", "two_pass", "fused", "fused_v1", "fused_rows"]:
             sv.SetTuning(mode)
             r.shadowVolumeImage.upload(np.full(nsv ** 3, -7.0, np.float32))     # poison: every voxel must be rewritten
             r.UpdateShadowVolume()
             assert sv.last_build_mode() == mode
             out[mode] = r.shadowVolumeImage.download()
-        for mode in ["single_pass", "two_pass", "fused", "fused_v1"]:
+        for mode in ["single_pass", "two_pass", "fused", "fused_v1", "fused_rows"]:
             assert np.array_equal(_bits(out[mode]), _bits(out["generic"])), f"{mode} differs from the literal kernel ({shape}, {light}, N={nsv})"
         _sv_check(out["generic"], orc.shadow_volume(cloud, r.cloudProperties, r.shadowVolumeProperties))
         r.close()

@@ -217,7 +217,7 @@ def live(path, source_sha, config):
         elif r[ni] == "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed":
             d["dram_throughput_pct"] = v
     kernels = {}
-    for fam in ("pt_wavefront_kernel", "sv_fused_kernel", "fold_kernel", "group_reduce_kernel", "group_scale_kernel", "pt_classify_kernel"):
+    for fam in ("pt_wavefront_kernel", "sv_fused", "fold_kernel", "group_reduce_kernel", "group_scale_kernel", "pt_classify_kernel"):
         ids = [i for i, d in by_id.items() if fam in d["kernel"]]
         if ids:
             d = dict(by_id[ids[-1]])

@@ -20,7 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="512:512,1024:1024,500:128")
     ap.add_argument("--layout", default="linear")
-    ap.add_argument("--mode", default="auto", choices=["auto", "generic", "single_pass", "two_pass", "fused", "fused_v1"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "generic", "single_pass", "two_pass", "fused", "fused_v1", "fused_rows"])
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--light", default="1,-1,0")
     ap.add_argument("--zero", action="store_true", help="an empty cloud: the build degenerates to storing ones (its floor)")
