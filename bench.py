@@ -650,7 +650,7 @@ def run_ours(args, wl):
         e2e_finish(pipes[0])
         barrier()
         serial_s = time.perf_counter() - t0
-        n_e2e = max(6, args.steps)                                              # pipelined steps in the timed region (the fill is inside)
+        n_e2e = max(16, args.steps)                                             # pipelined steps in the timed region (the fill is inside)
         barrier()
         t0 = time.perf_counter()
         e2e_enqueue(pipes[0])
