@@ -615,13 +615,17 @@ def run_ours(args, wl):
 
         my = frames_for_rank(all_seeds, rank, world)
 
-        def e2e_enqueue(p):
+        def e2e_upload(p):
+            """first half of a step: the density grid leaves host memory (copy engine; at N > 1 the slices then travel GPU to GPU)"""
             if world > 1:
                 split.group.staging_all_gather(p.k, host_grid.data_ptr(), 4 * n_vox, p.s)       # H2D of my slice + peer exchange
                 p.r.cloudImage.upload_device(split.group.staging_ptr(p.k), p.s)                # retile into the brick layout
                 split.group.staging_release(p.k, p.s)
             else:
                 p.r.cloudImage.upload(hg, p.s, wait=False)                                     # H2D: the density grid
+
+        def e2e_render(p):
+            """second half: majorant (read back: SetCloudProperties needs it on the host), tables, shadow volume, picture, combine"""
             p.r.SetCloudProperties((wl.n_cloud,) * 3, (1.0 / wl.n_cloud,) * 3, p.r.cloudImage.majorant(p.s))
             p.r.UpdateCloudData(p.s)                                                           # descriptor updates + shadow-volume rebuild
             if len(my) * world == spp_total and args.combine == "push":      # even split: only the tracked pixels cross between the GPUs, pushed by the fold
@@ -635,6 +639,10 @@ def run_ours(args, wl):
                     split.group.all_reduce_lists_sum_scale(1.0 / spp_total, 1.0 / len(my), p.r.pathTracingTechnique.PixelLists(), p.s, p.k)
                 else:
                     split.group.all_reduce_sum_scale(1.0 / spp_total, p.s, p.k)
+
+        def e2e_enqueue(p):
+            e2e_upload(p)
+            e2e_render(p)
 
         def e2e_finish(p):
             p.img.download(p.s, out=p.hi)                                                      # D2H: the picture (synchronises p.s)
@@ -653,6 +661,8 @@ def run_ours(args, wl):
         n_e2e = max(16, args.steps)                                             # pipelined steps in the timed region (the fill is inside)
         barrier()
         t0 = time.perf_counter()
+        # (enqueueing step i + 1's upload before step i's majorant read-back -- so that the copy engine never idles -- was
+        # measured and serialised the steps instead: 16.9 ms per step at N = 1, profiles/r2t_e2e_reorder.txt)
         e2e_enqueue(pipes[0])
         for i in range(1, n_e2e):
             e2e_enqueue(pipes[i % 2])
