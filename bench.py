@@ -549,7 +549,11 @@ def run_ours(args, wl):
     else:
         prof_info = {"file": None, "bench_source_sha": sha, "stale": True}
     roofline = {"kernel": "pt_wavefront_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "dram": dram, "issue": issue, "ncu": prof_info, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                # which limiter binds, and how close the kernel runs to it (the HBM block above is SURVEY 8d's definition and is
+                # void as a bound for this kernel: see `note`)
+                "binding": "issue" if issue else None, "binding_frac": issue["frac"] if issue else None,
+                "dram": dram, "issue": issue, "ncu": prof_info, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_rank / max(1, k_n), "launches_per_step": k_n,
                 "kernel_ms_per_step": k_ms, "kernel_share_of_step": k_ms / ms_per_step if ms_per_step > 0 else None,
                 "reference_steps_per_path": ref_steps, "reference_collisions_per_path": ref_coll,
